@@ -1,0 +1,128 @@
+/* pffdtd_b200.h -- C ABI of libpffdtd_b200.so, the B200-native replacement for the simulation
+ * step of bsxfun/pffdtd.
+ *
+ * The reference has no plugin/FFI interface; its in-process contract for this path is
+ *     double run_sim(const struct SimData *sd)        c_cuda/gpu_engine.h:665  (CPU: cpu_engine.h:52)
+ * fed by load_sim_data()/scale_input() (c_cuda/fdtd_data.h:99,879) and drained by
+ * rescale_output()/write_outputs() (fdtd_data.h:912,928); the Python twin is
+ * SimEngine.run_steps(nstart,nsteps) (python/fdtd/sim_fdtd.py:529).  The entry points below are
+ * what a binding of that contract would call.  Plain pointers and sizes only; every function
+ * returns 0 on success or a negative PFFDTD_E* code (the reference aborts via assert/exit,
+ * gpu_engine.h:192-200; here the message is kept in pffdtd_last_error()).
+ *
+ * Conventions (all the reference's, SURVEY.md "Index conventions"):
+ *   grid Nx x Ny x Nz, z contiguous, linear index ii = ix*Ny*Nz + iy*Nz + iz;
+ *   outermost layer on every axis is a halo; two pressure grids u1 (state n), u0 (state n-1,
+ *   overwritten with n+1); receivers read u1; sources are added to the new state.
+ *   Step order and arithmetic follow the C CPU engine exactly in both
+ *   precisions, so fp64 AND fp32 results are bit-identical to cpu_engine.h.
+ */
+#ifndef PFFDTD_B200_H
+#define PFFDTD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFFDTD_MMB 12 /* max RLC branches per material   (fdtd_data.h:33 MMb) */
+#define PFFDTD_MNM 64 /* max number of materials         (fdtd_data.h:35 MNm) */
+
+#define PFFDTD_OK 0
+#define PFFDTD_EINVAL (-1)  /* bad argument / inconsistent description */
+#define PFFDTD_ECUDA (-2)   /* CUDA runtime / driver error */
+#define PFFDTD_ENCCL (-3)   /* NCCL error */
+#define PFFDTD_ESTATE (-4)  /* call not valid in the current state */
+
+/* Problem description handed to the engine: the fields of the reference's `struct SimData`
+ * (fdtd_data.h:38-76) after load_sim_data()+scale_input(), for ONE slab of the grid.
+ * Arrays are borrowed for the duration of pffdtd_create() only (copied to the device).
+ * "Real" quantities (a1,a2,sl2,lo2, ssaf_bnl, mat_beta, mat_quads) travel as doubles that
+ * already hold the value rounded to the working precision, so one layout serves fp32 and fp64. */
+typedef struct pffdtd_desc {
+   int32_t struct_size;  /* = sizeof(pffdtd_desc), ABI check */
+   int32_t precision;    /* 1 = fp32, 2 = fp64                      (Makefile -DPRECISION, fdtd_common.h:43-71) */
+   int32_t fcc_flag;     /* 0 Cartesian, 1 FCC checkerboard, 2 FCC folded (fdtd_data.h:162-165) */
+   int32_t Nm;           /* number of materials                       (SimData.Nm) */
+   int64_t Nx, Ny, Nz;   /* slab dims INCLUDING halo planes            (gpuHostData.Nxh, gpu_engine.h:755-760) */
+   int64_t Nb, Nbl, Nba; /* boundary / lossy-boundary / ABC node counts in this slab */
+   int64_t Ns, Nr, Nt;   /* source nodes, receiver nodes (this slab), time steps */
+   double l, l2;         /* Courant number and its square            (SimData.l, l2) */
+   double a1, a2;        /* stencil coefficients                     (fdtd_data.h:186-194) */
+   double sl2, lo2;      /* (1+EPS)*lfac*l2 and l/2 */
+   /* slab placement (gpu_engine.h:532-543, 784-823): global x index of local plane 0, and
+    * whether local plane 0 / Nx-1 is a GLOBAL halo plane (mirror there) or a neighbour's plane */
+   int64_t ix0;
+   int32_t x_lo_edge, x_hi_edge;
+   const int64_t *bn_ixyz;   /* [Nb]  slab-local linear indices, ascending not required */
+   const uint16_t *adj_bn;   /* [Nb]  adjacency bits, bit j = neighbour j reachable (fdtd_data.h:532-538) */
+   const int64_t *bnl_ixyz;  /* [Nbl] */
+   const int8_t *mat_bnl;    /* [Nbl] material id */
+   const double *ssaf_bnl;   /* [Nbl] */
+   const int64_t *bna_ixyz;  /* [Nba] */
+   const int8_t *Q_bna;      /* [Nba] 1 face, 2 edge, 3 corner */
+   const int64_t *in_ixyz;   /* [Ns] */
+   const int64_t *out_ixyz;  /* [Nr] */
+   const double *in_sigs;    /* [Ns*Nt] row per source node, already scale_input()-scaled */
+   const int8_t *Mb;         /* [Nm] branches per material */
+   const double *mat_beta;   /* [Nm] */
+   const double *mat_quads;  /* [Nm*PFFDTD_MMB*4] (b, bd, bDh, bFh) per (material, branch) (fdtd_data.h:79-84) */
+} pffdtd_desc;
+
+typedef struct pffdtd_engine pffdtd_engine; /* opaque */
+
+/* last error message of the calling thread's most recent failing call */
+const char *pffdtd_last_error(void);
+/* library/version string, e.g. "pffdtd_b200 0.1 sm_100a" */
+const char *pffdtd_version(void);
+
+/* Allocate all simulation state on CUDA device `device` and upload the description.
+ * Replaces the allocation half of run_sim (gpu_engine.h:739-974). */
+int pffdtd_create(const pffdtd_desc *desc, int device, pffdtd_engine **out);
+int pffdtd_destroy(pffdtd_engine *e);
+
+/* Multi-GPU (one process per GPU): rank 0 obtains an id, the host shares it, every rank joins.
+ * Neighbour ranks exchange one Ny*Nz plane per side per step (replaces the
+ * cudaMemcpyPeerAsync waves of gpu_engine.h:1086-1126) with ncclSend/ncclRecv, overlapped
+ * with the interior update. */
+int pffdtd_comm_unique_id(void *id128 /* 128 bytes out */);
+int pffdtd_comm_init(pffdtd_engine *e, const void *id128, int rank, int nranks);
+
+/* Options: "air_kernel" (0 generic, 1 tiled/TMA), "use_graph" (0/1), "overlap" (0/1). */
+int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t value);
+/* Counters/timers: "launches", "air_ms" (CUDA-event time of air kernels since reset), "steps". */
+int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out);
+int pffdtd_reset_stats(pffdtd_engine *e);
+
+/* Advance time steps nstart .. nstart+nsteps-1 (the hot loop, gpu_engine.h:993-1170 /
+ * sim_fdtd.py:529).  Asynchronous on the engine's streams; source samples come from the
+ * uploaded in_sigs, receiver samples accumulate on the device. */
+int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps);
+/* One step with HOST buffers: in_samples[Ns] (this step's source samples, NULL = use uploaded
+ * in_sigs) are copied to the device, the step runs, and the step's receiver samples
+ * out_samples[Nr] are copied back; blocks until done (the per-step D2H of gpu_engine.h:1059-1075). */
+int pffdtd_step_host(pffdtd_engine *e, int64_t n, const double *in_samples, double *out_samples);
+/* Block until all queued work is complete. */
+int pffdtd_sync(pffdtd_engine *e);
+
+/* Receiver traces for steps [n0,n1): u_out[nr*(n1-n0) + (n-n0)], device (sorted) receiver order,
+ * widened to double as the reference does (gpu_engine.h:1072). */
+int pffdtd_read_outputs(pffdtd_engine *e, int64_t n0, int64_t n1, double *u_out);
+/* Copy a whole pressure grid to the host in the reference's unpadded layout
+ * (which: 1 = u1 current state, 0 = u0), widened to double.  For energy checks and plots
+ * (sim_fdtd.py:640-658 gather_slice). */
+int pffdtd_read_grid(pffdtd_engine *e, int which, double *out /* Nx*Ny*Nz */);
+/* Overwrite a pressure grid from the host (initial conditions for energy tests). */
+int pffdtd_write_grid(pffdtd_engine *e, int which, const double *in /* Nx*Ny*Nz */);
+/* Boundary ODE state (vh1, gh1: [Nbl*PFFDTD_MMB], reference CPU layout nb*MMb+m) for energy checks. */
+int pffdtd_read_boundary_state(pffdtd_engine *e, double *vh1, double *gh1);
+
+/* Whole-run convenience with the reference's run_sim() shape: create, run Nt steps, write
+ * u_out[Nr*Nt], destroy; returns elapsed seconds of the loop through *elapsed_s. */
+int pffdtd_run_sim(const pffdtd_desc *desc, int device, double *u_out, double *elapsed_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFFDTD_B200_H */
