@@ -1,0 +1,777 @@
+// engine.cu -- libpffdtd_b200.so: the C ABI of include/pffdtd_b200.h over the sm_100a kernels.
+//
+// Replaces run_sim of the reference (c_cuda/gpu_engine.h:665-1255): allocation + upload
+// (:739-974), the host-driven time loop (:993-1170) and the halo exchange (:1086-1126).  Step order
+// and arithmetic follow the reference CPU engine (cpu_engine.h:129-325), see kernels.cuh.
+//
+// One engine = one slab of the grid on one device; one host thread per engine.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <chrono>
+#include <dlfcn.h>
+#include <cuda_runtime.h>
+
+#include "pffdtd_b200.h"
+#include "kernels.cuh"
+#include "air_tma.cuh"
+
+using pf::i64;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+   char buf[1024];
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(buf, sizeof buf, fmt, ap);
+   va_end(ap);
+   g_err = buf;
+   return code;
+}
+#define CU(call)                                                                                           \
+   do {                                                                                                    \
+      cudaError_t err__ = (call);                                                                          \
+      if (err__ != cudaSuccess)                                                                            \
+         return fail(PFFDTD_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(err__)); \
+   } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, bound at run time so that the library loads on hosts without it
+// ------------------------------------------------------------------------------------------------
+struct Nccl {
+   void *lib = nullptr;
+   int (*GetUniqueId)(void *) = nullptr;
+   int (*CommInitRank)(void **, int, /*ncclUniqueId by value*/ struct Id128, int) = nullptr;
+   int (*CommDestroy)(void *) = nullptr;
+   int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+   int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+   int (*GroupStart)() = nullptr;
+   int (*GroupEnd)() = nullptr;
+   const char *(*GetErrorString)(int) = nullptr;
+};
+struct Id128 {
+   char b[128];
+};
+static Nccl g_nccl;
+static int nccl_load() {
+   if (g_nccl.lib) return 0;
+   const char *names[] = {getenv("PFFDTD_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+   void *h = nullptr;
+   for (const char *n : names) {
+      if (n && *n && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+   }
+   if (!h) return fail(PFFDTD_ENCCL, "cannot load libnccl.so.2 (set PFFDTD_NCCL_LIB): %s", dlerror());
+#define SYM(field, name)                                                                      \
+   *(void **)(&g_nccl.field) = dlsym(h, name);                                                \
+   if (!g_nccl.field) return fail(PFFDTD_ENCCL, "libnccl lacks %s", name);
+   SYM(GetUniqueId, "ncclGetUniqueId")
+   SYM(CommInitRank, "ncclCommInitRank")
+   SYM(CommDestroy, "ncclCommDestroy")
+   SYM(Send, "ncclSend")
+   SYM(Recv, "ncclRecv")
+   SYM(GroupStart, "ncclGroupStart")
+   SYM(GroupEnd, "ncclGroupEnd")
+   SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+   g_nccl.lib = h;
+   return 0;
+}
+#define NC(call)                                                                                       \
+   do {                                                                                                \
+      int err__ = (call);                                                                              \
+      if (err__ != 0)                                                                                  \
+         return fail(PFFDTD_ENCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(err__)); \
+   } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------------
+struct EvPair {
+   cudaEvent_t a, b;
+};
+
+struct pffdtd_engine {
+   int device = 0, precision = 0, fcc = 0, Nm = 0, NN = 6;
+   i64 Nx = 0, Ny = 0, Nz = 0, Nzp = 0, Nb = 0, Nbl = 0, Nba = 0, Ns = 0, Nr = 0, Nt = 0;
+   i64 ix0 = 0;
+   int x_lo_edge = 1, x_hi_edge = 1;
+   double l = 0, a1 = 0, a2 = 0, sl2 = 0, lo2 = 0;
+   size_t rs = 4;  // sizeof(Real)
+   pf::Offsets off{};
+   // device memory
+   void *u[2] = {nullptr, nullptr};  // u[cur] = u1 (state n), u[cur^1] = u0
+   int cur = 0;
+   uint32_t *mask = nullptr;
+   i64 *bn = nullptr, *bnl = nullptr, *bna = nullptr, *in = nullptr, *out = nullptr;
+   uint16_t *adj = nullptr;
+   int8_t *mat = nullptr, *Q = nullptr, *Mb = nullptr;
+   void *ssaf = nullptr, *beta = nullptr, *quads = nullptr, *insig = nullptr, *uout = nullptr;
+   void *hist[2] = {nullptr, nullptr}, *u2ba = nullptr, *vh1 = nullptr, *gh1 = nullptr;
+   int serial_src = 0;
+   // prefix/suffix sizes of the sorted node lists that lie in the first/last owned plane (edge work
+   // that must finish before the halo exchange); only valid when `sorted`
+   int sorted = 0;
+   i64 nb_lo = 0, nb_hi = 0, nbl_lo = 0, nbl_hi = 0, nba_lo = 0, nba_hi = 0, ns_lo = 0, ns_hi = 0;
+   // host staging (pinned)
+   void *h_in = nullptr, *h_out = nullptr;
+   // streams / events
+   cudaStream_t s_main = nullptr, s_comm = nullptr;
+   cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_step = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+   // comm
+   void *comm = nullptr;
+   int rank = 0, nranks = 1, comm_pending = 0;
+   // options
+   int air_kernel = 1, overlap = 1, profile_air = 0, manual_halo = 0;
+   // stats
+   i64 steps_done = 0;  // next time index expected by run_steps
+   double launches = 0;
+   std::vector<EvPair> air_ev;
+   size_t air_ev_used = 0;
+   double air_ms = 0;
+   i64 air_timed = 0;
+   pf::AirTma tma;
+   std::vector<void *> allocs;
+};
+
+template <typename T>
+static int dalloc(pffdtd_engine *e, T **p, size_t count, bool zero = true) {
+   size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+   CU(cudaMalloc((void **)p, bytes));
+   e->allocs.push_back((void *)*p);
+   if (zero) CU(cudaMemset(*p, 0, bytes));
+   return 0;
+}
+static int dalloc_bytes(pffdtd_engine *e, void **p, size_t bytes, bool zero = true) {
+   bytes = std::max<size_t>(bytes, 16);
+   CU(cudaMalloc(p, bytes));
+   e->allocs.push_back(*p);
+   if (zero) CU(cudaMemset(*p, 0, bytes));
+   return 0;
+}
+
+// doubles holding Real-rounded values -> Real array on the device
+static int upload_real(pffdtd_engine *e, void **dst, const double *src, size_t n) {
+   if (dalloc_bytes(e, dst, n * e->rs)) return PFFDTD_ECUDA;
+   if (n == 0) return 0;
+   if (e->precision == 2) {
+      CU(cudaMemcpy(*dst, src, n * 8, cudaMemcpyHostToDevice));
+   } else {
+      std::vector<float> tmp(n);
+      for (size_t i = 0; i < n; i++) tmp[i] = (float)src[i];
+      CU(cudaMemcpy(*dst, tmp.data(), n * 4, cudaMemcpyHostToDevice));
+   }
+   return 0;
+}
+
+// reference-layout linear indices -> padded pitch; checks range
+static int upload_idx(pffdtd_engine *e, i64 **dst, const int64_t *src, i64 n, const char *what, bool interior) {
+   if (dalloc(e, dst, (size_t)n, false)) return PFFDTD_ECUDA;
+   if (n == 0) return 0;
+   if (!src) return fail(PFFDTD_EINVAL, "%s is NULL", what);
+   std::vector<i64> tmp((size_t)n);
+   const i64 Npts = e->Nx * e->Ny * e->Nz;
+   for (i64 i = 0; i < n; i++) {
+      const i64 v = src[i];
+      if (v < 0 || v >= Npts) return fail(PFFDTD_EINVAL, "%s[%lld]=%lld outside the grid", what, (long long)i, (long long)v);
+      const i64 row = v / e->Nz, iz = v - row * e->Nz;
+      if (interior) {
+         const i64 ix = row / e->Ny, iy = row - ix * e->Ny;
+         if (ix < 1 || ix > e->Nx - 2 || iy < 1 || iy > e->Ny - 2 || iz < 1 || iz > e->Nz - 2)
+            return fail(PFFDTD_EINVAL, "%s[%lld]=%lld lies on the halo layer", what, (long long)i, (long long)v);
+      }
+      tmp[(size_t)i] = row * e->Nzp + iz;
+   }
+   CU(cudaMemcpy(*dst, tmp.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+   return 0;
+}
+
+template <typename T>
+static int upload_raw(pffdtd_engine *e, T **dst, const T *src, i64 n, const char *what) {
+   if (dalloc(e, dst, (size_t)n, false)) return PFFDTD_ECUDA;
+   if (n == 0) return 0;
+   if (!src) return fail(PFFDTD_EINVAL, "%s is NULL", what);
+   CU(cudaMemcpy(*dst, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice));
+   return 0;
+}
+
+// count of leading entries of a sorted list below `limit`, and of trailing entries >= `from`
+static void edge_counts(const int64_t *a, i64 n, i64 limit, i64 from, i64 *lo, i64 *hi) {
+   *lo = std::lower_bound(a, a + n, limit) - a;
+   *hi = (a + n) - std::lower_bound(a, a + n, from);
+}
+static bool ascending(const int64_t *a, i64 n) {
+   for (i64 i = 1; i < n; i++)
+      if (a[i] <= a[i - 1]) return false;
+   return true;
+}
+
+extern "C" const char *pffdtd_last_error(void) { return g_err.c_str(); }
+extern "C" const char *pffdtd_version(void) { return "pffdtd_b200 0.1 sm_100a"; }
+
+extern "C" int pffdtd_destroy(pffdtd_engine *e) {
+   if (!e) return PFFDTD_OK;
+   cudaSetDevice(e->device);
+   if (e->s_main) cudaStreamSynchronize(e->s_main);
+   if (e->s_comm) cudaStreamSynchronize(e->s_comm);
+   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+   for (void *p : e->allocs) cudaFree(p);
+   if (e->h_in) cudaFreeHost(e->h_in);
+   if (e->h_out) cudaFreeHost(e->h_out);
+   for (auto &p : e->air_ev) {
+      cudaEventDestroy(p.a);
+      cudaEventDestroy(p.b);
+   }
+   if (e->ev_edge) cudaEventDestroy(e->ev_edge);
+   if (e->ev_comm) cudaEventDestroy(e->ev_comm);
+   if (e->ev_step) cudaEventDestroy(e->ev_step);
+   if (e->ev_t0) cudaEventDestroy(e->ev_t0);
+   if (e->ev_t1) cudaEventDestroy(e->ev_t1);
+   if (e->s_main) cudaStreamDestroy(e->s_main);
+   if (e->s_comm) cudaStreamDestroy(e->s_comm);
+   delete e;
+   return PFFDTD_OK;
+}
+
+static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
+   if (d->precision != 1 && d->precision != 2) return fail(PFFDTD_EINVAL, "precision must be 1 or 2");
+   if (d->fcc_flag < 0 || d->fcc_flag > 2) return fail(PFFDTD_EINVAL, "fcc_flag must be 0, 1 or 2");
+   if (d->Nx < 3 || d->Ny < 3 || d->Nz < 3) return fail(PFFDTD_EINVAL, "grid dims must be >= 3");
+   if (d->Nb < 0 || d->Nbl < 0 || d->Nba < 0 || d->Ns < 0 || d->Nr < 0 || d->Nt < 0 || d->Nm < 0 || d->Nm > PFFDTD_MNM)
+      return fail(PFFDTD_EINVAL, "negative count or too many materials");
+   if (d->Nbl > 0 && (!d->Mb || !d->mat_beta || !d->mat_quads || !d->mat_bnl || !d->ssaf_bnl))
+      return fail(PFFDTD_EINVAL, "lossy nodes without material tables");
+   int ndev = 0;
+   CU(cudaGetDeviceCount(&ndev));
+   if (device < 0 || device >= ndev) return fail(PFFDTD_ECUDA, "no CUDA device %d (%d visible)", device, ndev);
+   CU(cudaSetDevice(device));
+   e->device = device;
+   e->precision = d->precision;
+   e->rs = d->precision == 1 ? 4 : 8;
+   e->fcc = d->fcc_flag;
+   e->NN = d->fcc_flag ? 12 : 6;
+   e->Nm = d->Nm;
+   e->Nx = d->Nx, e->Ny = d->Ny, e->Nz = d->Nz;
+   e->Nzp = (d->Nz + 31) / 32 * 32;
+   e->Nb = d->Nb, e->Nbl = d->Nbl, e->Nba = d->Nba, e->Ns = d->Ns, e->Nr = d->Nr, e->Nt = d->Nt;
+   e->ix0 = d->ix0, e->x_lo_edge = d->x_lo_edge, e->x_hi_edge = d->x_hi_edge;
+   e->l = d->l, e->a1 = d->a1, e->a2 = d->a2, e->sl2 = d->sl2, e->lo2 = d->lo2;
+   for (i64 i = 0; i < d->Nbl; i++) {
+      const int k = d->mat_bnl[i];
+      if (k < 0 || k >= d->Nm) return fail(PFFDTD_EINVAL, "mat_bnl[%lld]=%d out of range", (long long)i, k);
+   }
+   for (int k = 0; k < d->Nm; k++)
+      if (d->Mb[k] < 0 || d->Mb[k] > PFFDTD_MMB) return fail(PFFDTD_EINVAL, "Mb[%d]=%d out of range", k, d->Mb[k]);
+
+   const i64 sx = e->Ny * e->Nzp, sy = e->Nzp;
+   if (e->fcc == 0) {
+      const i64 o[6] = {sx, -sx, sy, -sy, 1, -1};
+      for (int j = 0; j < 6; j++) e->off.o[j] = o[j];
+   } else {
+      const i64 o[12] = {sx + sy, -sx - sy, sy + 1, -sy - 1, sx + 1, -sx - 1, sx - sy, -sx + sy, sy - 1, -sy + 1, sx - 1, -sx + 1};
+      for (int j = 0; j < 12; j++) e->off.o[j] = o[j];
+   }
+
+   CU(cudaStreamCreateWithFlags(&e->s_main, cudaStreamNonBlocking));
+   CU(cudaStreamCreateWithFlags(&e->s_comm, cudaStreamNonBlocking));
+   CU(cudaEventCreateWithFlags(&e->ev_edge, cudaEventDisableTiming));
+   CU(cudaEventCreateWithFlags(&e->ev_comm, cudaEventDisableTiming));
+   CU(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
+   CU(cudaEventCreate(&e->ev_t0));
+   CU(cudaEventCreate(&e->ev_t1));
+
+   const size_t npad = (size_t)(e->Nx * e->Ny * e->Nzp);
+   if (dalloc_bytes(e, &e->u[0], npad * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->u[1], npad * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc(e, &e->mask, npad / 32)) return PFFDTD_ECUDA;
+
+   int rc;
+   if ((rc = upload_idx(e, &e->bn, d->bn_ixyz, e->Nb, "bn_ixyz", true))) return rc;
+   if ((rc = upload_idx(e, &e->bnl, d->bnl_ixyz, e->Nbl, "bnl_ixyz", true))) return rc;
+   if ((rc = upload_idx(e, &e->bna, d->bna_ixyz, e->Nba, "bna_ixyz", true))) return rc;
+   if ((rc = upload_idx(e, &e->in, d->in_ixyz, e->Ns, "in_ixyz", true))) return rc;
+   if ((rc = upload_idx(e, &e->out, d->out_ixyz, e->Nr, "out_ixyz", false))) return rc;
+   if ((rc = upload_raw(e, &e->adj, d->adj_bn, e->Nb, "adj_bn"))) return rc;
+   if ((rc = upload_raw(e, &e->mat, d->mat_bnl, e->Nbl, "mat_bnl"))) return rc;
+   if ((rc = upload_raw(e, &e->Q, d->Q_bna, e->Nba, "Q_bna"))) return rc;
+   if ((rc = upload_raw(e, &e->Mb, d->Mb, (i64)e->Nm, "Mb"))) return rc;
+   if ((rc = upload_real(e, &e->ssaf, d->ssaf_bnl, (size_t)e->Nbl))) return rc;
+   if ((rc = upload_real(e, &e->beta, d->mat_beta, (size_t)e->Nm))) return rc;
+   if ((rc = upload_real(e, &e->quads, d->mat_quads, (size_t)e->Nm * PFFDTD_MMB * 4))) return rc;
+
+   // source samples: (Real)in_sigs (cpu_engine.h:312), stored step-major [Nt][Ns]
+   {
+      const size_t n = (size_t)(e->Ns * e->Nt);
+      std::vector<double> t(n);
+      for (i64 s = 0; s < e->Ns; s++)
+         for (i64 k = 0; k < e->Nt; k++) t[(size_t)(k * e->Ns + s)] = d->in_sigs ? d->in_sigs[s * e->Nt + k] : 0.0;
+      if ((rc = upload_real(e, &e->insig, t.data(), n))) return rc;
+   }
+   if (dalloc_bytes(e, &e->uout, (size_t)(e->Nr * std::max<i64>(e->Nt, 1)) * e->rs)) return PFFDTD_ECUDA;
+   for (int k = 0; k < 2; k++)
+      if (dalloc_bytes(e, &e->hist[k], (size_t)e->Nbl * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->u2ba, (size_t)e->Nba * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->vh1, (size_t)e->Nbl * PFFDTD_MMB * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->gh1, (size_t)e->Nbl * PFFDTD_MMB * e->rs)) return PFFDTD_ECUDA;
+   CU(cudaMallocHost(&e->h_in, std::max<size_t>((size_t)e->Ns * 8, 64)));
+   CU(cudaMallocHost(&e->h_out, std::max<size_t>((size_t)e->Nr * 8, 64)));
+
+   // duplicate source nodes keep the reference's serial accumulation order
+   {
+      std::vector<int64_t> t(d->in_ixyz, d->in_ixyz + e->Ns);
+      std::sort(t.begin(), t.end());
+      e->serial_src = std::adjacent_find(t.begin(), t.end()) != t.end();
+   }
+   // edge/interior split for the overlapped halo exchange needs ascending lists (gpu_engine.h:497-513)
+   if (ascending(d->bn_ixyz, e->Nb) && ascending(d->bnl_ixyz, e->Nbl) && ascending(d->bna_ixyz, e->Nba) &&
+       ascending(d->in_ixyz, e->Ns)) {
+      const i64 P = e->Ny * e->Nz;
+      e->sorted = 1;
+      edge_counts(d->bn_ixyz, e->Nb, 2 * P, (e->Nx - 2) * P, &e->nb_lo, &e->nb_hi);
+      edge_counts(d->bnl_ixyz, e->Nbl, 2 * P, (e->Nx - 2) * P, &e->nbl_lo, &e->nbl_hi);
+      edge_counts(d->bna_ixyz, e->Nba, 2 * P, (e->Nx - 2) * P, &e->nba_lo, &e->nba_hi);
+      edge_counts(d->in_ixyz, e->Ns, 2 * P, (e->Nx - 2) * P, &e->ns_lo, &e->ns_hi);
+   }
+
+   // mask
+   {
+      const i64 words = (i64)(npad / 32);
+      pf::k_mask_init<<<(unsigned)((words + 255) / 256), 256, 0, e->s_main>>>(e->mask, e->Nx, e->Ny, e->Nz, e->Nzp, e->fcc, e->ix0);
+      if (e->Nb) pf::k_mask_nodes<<<(unsigned)((e->Nb + 255) / 256), 256, 0, e->s_main>>>(e->mask, e->bn, e->Nb);
+      CU(cudaGetLastError());
+   }
+   if ((rc = pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->u[0], e->u[1]))) {
+      // not fatal: fall back to the generic kernel, remember why
+      e->air_kernel = 0;
+   }
+   CU(cudaStreamSynchronize(e->s_main));
+   return PFFDTD_OK;
+}
+
+extern "C" int pffdtd_create(const pffdtd_desc *desc, int device, pffdtd_engine **out) {
+   if (!desc || !out) return fail(PFFDTD_EINVAL, "NULL argument");
+   if (desc->struct_size != (int32_t)sizeof(pffdtd_desc))
+      return fail(PFFDTD_EINVAL, "pffdtd_desc size mismatch: caller %d, library %d", desc->struct_size, (int)sizeof(pffdtd_desc));
+   pffdtd_engine *e = new pffdtd_engine();
+   int rc = create_impl(desc, device, e);
+   if (rc != PFFDTD_OK) {
+      std::string keep = g_err;
+      pffdtd_destroy(e);
+      g_err = keep;
+      return rc;
+   }
+   *out = e;
+   return PFFDTD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// comm
+// ------------------------------------------------------------------------------------------------
+extern "C" int pffdtd_comm_unique_id(void *id128) {
+   if (!id128) return fail(PFFDTD_EINVAL, "NULL id");
+   if (nccl_load()) return PFFDTD_ENCCL;
+   NC(g_nccl.GetUniqueId(id128));
+   return PFFDTD_OK;
+}
+
+extern "C" int pffdtd_comm_init(pffdtd_engine *e, const void *id128, int rank, int nranks) {
+   if (!e || !id128 || rank < 0 || rank >= nranks) return fail(PFFDTD_EINVAL, "bad comm arguments");
+   if (nccl_load()) return PFFDTD_ENCCL;
+   CU(cudaSetDevice(e->device));
+   if ((rank > 0) == (e->x_lo_edge != 0) || (rank < nranks - 1) == (e->x_hi_edge != 0))
+      return fail(PFFDTD_EINVAL, "slab edges (%d,%d) disagree with rank %d of %d", e->x_lo_edge, e->x_hi_edge, rank, nranks);
+   Id128 id;
+   memcpy(id.b, id128, 128);
+   NC(g_nccl.CommInitRank(&e->comm, nranks, id, rank));
+   e->rank = rank;
+   e->nranks = nranks;
+   return PFFDTD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// options / stats
+// ------------------------------------------------------------------------------------------------
+extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t value) {
+   if (!e || !key) return fail(PFFDTD_EINVAL, "NULL argument");
+   std::string k(key);
+   if (k == "air_kernel") {
+      if (value == 1 && !e->tma.ok) return fail(PFFDTD_ESTATE, "tiled air kernel unavailable: %s", e->tma.why.c_str());
+      if (value < 0 || value > 1) return fail(PFFDTD_EINVAL, "air_kernel must be 0 or 1");
+      e->air_kernel = (int)value;
+   } else if (k == "overlap") {
+      e->overlap = value != 0;
+   } else if (k == "profile_air") {
+      e->profile_air = value != 0;
+   } else if (k == "air_xc") {
+      e->tma.xc = (int)value;
+   } else if (k == "manual_halo") {
+      e->manual_halo = value != 0;
+   } else {
+      return fail(PFFDTD_EINVAL, "unknown option %s", key);
+   }
+   return PFFDTD_OK;
+}
+
+static int drain_air_events(pffdtd_engine *e) {
+   for (size_t i = 0; i < e->air_ev_used; i++) {
+      float ms = 0;
+      CU(cudaEventSynchronize(e->air_ev[i].b));
+      CU(cudaEventElapsedTime(&ms, e->air_ev[i].a, e->air_ev[i].b));
+      e->air_ms += ms;
+      e->air_timed++;
+   }
+   e->air_ev_used = 0;
+   return 0;
+}
+
+extern "C" int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out) {
+   if (!e || !key || !out) return fail(PFFDTD_EINVAL, "NULL argument");
+   std::string k(key);
+   if (k == "launches") *out = e->launches;
+   else if (k == "steps") *out = (double)e->steps_done;
+   else if (k == "air_ms" || k == "air_launches_timed") {
+      CU(cudaSetDevice(e->device));
+      if (drain_air_events(e)) return PFFDTD_ECUDA;
+      *out = k == "air_ms" ? e->air_ms : (double)e->air_timed;
+   } else if (k == "timer_start") {
+      // device-side stopwatch on the engine's own stream (torch.cuda.Event would not see it)
+      CU(cudaSetDevice(e->device));
+      CU(cudaEventRecord(e->ev_t0, e->s_main));
+      *out = 0;
+   } else if (k == "timer_stop_ms") {
+      CU(cudaSetDevice(e->device));
+      if (e->comm_pending) CU(cudaStreamWaitEvent(e->s_main, e->ev_comm, 0));
+      CU(cudaEventRecord(e->ev_t1, e->s_main));
+      CU(cudaEventSynchronize(e->ev_t1));
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1));
+      *out = ms;
+   } else if (k == "air_kernel") *out = e->air_kernel;
+   else if (k == "Nzp") *out = (double)e->Nzp;
+   else return fail(PFFDTD_EINVAL, "unknown stat %s", key);
+   return PFFDTD_OK;
+}
+
+extern "C" int pffdtd_reset_stats(pffdtd_engine *e) {
+   if (!e) return fail(PFFDTD_EINVAL, "NULL engine");
+   CU(cudaSetDevice(e->device));
+   if (drain_air_events(e)) return PFFDTD_ECUDA;
+   e->launches = 0;
+   e->air_ms = 0;
+   e->air_timed = 0;
+   return PFFDTD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one time step
+// ------------------------------------------------------------------------------------------------
+static inline unsigned nblk(i64 n, int b) { return (unsigned)((n + b - 1) / b); }
+
+// a contiguous piece of one step's work: x-planes [xb,xe) and the node-list ranges that live in them
+struct Part {
+   i64 xb, xe, b0, nb, l0, nbl, a0, nba, s0, ns;
+};
+
+template <typename Real>
+struct Step {
+   pffdtd_engine *e;
+   Real *u1, *u0;
+   cudaStream_t s;
+   i64 n;
+
+   // 4. air update of planes [xb, xe)
+   int air(i64 xb, i64 xe) {
+      if (xe <= xb) return 0;
+      const bool timed = e->profile_air;
+      EvPair *ev = nullptr;
+      if (timed) {
+         if (e->air_ev_used == e->air_ev.size()) {
+            if (e->air_ev.size() >= 4096) {
+               if (drain_air_events(e)) return PFFDTD_ECUDA;
+            } else {
+               EvPair p;
+               CU(cudaEventCreate(&p.a));
+               CU(cudaEventCreate(&p.b));
+               e->air_ev.push_back(p);
+            }
+         }
+         ev = &e->air_ev[e->air_ev_used++];
+         CU(cudaEventRecord(ev->a, s));
+      }
+      if (e->air_kernel == 1) {
+         int rc = pf::air_tma_launch<Real>(&e->tma, e->cur, u1, u0, e->mask, xb, xe, (Real)e->a1, (Real)e->a2, s);
+         if (rc) return fail(PFFDTD_ECUDA, "tiled air kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+      } else {
+         dim3 blk(64, 4, 1);
+         dim3 grd(nblk(e->Nzp, 64), nblk(e->Ny, 4), (unsigned)(xe - xb));
+         if (e->fcc)
+            pf::k_air_generic<Real, 12><<<grd, blk, 0, s>>>(u1, u0, e->mask, e->Ny, e->Nzp, xb, (Real)e->a1, (Real)e->a2, e->off);
+         else
+            pf::k_air_generic<Real, 6><<<grd, blk, 0, s>>>(u1, u0, e->mask, e->Ny, e->Nzp, xb, (Real)e->a1, (Real)e->a2, e->off);
+      }
+      e->launches += 1;
+      if (timed) CU(cudaEventRecord(ev->b, s));
+      return 0;
+   }
+   // 4-7 and 9 for one part, in the reference's order: air, ABC, rigid, FD, sources
+   int part(const Part &p) {
+      int rc = air(p.xb, p.xe);
+      if (rc) return rc;
+      if (p.nba > 0) {
+         pf::k_abc<Real><<<nblk(p.nba, 128), 128, 0, s>>>(u0, e->bna, e->Q, (const Real *)e->u2ba, p.a0, p.nba, (Real)e->l);
+         e->launches += 1;
+      }
+      if (p.nb > 0) {
+         if (e->fcc)
+            pf::k_rigid<Real, 12><<<nblk(p.nb, 128), 128, 0, s>>>(u1, u0, e->bn, e->adj, p.b0, p.nb, (Real)e->sl2, (Real)e->a2, e->off);
+         else
+            pf::k_rigid<Real, 6><<<nblk(p.nb, 128), 128, 0, s>>>(u1, u0, e->bn, e->adj, p.b0, p.nb, (Real)e->sl2, (Real)e->a2, e->off);
+         e->launches += 1;
+      }
+      if (p.nbl > 0) {
+         pf::MatTable mt{e->quads, e->beta, e->Mb};
+         pf::k_fd<Real, PFFDTD_MMB><<<nblk(p.nbl, 128), 128, 0, s>>>(u0, e->bnl, e->mat, (const Real *)e->ssaf, (Real *)e->hist[n & 1],
+                                                                    (Real *)e->vh1, (Real *)e->gh1, p.l0, p.nbl, e->Nbl, (Real)e->lo2, mt);
+         e->launches += 1;
+      }
+      if (p.ns > 0) {
+         pf::k_src<Real><<<nblk(p.ns, 128), 128, 0, s>>>(u0, e->in, (const Real *)e->insig + n * e->Ns, p.s0, p.ns, e->serial_src);
+         e->launches += 1;
+      }
+      return 0;
+   }
+};
+
+// exchange of the new state's edge planes (unew = u0 before the swap):
+// plane 1 -> lower neighbour's plane Nx-1, plane Nx-2 -> upper neighbour's plane 0.
+// Replaces the four cudaMemcpyPeerAsync waves of gpu_engine.h:1086-1126.
+static int exchange(pffdtd_engine *e, void *unew, cudaStream_t s) {
+   if (!e->comm) return 0;
+   const size_t pb = (size_t)(e->Ny * e->Nzp) * e->rs;
+   char *g = (char *)unew;
+   NC(g_nccl.GroupStart());
+   if (!e->x_lo_edge) {
+      NC(g_nccl.Send(g + pb, pb, /*ncclInt8*/ 0, e->rank - 1, e->comm, s));
+      NC(g_nccl.Recv(g, pb, 0, e->rank - 1, e->comm, s));
+   }
+   if (!e->x_hi_edge) {
+      NC(g_nccl.Send(g + (size_t)(e->Nx - 2) * pb, pb, 0, e->rank + 1, e->comm, s));
+      NC(g_nccl.Recv(g + (size_t)(e->Nx - 1) * pb, pb, 0, e->rank + 1, e->comm, s));
+   }
+   NC(g_nccl.GroupEnd());
+   return 0;
+}
+
+template <typename Real>
+static int step_impl(pffdtd_engine *e, i64 n) {
+   if (n < 0 || n >= e->Nt) return fail(PFFDTD_EINVAL, "step %lld outside [0,%lld)", (long long)n, (long long)e->Nt);
+   Step<Real> st{e, (Real *)e->u[e->cur], (Real *)e->u[e->cur ^ 1], e->s_main, n};
+   Real *u1 = st.u1, *u0 = st.u0;
+   cudaStream_t s = e->s_main;
+   const i64 Nx = e->Nx, Ny = e->Ny, Nz = e->Nz, Nzp = e->Nzp;
+   int rc;
+
+   // the halo planes of u1 come from the previous step's exchange
+   if (e->comm_pending) {
+      CU(cudaStreamWaitEvent(s, e->ev_comm, 0));
+      e->comm_pending = 0;
+   }
+   // 1. previous-state values at the ABC nodes
+   if (e->Nba) {
+      pf::k_gather<Real><<<nblk(e->Nba, 128), 128, 0, s>>>(u0, e->bna, (Real *)e->u2ba, e->Nba);
+      e->launches += 1;
+   }
+   // 2. folded FCC seam row
+   if (e->fcc == 2) {
+      pf::k_fold_seam<Real><<<dim3(nblk(Nz, 128), (unsigned)Nx), 128, 0, s>>>(u1, Nx, Ny, Nz, Nzp);
+      e->launches += 1;
+   }
+   // 3. halo mirrors z, y, x
+   pf::k_flip_z<Real><<<nblk(Nx * Ny, 128), 128, 0, s>>>(u1, Nx * Ny, Nz, Nzp);
+   pf::k_flip_y<Real><<<dim3(nblk(Nz, 128), (unsigned)Nx), 128, 0, s>>>(u1, Nx, Ny, Nz, Nzp, e->fcc != 2);
+   e->launches += 2;
+   if (e->x_lo_edge || e->x_hi_edge) {
+      pf::k_flip_x<Real><<<dim3(nblk(Nz, 128), (unsigned)Ny), 128, 0, s>>>(u1, Nx, Ny, Nz, Nzp, e->x_lo_edge, e->x_hi_edge);
+      e->launches += 1;
+   }
+   // 8. receivers read the current state
+   if (e->Nr) {
+      pf::k_gather<Real><<<nblk(e->Nr, 128), 128, 0, s>>>(u1, e->out, (Real *)e->uout + n * e->Nr, e->Nr);
+      e->launches += 1;
+   }
+   const bool lo = e->comm && !e->x_lo_edge, hi = e->comm && !e->x_hi_edge;
+   const bool split = (lo || hi) && e->overlap && e->sorted && Nx >= 5;
+   if (split) {
+      // planes the neighbours need first, then the exchange on the comm stream while the interior runs
+      if (lo && (rc = st.part(Part{1, 2, 0, e->nb_lo, 0, e->nbl_lo, 0, e->nba_lo, 0, e->ns_lo}))) return rc;
+      if (hi && (rc = st.part(Part{Nx - 2, Nx - 1, e->Nb - e->nb_hi, e->nb_hi, e->Nbl - e->nbl_hi, e->nbl_hi, e->Nba - e->nba_hi,
+                                   e->nba_hi, e->Ns - e->ns_hi, e->ns_hi})))
+         return rc;
+      CU(cudaGetLastError());
+      CU(cudaEventRecord(e->ev_edge, s));
+      CU(cudaStreamWaitEvent(e->s_comm, e->ev_edge, 0));
+      if ((rc = exchange(e, u0, e->s_comm))) return rc;
+      CU(cudaEventRecord(e->ev_comm, e->s_comm));
+      e->comm_pending = 1;
+      const i64 b0 = lo ? e->nb_lo : 0, b1 = hi ? e->nb_hi : 0, l0 = lo ? e->nbl_lo : 0, l1 = hi ? e->nbl_hi : 0;
+      const i64 a0 = lo ? e->nba_lo : 0, a1 = hi ? e->nba_hi : 0, s0 = lo ? e->ns_lo : 0, s1 = hi ? e->ns_hi : 0;
+      if ((rc = st.part(Part{lo ? 2 : 1, hi ? Nx - 2 : Nx - 1, b0, e->Nb - b0 - b1, l0, e->Nbl - l0 - l1, a0, e->Nba - a0 - a1, s0,
+                             e->Ns - s0 - s1})))
+         return rc;
+      CU(cudaGetLastError());
+   } else {
+      if ((rc = st.part(Part{1, Nx - 1, 0, e->Nb, 0, e->Nbl, 0, e->Nba, 0, e->Ns}))) return rc;
+      CU(cudaGetLastError());
+      if ((rc = exchange(e, u0, s))) return rc;
+   }
+   // 10. swap (the boundary history rotates through hist[n&1])
+   e->cur ^= 1;
+   e->steps_done = n + 1;
+   return PFFDTD_OK;
+}
+
+static int step_any(pffdtd_engine *e, i64 n) { return e->precision == 1 ? step_impl<float>(e, n) : step_impl<double>(e, n); }
+
+extern "C" int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps) {
+   if (!e) return fail(PFFDTD_EINVAL, "NULL engine");
+   if (nsteps < 0 || nstart < 0 || nstart + nsteps > e->Nt)
+      return fail(PFFDTD_EINVAL, "steps [%lld,%lld) outside [0,%lld)", (long long)nstart, (long long)(nstart + nsteps), (long long)e->Nt);
+   if ((!e->x_lo_edge || !e->x_hi_edge) && !e->comm && !e->manual_halo)
+      return fail(PFFDTD_ESTATE, "slab engine without communicator: call pffdtd_comm_init");
+   CU(cudaSetDevice(e->device));
+   for (i64 n = nstart; n < nstart + nsteps; n++) {
+      int rc = step_any(e, n);
+      if (rc) return rc;
+   }
+   return PFFDTD_OK;
+}
+
+extern "C" int pffdtd_sync(pffdtd_engine *e) {
+   if (!e) return fail(PFFDTD_EINVAL, "NULL engine");
+   CU(cudaSetDevice(e->device));
+   CU(cudaStreamSynchronize(e->s_main));
+   CU(cudaStreamSynchronize(e->s_comm));
+   return PFFDTD_OK;
+}
+
+extern "C" int pffdtd_step_host(pffdtd_engine *e, int64_t n, const double *in_samples, double *out_samples) {
+   if (!e) return fail(PFFDTD_EINVAL, "NULL engine");
+   if (n < 0 || n >= e->Nt) return fail(PFFDTD_EINVAL, "step %lld outside [0,%lld)", (long long)n, (long long)e->Nt);
+   if ((!e->x_lo_edge || !e->x_hi_edge) && !e->comm && !e->manual_halo)
+      return fail(PFFDTD_ESTATE, "slab engine without communicator: call pffdtd_comm_init");
+   CU(cudaSetDevice(e->device));
+   if (in_samples && e->Ns) {
+      if (e->precision == 1) for (i64 s = 0; s < e->Ns; s++) ((float *)e->h_in)[s] = (float)in_samples[s];
+      else memcpy(e->h_in, in_samples, (size_t)e->Ns * 8);
+      CU(cudaMemcpyAsync((char *)e->insig + (size_t)(n * e->Ns) * e->rs, e->h_in, (size_t)e->Ns * e->rs, cudaMemcpyHostToDevice, e->s_main));
+   }
+   int rc = step_any(e, n);
+   if (rc) return rc;
+   if (out_samples && e->Nr)
+      CU(cudaMemcpyAsync(e->h_out, (char *)e->uout + (size_t)(n * e->Nr) * e->rs, (size_t)e->Nr * e->rs, cudaMemcpyDeviceToHost, e->s_main));
+   CU(cudaStreamSynchronize(e->s_main));
+   if (out_samples) {
+      if (e->precision == 1) for (i64 r = 0; r < e->Nr; r++) out_samples[r] = (double)((float *)e->h_out)[r];
+      else memcpy(out_samples, e->h_out, (size_t)e->Nr * 8);
+   }
+   return PFFDTD_OK;
+}
+
+extern "C" int pffdtd_read_outputs(pffdtd_engine *e, int64_t n0, int64_t n1, double *u_out) {
+   if (!e || !u_out) return fail(PFFDTD_EINVAL, "NULL argument");
+   if (n0 < 0 || n1 < n0 || n1 > e->Nt) return fail(PFFDTD_EINVAL, "bad step range");
+   CU(cudaSetDevice(e->device));
+   CU(cudaStreamSynchronize(e->s_main));
+   const i64 W = n1 - n0;
+   if (W == 0 || e->Nr == 0) return PFFDTD_OK;
+   std::vector<char> tmp((size_t)(W * e->Nr) * e->rs);
+   CU(cudaMemcpy(tmp.data(), (char *)e->uout + (size_t)(n0 * e->Nr) * e->rs, tmp.size(), cudaMemcpyDeviceToHost));
+   for (i64 k = 0; k < W; k++)
+      for (i64 r = 0; r < e->Nr; r++)
+         u_out[r * W + k] = e->precision == 1 ? (double)((float *)tmp.data())[k * e->Nr + r] : ((double *)tmp.data())[k * e->Nr + r];
+   return PFFDTD_OK;
+}
+
+template <typename Real>
+static int grid_io(pffdtd_engine *e, int which, double *host, bool to_host) {
+   Real *g = (Real *)e->u[which ? e->cur : e->cur ^ 1];
+   const i64 nrows = e->Nx * e->Ny;
+   // through a device staging buffer of one x-plane at a time in the reference layout
+   const i64 rows_per = e->Ny;
+   double *stage = nullptr;
+   CU(cudaMalloc((void **)&stage, (size_t)(rows_per * e->Nz) * 8));
+   int rc = PFFDTD_OK;
+   for (i64 r0 = 0; r0 < nrows && rc == PFFDTD_OK; r0 += rows_per) {
+      dim3 grd(nblk(e->Nz, 128), (unsigned)rows_per, 1);
+      cudaError_t ce;
+      if (to_host) {
+         pf::k_unpad<Real><<<grd, 128, 0, e->s_main>>>(g + r0 * e->Nzp, stage, rows_per, e->Nz, e->Nzp);
+         ce = cudaMemcpyAsync(host + r0 * e->Nz, stage, (size_t)(rows_per * e->Nz) * 8, cudaMemcpyDeviceToHost, e->s_main);
+      } else {
+         ce = cudaMemcpyAsync(stage, host + r0 * e->Nz, (size_t)(rows_per * e->Nz) * 8, cudaMemcpyHostToDevice, e->s_main);
+         pf::k_pad<Real><<<grd, 128, 0, e->s_main>>>(g + r0 * e->Nzp, stage, rows_per, e->Nz, e->Nzp);
+      }
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->s_main);
+      if (ce != cudaSuccess) rc = fail(PFFDTD_ECUDA, "grid transfer: %s", cudaGetErrorString(ce));
+   }
+   cudaFree(stage);
+   return rc;
+}
+
+extern "C" int pffdtd_read_grid(pffdtd_engine *e, int which, double *out) {
+   if (!e || !out) return fail(PFFDTD_EINVAL, "NULL argument");
+   CU(cudaSetDevice(e->device));
+   int rc = pffdtd_sync(e);
+   if (rc) return rc;
+   return e->precision == 1 ? grid_io<float>(e, which, out, true) : grid_io<double>(e, which, out, true);
+}
+
+extern "C" int pffdtd_write_grid(pffdtd_engine *e, int which, const double *in) {
+   if (!e || !in) return fail(PFFDTD_EINVAL, "NULL argument");
+   CU(cudaSetDevice(e->device));
+   int rc = pffdtd_sync(e);
+   if (rc) return rc;
+   return e->precision == 1 ? grid_io<float>(e, which, (double *)in, false) : grid_io<double>(e, which, (double *)in, false);
+}
+
+extern "C" int pffdtd_read_boundary_state(pffdtd_engine *e, double *vh1, double *gh1) {
+   if (!e || !vh1 || !gh1) return fail(PFFDTD_EINVAL, "NULL argument");
+   CU(cudaSetDevice(e->device));
+   int rc = pffdtd_sync(e);
+   if (rc) return rc;
+   const size_t n = (size_t)e->Nbl * PFFDTD_MMB;
+   if (n == 0) return PFFDTD_OK;
+   std::vector<char> tv(n * e->rs), tg(n * e->rs);
+   CU(cudaMemcpy(tv.data(), e->vh1, tv.size(), cudaMemcpyDeviceToHost));
+   CU(cudaMemcpy(tg.data(), e->gh1, tg.size(), cudaMemcpyDeviceToHost));
+   for (i64 i = 0; i < e->Nbl; i++)
+      for (int m = 0; m < PFFDTD_MMB; m++) {
+         const size_t src = (size_t)m * e->Nbl + i, dst = (size_t)i * PFFDTD_MMB + m;
+         vh1[dst] = e->precision == 1 ? (double)((float *)tv.data())[src] : ((double *)tv.data())[src];
+         gh1[dst] = e->precision == 1 ? (double)((float *)tg.data())[src] : ((double *)tg.data())[src];
+      }
+   return PFFDTD_OK;
+}
+
+extern "C" int pffdtd_run_sim(const pffdtd_desc *desc, int device, double *u_out, double *elapsed_s) {
+   if (!desc || !u_out) return fail(PFFDTD_EINVAL, "NULL argument");
+   pffdtd_engine *e = nullptr;
+   int rc = pffdtd_create(desc, device, &e);
+   if (rc) return rc;
+   auto t0 = std::chrono::steady_clock::now();
+   rc = pffdtd_run_steps(e, 0, desc->Nt);
+   if (rc == PFFDTD_OK) rc = pffdtd_sync(e);
+   auto t1 = std::chrono::steady_clock::now();
+   if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+   if (rc == PFFDTD_OK) rc = pffdtd_read_outputs(e, 0, desc->Nt, u_out);
+   std::string keep = g_err;
+   pffdtd_destroy(e);
+   g_err = keep;
+   return rc;
+}

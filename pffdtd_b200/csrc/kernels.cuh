@@ -1,0 +1,272 @@
+// kernels.cuh -- device kernels of the simulation step, everything except the tiled TMA air kernel
+// (air_tma.cuh).  One time step follows the reference C CPU engine (c_cuda/cpu_engine.h:129-325,
+// SURVEY.md App. B) operation for operation: every product and sum below is an explicitly rounded
+// IEEE operation (__fmul_rn/__fadd_rn/... never contract into FMAs), in the reference's order, so fp32
+// and fp64 results are bit-identical to the CPU engine.
+//
+// Device layout: grids are [Nx][Ny][Nzp], z contiguous, Nzp = Nz rounded up to 32 elements so that
+// every row starts on a 128-byte (fp32) / 256-byte (fp64) line and 16-byte vectors / TMA strides are
+// legal.  All node lists are re-linearised to that pitch at create time.  `mask` has one bit per
+// padded node, 32 nodes per word (LSB first, the reference's convention fdtd_data.h:567-572 extended):
+// a set bit means "the air update must not write this node": boundary nodes, the outer halo layer,
+// the z padding and -- for the checkerboard FCC layout (fcc_flag 1) -- the unused odd-parity nodes.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pf {
+
+typedef long long i64;
+
+template <typename Real> struct Ops;
+template <> struct Ops<float> {
+   static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+   static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+   static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+   static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+template <> struct Ops<double> {
+   static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+   static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+   static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+   static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+
+// neighbour offsets in adjacency-bit order (cpu_engine.h:249-254 Cartesian, :273-284 FCC)
+struct Offsets {
+   i64 o[12];
+};
+
+// ------------------------------------------------------------------------------------------------
+// mask construction (create time)
+// ------------------------------------------------------------------------------------------------
+// one thread per 32-node word: halo layer, z padding, odd parity for fcc_flag==1
+__global__ void k_mask_init(uint32_t *mask, i64 Nx, i64 Ny, i64 Nz, i64 Nzp, int fcc_flag, i64 ix0) {
+   const i64 wpr = Nzp >> 5;  // words per row
+   const i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   if (w >= Nx * Ny * wpr) return;
+   const i64 row = w / wpr;
+   const i64 z0 = (w - row * wpr) << 5;
+   const i64 ix = row / Ny, iy = row - ix * Ny;
+   uint32_t bits = 0;
+   const bool edge_row = (ix == 0) || (ix == Nx - 1) || (iy == 0) || (iy == Ny - 1);
+   for (int b = 0; b < 32; b++) {
+      const i64 iz = z0 + b;
+      bool m = edge_row || iz == 0 || iz >= Nz - 1;
+      if (fcc_flag == 1 && ((ix0 + ix + iy + iz) & 1)) m = true;
+      bits |= (m ? 1u : 0u) << b;
+   }
+   mask[w] = bits;
+}
+
+__global__ void k_mask_nodes(uint32_t *mask, const i64 *bn, i64 Nb) {
+   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= Nb) return;
+   const i64 c = bn[i];
+   atomicOr(&mask[c >> 5], 1u << (c & 31));
+}
+
+// ------------------------------------------------------------------------------------------------
+// step 1: u2ba[i] = u0[bna[i]]                                        (cpu_engine.h:131-134)
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void k_gather(const Real *__restrict__ u, const i64 *__restrict__ idx, Real *__restrict__ out, i64 n) {
+   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) out[i] = u[idx[i]];
+}
+
+// ------------------------------------------------------------------------------------------------
+// step 2+3: folded-FCC seam row and halo mirrors                      (cpu_engine.h:135-172)
+// The reference applies z, then y, then x mirrors, each over the FULL face, so edges and corners
+// pick up already-mirrored values.  Three launches in stream order keep exactly that.
+// ------------------------------------------------------------------------------------------------
+// rows (ix,iy): optional seam copy is a separate kernel because it must precede the z mirror of row Ny-1
+template <typename Real>
+__global__ void k_fold_seam(Real *u1, i64 Nx, i64 Ny, i64 Nz, i64 Nzp) {
+   const i64 iz = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   const i64 ix = blockIdx.y;
+   if (iz >= Nz) return;
+   Real *pl = u1 + ix * Ny * Nzp;
+   pl[(Ny - 1) * Nzp + iz] = pl[(Ny - 2) * Nzp + iz];
+}
+
+template <typename Real>
+__global__ void k_flip_z(Real *u1, i64 nrows, i64 Nz, i64 Nzp) {
+   const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   if (r >= nrows) return;
+   Real *row = u1 + r * Nzp;
+   row[0] = row[2];
+   row[Nz - 1] = row[Nz - 3];
+}
+
+template <typename Real>
+__global__ void k_flip_y(Real *u1, i64 Nx, i64 Ny, i64 Nz, i64 Nzp, int do_yend) {
+   const i64 iz = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   const i64 ix = blockIdx.y;
+   if (iz >= Nz) return;
+   Real *pl = u1 + ix * Ny * Nzp;
+   pl[iz] = pl[2 * Nzp + iz];
+   if (do_yend) pl[(Ny - 1) * Nzp + iz] = pl[(Ny - 3) * Nzp + iz];
+}
+
+template <typename Real>
+__global__ void k_flip_x(Real *u1, i64 Nx, i64 Ny, i64 Nz, i64 Nzp, int lo, int hi) {
+   const i64 iz = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   const i64 iy = blockIdx.y;
+   if (iz >= Nz) return;
+   const i64 P = Ny * Nzp, r = iy * Nzp + iz;
+   if (lo) u1[r] = u1[2 * P + r];
+   if (hi) u1[(Nx - 1) * P + r] = u1[(Nx - 3) * P + r];
+}
+
+// ------------------------------------------------------------------------------------------------
+// step 4 (generic air kernel, one thread per node)                    (cpu_engine.h:175-223)
+//   p = a1*u1[c] - u0[c];  p += a2*u1[c+off_j] for j in bit order;  u0[c] = p   unless masked
+// ------------------------------------------------------------------------------------------------
+template <typename Real, int NN>
+__global__ void __launch_bounds__(256) k_air_generic(const Real *__restrict__ u1, Real *__restrict__ u0,
+                                                      const uint32_t *__restrict__ mask, i64 Ny, i64 Nzp, i64 x_begin,
+                                                      Real a1, Real a2, Offsets off) {
+   typedef Ops<Real> O;
+   const i64 iz = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   const i64 iy = (i64)blockIdx.y * blockDim.y + threadIdx.y;
+   const i64 ix = x_begin + blockIdx.z;
+   if (iz >= Nzp || iy >= Ny) return;
+   const i64 c = (ix * Ny + iy) * Nzp + iz;
+   if ((mask[c >> 5] >> (c & 31)) & 1u) return;
+   Real p = O::sub(O::mul(a1, u1[c]), u0[c]);
+#pragma unroll
+   for (int j = 0; j < NN; j++) p = O::add(p, O::mul(a2, u1[c + off.o[j]]));
+   u0[c] = p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// step 5: absorbing shell                                             (cpu_engine.h:225-229)
+//   lQ = l*Q (Real);  u0 = (u0 + lQ*u2ba)/(1.0 + lQ): the literal 1.0 makes the division a DOUBLE
+//   division of a Real numerator in the reference, also when Real is float.
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void k_abc(Real *__restrict__ u0, const i64 *__restrict__ bna, const int8_t *__restrict__ Q,
+                      const Real *__restrict__ u2ba, i64 i0, i64 n, Real l) {
+   typedef Ops<Real> O;
+   const i64 i = i0 + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= i0 + n) return;
+   const Real lQ = O::mul(l, (Real)Q[i]);
+   const i64 ib = bna[i];
+   const Real num = O::add(u0[ib], O::mul(lQ, u2ba[i]));
+   const double den = __dadd_rn(1.0, (double)lQ);
+   u0[ib] = (Real)__ddiv_rn((double)num, den);
+}
+
+// ------------------------------------------------------------------------------------------------
+// step 6: rigid boundary nodes                                        (cpu_engine.h:234-287)
+//   b1 = 2 - sl2*K;  p = b1*u1[c] - u0[c];  p += (b2*(Real)bit_j)*u1[c+off_j]
+// ------------------------------------------------------------------------------------------------
+template <typename Real, int NN>
+__global__ void k_rigid(const Real *__restrict__ u1, Real *__restrict__ u0, const i64 *__restrict__ bn,
+                        const uint16_t *__restrict__ adj_bn, i64 i0, i64 n, Real sl2, Real a2, Offsets off) {
+   typedef Ops<Real> O;
+   const i64 i = i0 + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= i0 + n) return;
+   const i64 c = bn[i];
+   const unsigned adj = adj_bn[i];
+   const Real K = (Real)__popc(adj);
+   const Real b1 = O::sub((Real)2.0, O::mul(sl2, K));
+   Real p = O::sub(O::mul(b1, u1[c]), u0[c]);
+#pragma unroll
+   for (int j = 0; j < NN; j++) {
+      const Real bit = (Real)((adj >> j) & 1u);
+      p = O::add(p, O::mul(O::mul(a2, bit), u1[c + off.o[j]]));
+   }
+   u0[c] = p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// step 7: frequency-dependent (RLC branch) boundary nodes      (cpu_engine.h:290-301, 363-405)
+// State vh1/gh1 is stored branch-major [m][Nbl] so that a warp's accesses coalesce.
+// hist = the node's value two steps back on entry (u2b), this step's value on exit (u0b -> u2b of n+2).
+// ------------------------------------------------------------------------------------------------
+struct MatTable {
+   const void *quads;  // Real [Nm][MMB][4] = b, bd, bDh, bFh
+   const void *beta;   // Real [Nm]
+   const int8_t *Mb;   // [Nm]
+};
+
+template <typename Real, int MMB>
+__global__ void k_fd(Real *__restrict__ u0, const i64 *__restrict__ bnl, const int8_t *__restrict__ mat_bnl,
+                     const Real *__restrict__ ssaf_bnl, Real *__restrict__ hist, Real *__restrict__ vh1,
+                     Real *__restrict__ gh1, i64 i0, i64 n, i64 Nbl, Real lo2, MatTable mt) {
+   typedef Ops<Real> O;
+   const i64 i = i0 + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= i0 + n) return;
+   const Real one = (Real)1.0, two = (Real)2.0;
+   const int k = mat_bnl[i];
+   const Real *q = (const Real *)mt.quads + (i64)k * MMB * 4;
+   const Real beta = ((const Real *)mt.beta)[k];
+   const int Mb = mt.Mb[k];
+   const i64 c = bnl[i];
+   const Real ssaf = ssaf_bnl[i];
+   const Real lo2Kbg = O::mul(O::mul(lo2, ssaf), beta);
+   const Real den = O::add(one, lo2Kbg);
+   const Real fac = O::div(O::mul(O::mul(two, lo2), ssaf), den);
+   const Real u2 = hist[i];
+   Real u = O::div(O::add(u0[c], O::mul(lo2Kbg, u2)), den);
+   Real v1[MMB], g1[MMB];
+#pragma unroll
+   for (int m = 0; m < MMB; m++) {
+      if (m < Mb) {
+         v1[m] = vh1[(i64)m * Nbl + i];
+         g1[m] = gh1[(i64)m * Nbl + i];
+         const Real bDh = q[4 * m + 2], bFh = q[4 * m + 3];
+         u = O::sub(u, O::mul(fac, O::sub(O::mul(O::mul(two, bDh), v1[m]), O::mul(bFh, g1[m]))));
+      }
+   }
+   const Real du = O::sub(u, u2);
+#pragma unroll
+   for (int m = 0; m < MMB; m++) {
+      if (m < Mb) {
+         const Real b = q[4 * m + 0], bd = q[4 * m + 1], bFh = q[4 * m + 3];
+         const Real v0 = O::sub(O::add(O::mul(b, du), O::mul(bd, v1[m])), O::mul(O::mul(two, bFh), g1[m]));
+         gh1[(i64)m * Nbl + i] = O::add(g1[m], O::div(O::add(v0, v1[m]), two));
+         vh1[(i64)m * Nbl + i] = v0;
+      }
+   }
+   hist[i] = u;
+   u0[c] = u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// step 9: sources are added to the NEW state u0 (cpu_engine.h:310-313); step 8, the receivers
+// reading the CURRENT state u1 (cpu_engine.h:304-307), is k_gather.
+// `serial_src` keeps the reference's serial order when two source entries name the same node.
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void k_src(Real *__restrict__ u0, const i64 *__restrict__ in_ixyz, const Real *__restrict__ in_row, i64 s0, i64 ns,
+                      int serial_src) {
+   typedef Ops<Real> O;
+   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   if (serial_src) {
+      if (i == 0)
+         for (i64 s = s0; s < s0 + ns; s++) u0[in_ixyz[s]] = O::add(u0[in_ixyz[s]], in_row[s]);
+   } else if (i < ns) {
+      u0[in_ixyz[s0 + i]] = O::add(u0[in_ixyz[s0 + i]], in_row[s0 + i]);
+   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion for grid read-back / initialisation (reference layout <-> padded, double <-> Real)
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+__global__ void k_unpad(const Real *__restrict__ u, double *__restrict__ out, i64 nrows, i64 Nz, i64 Nzp) {
+   const i64 iz = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   const i64 r = blockIdx.y + (i64)blockIdx.z * gridDim.y;
+   if (iz < Nz && r < nrows) out[r * Nz + iz] = (double)u[r * Nzp + iz];
+}
+template <typename Real>
+__global__ void k_pad(Real *__restrict__ u, const double *__restrict__ in, i64 nrows, i64 Nz, i64 Nzp) {
+   const i64 iz = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   const i64 r = blockIdx.y + (i64)blockIdx.z * gridDim.y;
+   if (iz < Nz && r < nrows) u[r * Nzp + iz] = (Real)in[r * Nz + iz];
+}
+
+}  // namespace pf

@@ -1,0 +1,181 @@
+"""ctypes binding of libpffdtd_b200.so (include/pffdtd_b200.h) -- the only way the Python host reaches
+the GPU.  There is no CPU fallback: if the library or a CUDA device is missing every call raises.
+
+`Engine` wraps one `pffdtd_engine` (one slab of the grid on one device); `build()` compiles the
+library in-tree with nvcc for sm_100a.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from .sim_data import SimData, pffdtd_desc
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libpffdtd_b200.so"
+HEADER = HERE.parent / "include" / "pffdtd_b200.h"
+
+OK, EINVAL, ECUDA, ENCCL, ESTATE = 0, -1, -2, -3, -4
+
+
+class PffdtdError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+def build(force=False, quiet=True):
+    """nvcc -gencode arch=compute_100a,code=sm_100a -> pffdtd_b200/libpffdtd_b200.so"""
+    args = ["make", "-C", str(HERE / "csrc")] + (["-B"] if force else [])
+    r = subprocess.run(args, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libpffdtd_b200.so failed:\n" + r.stdout + r.stderr)
+    if not quiet:
+        print(r.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """load the shared library (building it first if it is not there) and declare the prototypes"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        build()
+    L = C.CDLL(str(LIB_PATH))
+    vp, i64, dp = C.c_void_p, C.c_int64, C.POINTER(C.c_double)
+    L.pffdtd_last_error.restype = C.c_char_p
+    L.pffdtd_version.restype = C.c_char_p
+    L.pffdtd_create.argtypes = [C.POINTER(pffdtd_desc), C.c_int, C.POINTER(vp)]
+    L.pffdtd_destroy.argtypes = [vp]
+    L.pffdtd_comm_unique_id.argtypes = [vp]
+    L.pffdtd_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.pffdtd_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.pffdtd_get_stat.argtypes = [vp, C.c_char_p, dp]
+    L.pffdtd_reset_stats.argtypes = [vp]
+    L.pffdtd_run_steps.argtypes = [vp, i64, i64]
+    L.pffdtd_step_host.argtypes = [vp, i64, vp, vp]
+    L.pffdtd_sync.argtypes = [vp]
+    L.pffdtd_read_outputs.argtypes = [vp, i64, i64, vp]
+    L.pffdtd_read_grid.argtypes = [vp, C.c_int, vp]
+    L.pffdtd_write_grid.argtypes = [vp, C.c_int, vp]
+    L.pffdtd_read_boundary_state.argtypes = [vp, vp, vp]
+    L.pffdtd_run_sim.argtypes = [C.POINTER(pffdtd_desc), C.c_int, vp, dp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != OK:
+        raise PffdtdError(rc, lib().pffdtd_last_error().decode(errors="replace"))
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(lib().pffdtd_comm_unique_id(buf))
+    return buf.raw
+
+
+class Engine:
+    """One slab on one device.  `sd` must already be scaled (`SimData.scale_input`) if the caller wants
+    the reference binaries' behaviour (fdtd_main.c:41-47)."""
+
+    def __init__(self, sd: SimData, device: int = 0):
+        self.sd = sd
+        self.L = lib()
+        self._desc = sd.desc()
+        h = C.c_void_p()
+        _check(self.L.pffdtd_create(C.byref(self._desc), int(device), C.byref(h)))
+        self.h = h
+        self._in = np.zeros(max(sd.Ns, 1), np.float64)
+        self._out = np.zeros(max(sd.Nr, 1), np.float64)
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pffdtd_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration
+    def comm_init(self, uid: bytes, rank: int, nranks: int):
+        buf = C.create_string_buffer(uid, 128)
+        _check(self.L.pffdtd_comm_init(self.h, buf, rank, nranks))
+
+    def set_option(self, key: str, value: int):
+        _check(self.L.pffdtd_set_option(self.h, key.encode(), int(value)))
+
+    def stat(self, key: str) -> float:
+        v = C.c_double()
+        _check(self.L.pffdtd_get_stat(self.h, key.encode(), C.byref(v)))
+        return v.value
+
+    def reset_stats(self):
+        _check(self.L.pffdtd_reset_stats(self.h))
+
+    # -- stepping
+    def run_steps(self, nstart: int, nsteps: int):
+        _check(self.L.pffdtd_run_steps(self.h, int(nstart), int(nsteps)))
+
+    def step_host(self, n: int, in_samples=None):
+        """one step through host buffers: source samples in, this step's receiver samples out"""
+        ip = None
+        if in_samples is not None:
+            self._in[:self.sd.Ns] = in_samples
+            ip = self._in.ctypes.data
+        _check(self.L.pffdtd_step_host(self.h, int(n), ip, self._out.ctypes.data))
+        return self._out[:self.sd.Nr]
+
+    def sync(self):
+        _check(self.L.pffdtd_sync(self.h))
+
+    # -- results
+    def read_outputs(self, n0=0, n1=None):
+        n1 = self.sd.Nt if n1 is None else n1
+        out = np.zeros((self.sd.Nr, n1 - n0), np.float64)
+        _check(self.L.pffdtd_read_outputs(self.h, n0, n1, out.ctypes.data))
+        return out
+
+    def read_grid(self, which=1):
+        g = np.empty(self.sd.Npts, np.float64)
+        _check(self.L.pffdtd_read_grid(self.h, which, g.ctypes.data))
+        return g.reshape(self.sd.Nx, self.sd.Ny, self.sd.Nz)
+
+    def write_grid(self, which, g):
+        g = np.ascontiguousarray(g, np.float64)
+        if g.size != self.sd.Npts:
+            raise ValueError("grid size mismatch")
+        _check(self.L.pffdtd_write_grid(self.h, which, g.ctypes.data))
+
+    def read_boundary_state(self):
+        n = self.sd.Nbl * 12
+        vh1, gh1 = np.zeros(max(n, 1)), np.zeros(max(n, 1))
+        _check(self.L.pffdtd_read_boundary_state(self.h, vh1.ctypes.data, gh1.ctypes.data))
+        return vh1[:n].reshape(-1, 12), gh1[:n].reshape(-1, 12)
+
+
+def run_sim(sd: SimData, device: int = 0):
+    """whole-run convenience with the reference's run_sim() shape -> (u_out [Nr,Nt] sorted order, seconds)"""
+    d = sd.desc()
+    out = np.zeros((sd.Nr, sd.Nt), np.float64)
+    t = C.c_double()
+    _check(lib().pffdtd_run_sim(C.byref(d), int(device), out.ctypes.data, C.byref(t)))
+    return out, t.value

@@ -1,0 +1,183 @@
+"""Host run loop: the drop-in for the reference's simulation step.
+
+Mirrors the reference's two front ends for this path --
+
+* the Python engine ``python3 -m fdtd.sim_fdtd --data_dir D [--nsteps N]`` (python/fdtd/sim_fdtd.py:39-937):
+  same class name, same method sequence (``load_h5_data, setup_mask, allocate_mem, set_coeffs, checks,
+  run_all / run_steps, save_outputs, print_last_samples``) and the same ``--ENGINE:`` log lines;
+* the C binaries' ``main`` (c_cuda/fdtd_main.c:35-59): load -> scale_input -> run_sim -> rescale_output ->
+  write_outputs -> print_last_samples, whose arithmetic (incl. the input scaling) is what the kernels
+  reproduce bit for bit.
+
+It reads the same four ``.h5`` files and writes the same ``sim_outs.h5``, but every
+time step runs in the sm_100a kernels of libpffdtd_b200.so.  Launched under ``torchrun`` with
+WORLD_SIZE > 1 the grid is split into x-slabs, one process per GPU (gpu_engine.h:516-662), and the halo
+planes travel by NCCL send/recv inside the library.
+
+    python -m pffdtd_b200.sim_fdtd --data_dir D [--precision {1,2}] [--nsteps N]
+"""
+from __future__ import annotations
+
+import os
+import time
+from pathlib import Path
+
+import numpy as np
+
+from . import folder_prep
+from .engine import Engine, comm_unique_id
+from .sim_data import SimData
+
+
+def _dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+class SimEngine:
+    def __init__(self, data_dir, energy_on=False, nthreads=None, precision=2, device=None, scale=True, quiet=False):
+        self.data_dir = Path(data_dir)
+        if energy_on:
+            raise NotImplementedError("the energy balance (sim_fdtd.py:587-620) is not part of the GPU step yet")
+        self.precision = int(precision)
+        self.rank, self.world, local = _dist_env()
+        self.device = local if device is None else int(device)
+        self.scale = scale
+        self.quiet = quiet or self.rank != 0
+        self.eng = None
+        self.sd_full = None
+        self.sd = None
+        self.u_out = None
+        self.t_elapsed = 0.0
+        del nthreads  # host threads play no role here; accepted for call compatibility
+
+    def print(self, fstring):
+        if not self.quiet:
+            print(f"--ENGINE: {fstring}", flush=True)
+
+    # ---- the reference's set-up sequence -------------------------------------------------------
+    def load_h5_data(self):
+        self.print("loading data..")
+        sd = SimData.load(self.data_dir, self.precision)
+        if self.scale:
+            sd.scale_input()  # fdtd_data.h:879-909
+        if self.world > 1 or sd.fcc_flag == 2:
+            if not sd.is_sorted():
+                self.print("sorting node lists (the reference needs a sort_sim_data'd folder here)")
+            sd = sd.sorted()
+        self.sd_full = sd
+        self.Nx, self.Ny, self.Nz, self.Nt, self.Nr, self.Ns = sd.Nx, sd.Ny, sd.Nz, sd.Nt, sd.Nr, sd.Ns
+        self.fcc = sd.fcc_flag > 0
+        self.out_reorder = sd.out_reorder
+        self.print(f"Nx={sd.Nx} Ny={sd.Ny} Nz={sd.Nz} Nb={sd.Nb} Nbl={sd.Nbl} Nba={sd.Nba} Ns={sd.Ns} Nr={sd.Nr} Nt={sd.Nt} "
+                   f"fcc_flag={sd.fcc_flag} precision={'single' if self.precision == 1 else 'double'}")
+
+    def setup_mask(self):
+        pass  # the node mask is built on the device at allocate_mem()
+
+    def allocate_mem(self):
+        self.sd = self.sd_full.slab(self.rank, self.world)
+        self.eng = Engine(self.sd, self.device)
+        if self.world > 1:
+            self._comm_init()
+
+    def set_coeffs(self):
+        pass  # derived in SimData.from_arrays exactly as load_sim_data does (fdtd_data.h:186-194, 424-460)
+
+    def checks(self):
+        pass  # SimData.from_arrays and pffdtd_create validate the description
+
+    def _comm_init(self):
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("gloo", rank=self.rank, world_size=self.world)
+        box = [comm_unique_id() if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.eng.comm_init(box[0], self.rank, self.world)
+
+    # ---- running ----------------------------------------------------------------------------------
+    def run_steps(self, nstart, nsteps):
+        self.eng.run_steps(nstart, nsteps)
+
+    def run_all(self, nsteps=1):
+        self.print("running..")
+        Npts = self.Nx * self.Ny * self.Nz
+        t0 = time.perf_counter()
+        # batches only bound how far the host runs ahead of the device; there is no per-step sync
+        batch = max(int(nsteps), 64)
+        for n in range(0, self.Nt, batch):
+            self.run_steps(n, min(batch, self.Nt - n))
+        self.eng.sync()
+        self.t_elapsed = time.perf_counter() - t0
+        self.print(f"Run-time loop: {self.t_elapsed:.6f}, {self.Nt * Npts / 1e6 / max(self.t_elapsed, 1e-12):.2f} MVox/s")
+        self._collect()
+
+    def _collect(self):
+        u = self.eng.read_outputs(0, self.Nt)
+        if self.world > 1:
+            import torch.distributed as dist
+            parts = [None] * self.world
+            dist.all_gather_object(parts, u)
+            u = np.concatenate(parts, axis=0)  # rank order == sorted receiver order
+        if self.scale:
+            u = self.sd_full.rescale_output(u)  # fdtd_data.h:912-925
+        self.u_out = u
+
+    def save_outputs(self):
+        if self.rank == 0:
+            self.sd_full.write_outputs(self.data_dir, self.u_out)
+        self.print(f"saved outputs in {self.data_dir}")
+
+    def print_last_samples(self, Np):
+        self.print("GRID OUTPUTS")
+        for i in range(self.Nr):
+            self.print(f"out {i}")
+            for n in range(max(self.Nt - Np, 0), self.Nt):
+                self.print(f"sample {n}: {self.u_out[self.out_reorder[i], n]:.16e}")
+
+    def close(self):
+        if self.eng is not None:
+            self.eng.close()
+            self.eng = None
+
+
+def run_folder(data_dir, precision=2, device=None, nsteps=1, quiet=True):
+    """load -> run -> write sim_outs.h5; returns u_out in file (original receiver) order"""
+    eng = SimEngine(data_dir, precision=precision, device=device, quiet=quiet)
+    eng.load_h5_data()
+    eng.setup_mask()
+    eng.allocate_mem()
+    eng.set_coeffs()
+    eng.checks()
+    eng.run_all(nsteps)
+    eng.save_outputs()
+    out = eng.sd_full.reorder_output(eng.u_out)
+    eng.close()
+    return out
+
+
+def main(argv=None):
+    import argparse
+    parser = argparse.ArgumentParser(description="B200 FDTD engine: drop-in for `python -m fdtd.sim_fdtd` / fdtd_main_gpu_*.x")
+    parser.add_argument("--data_dir", type=str, help="run directory")
+    parser.add_argument("--nsteps", type=int, default=1, help="run in batches of steps")
+    parser.add_argument("--nthreads", type=int, default=None, help="accepted for compatibility; unused")
+    parser.add_argument("--precision", type=int, default=2, choices=(1, 2), help="1 single (fdtd_main_gpu_single.x), 2 double")
+    parser.add_argument("--energy", action="store_true", help="energy balance (not available on the GPU path yet)")
+    parser.add_argument("--device", type=int, default=None)
+    args = parser.parse_args(argv)
+    if args.data_dir is None:
+        args.data_dir = os.getcwd()  # the C binaries run in the data folder (fdtd_main.c:35)
+    eng = SimEngine(args.data_dir, energy_on=args.energy, nthreads=args.nthreads, precision=args.precision, device=args.device)
+    eng.load_h5_data()
+    eng.setup_mask()
+    eng.allocate_mem()
+    eng.set_coeffs()
+    eng.checks()
+    eng.run_all(args.nsteps)
+    eng.save_outputs()
+    eng.print_last_samples(5)
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

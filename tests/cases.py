@@ -1,0 +1,48 @@
+"""Shared problem builders for the parity tests (deterministic, no RNG)."""
+import numpy as np
+
+from pffdtd_b200 import folder_prep, shoebox
+from pffdtd_b200.sim_data import SimData
+
+# name -> (make_shoebox kwargs, layout) ; layout: "cart", "fcc1" (checkerboard), "fcc2" (folded gpu folder)
+CASES = {
+    "cart_rigid": (dict(Nx=20, Ny=18, Nz=16, Nt=60, rigid=True), "cart"),
+    "cart_lossy": (dict(Nx=24, Ny=20, Nz=18, Nt=60, nmat=2, mb=3), "cart"),
+    "cart_lossy_mb11": (dict(Nx=30, Ny=22, Nz=37, Nt=50, nmat=3, mb=11), "cart"),
+    "cart_ragged": (dict(Nx=19, Ny=41, Nz=131, Nt=40, nmat=1, mb=4), "cart"),
+    "cart_wide": (dict(Nx=17, Ny=70, Nz=270, Nt=30, nmat=2, mb=2), "cart"),
+    "cart_hann": (dict(Nx=22, Ny=22, Nz=22, Nt=60, nmat=1, mb=5, sig="hann10"), "cart"),
+    "fcc1_lossy": (dict(Nx=24, Ny=20, Nz=18, Nt=50, fcc=True, nmat=2, mb=3), "fcc1"),
+    "fcc2_lossy": (dict(Nx=24, Ny=20, Nz=18, Nt=50, fcc=True, nmat=2, mb=3), "fcc2"),
+    "fcc2_rigid": (dict(Nx=26, Ny=24, Nz=40, Nt=40, fcc=True, rigid=True), "fcc2"),
+}
+
+
+def make_files(name):
+    kw, layout = CASES[name]
+    kw = dict(kw)
+    files = shoebox.make_shoebox(kw.pop("Nx"), kw.pop("Ny"), kw.pop("Nz"), kw.pop("Nt"), **kw)
+    if layout == "fcc2":
+        files = folder_prep.gpu_folder(files)
+    return files
+
+
+def make_sim_data(name, precision, scale=True):
+    files = make_files(name)
+    if precision == 1 and not int(files["comms_out"]["diff"]):
+        raise ValueError("fp32 needs diff")
+    sd = shoebox.sim_data_from_files(files, precision)
+    if scale:
+        sd.scale_input()
+    return sd
+
+
+def noise_grids(sd, seed=1234):
+    """random initial state on the interior nodes of both grids (energy / stress tests)"""
+    rng = np.random.default_rng(seed)
+    g = []
+    for _ in range(2):
+        a = np.zeros((sd.Nx, sd.Ny, sd.Nz))
+        a[1:-1, 1:-1, 1:-1] = rng.uniform(-1, 1, (sd.Nx - 2, sd.Ny - 2, sd.Nz - 2))
+        g.append(a.astype(sd.real).astype(np.float64))
+    return g

@@ -1,0 +1,111 @@
+"""CUDA path vs the CPU oracle, through the C ABI (include/pffdtd_b200.h).
+
+Bar: BIT-EXACT receiver traces and grids in fp64 AND fp32 -- the kernels reproduce the reference CPU
+engine's arithmetic (cpu_engine.h:129-325) operation for operation, so no tolerance is needed.
+"""
+import numpy as np
+import pytest
+
+from cases import CASES, make_sim_data, noise_grids
+from oracle import Oracle
+from pffdtd_b200.engine import Engine, PffdtdError, run_sim
+
+pytestmark = pytest.mark.gpu
+
+
+def _kernels(sd):
+    return (0, 1) if sd.fcc_flag == 0 else (0,)
+
+
+@pytest.mark.parametrize("precision", (2, 1))
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_traces_bit_exact(name, precision):
+    sd = make_sim_data(name, precision)
+    ref = Oracle(sd).run_all()
+    assert np.abs(ref).max() > 0
+    for ak in _kernels(sd):
+        with Engine(sd) as e:
+            e.set_option("air_kernel", ak)
+            e.run_steps(0, sd.Nt)
+            got = e.read_outputs()
+        assert np.array_equal(got, ref), f"{name} p{precision} air_kernel={ak}: max|d|={np.abs(got - ref).max():.3e}"
+
+
+@pytest.mark.parametrize("precision", (2, 1))
+@pytest.mark.parametrize("name", ("cart_lossy", "cart_ragged", "fcc1_lossy", "fcc2_lossy"))
+def test_full_state_bit_exact_from_noise(name, precision):
+    """whole grids + boundary ODE state after 25 steps from a random initial state: exercises every
+    interior node, the halo mirrors, the ABC shell and the lossy walls at once"""
+    sd = make_sim_data(name, precision)
+    g1, g0 = noise_grids(sd)
+    o = Oracle(sd)
+    o.write_grid(1, g1)
+    o.write_grid(0, g0)
+    o.run_steps(0, 25)
+    for ak in _kernels(sd):
+        with Engine(sd) as e:
+            e.set_option("air_kernel", ak)
+            e.write_grid(1, g1)
+            e.write_grid(0, g0)
+            e.run_steps(0, 25)
+            for which in (1, 0):
+                a, b = e.read_grid(which), o.read_grid(which)
+                if sd.fcc_flag == 1:  # unused odd-parity nodes are never written by either engine
+                    pass
+                assert np.array_equal(a, b), f"{name} p{precision} ak={ak} grid{which}: {np.abs(a - b).max():.3e}"
+            v, g = e.read_boundary_state()
+            vo, go = o.read_boundary_state()
+            assert np.array_equal(v, vo) and np.array_equal(g, go)
+
+
+def test_step_host_matches_run_steps():
+    sd = make_sim_data("cart_lossy", 1)
+    ref = Oracle(sd).run_all()
+    with Engine(sd) as e:
+        cols = [e.step_host(n, sd.in_sigs[:, n]).copy() for n in range(sd.Nt)]
+    assert np.array_equal(np.stack(cols, axis=1), ref)
+
+
+def test_run_sim_entry_point():
+    sd = make_sim_data("cart_rigid", 2)
+    out, t = run_sim(sd)
+    assert np.array_equal(out, Oracle(sd).run_all()) and t > 0
+
+
+def test_batched_equals_single_steps():
+    sd = make_sim_data("cart_hann", 2)
+    with Engine(sd) as a, Engine(sd) as b:
+        a.run_steps(0, sd.Nt)
+        for n in range(0, sd.Nt, 7):
+            b.run_steps(n, min(7, sd.Nt - n))
+        assert np.array_equal(a.read_outputs(), b.read_outputs())
+
+
+def test_linearity_in_the_source():
+    """doubling the input doubles every trace exactly (all operations are linear and scaling by 2 is exact)"""
+    sd = make_sim_data("cart_lossy", 2)
+    with Engine(sd) as e:
+        e.run_steps(0, sd.Nt)
+        u = e.read_outputs()
+    sd2 = make_sim_data("cart_lossy", 2)
+    sd2.in_sigs = sd2.in_sigs * 2.0
+    with Engine(sd2) as e:
+        e.run_steps(0, sd2.Nt)
+        u2 = e.read_outputs()
+    assert np.array_equal(u2, 2.0 * u)
+
+
+def test_errors_are_reported_not_fatal():
+    sd = make_sim_data("cart_rigid", 2)
+    with Engine(sd) as e:
+        with pytest.raises(PffdtdError):
+            e.run_steps(0, sd.Nt + 1)
+        with pytest.raises(PffdtdError):
+            e.set_option("no_such_option", 1)
+    bad = make_sim_data("cart_rigid", 2)
+    bad.bn_ixyz = bad.bn_ixyz.copy()
+    bad.bn_ixyz[0] = 0  # on the halo layer
+    with pytest.raises(PffdtdError):
+        Engine(bad)
+    with pytest.raises(PffdtdError):
+        Engine(sd, device=99)
