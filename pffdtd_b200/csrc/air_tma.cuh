@@ -34,8 +34,11 @@ struct AirTma {
    int precision = 0, fcc = 0;
    i64 Nx = 0, Ny = 0, Nz = 0, Nzp = 0;
    CUtensorMap map[2];  // over u[0], u[1]
+   void *base[2] = {nullptr, nullptr};
+   int cfg = 0;         // tile configuration, see PF_AIR_CONFIGS
    int xc = 0;          // planes per CTA chunk, 0 = automatic
    int sm_count = 148;
+   int slots = 0;       // resident CTAs of the chosen configuration on this device
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -98,150 +101,200 @@ struct AirCfg {
    static constexpr int ROWS = TY + 2;
    static constexpr int STAGE_BYTES = ROWS * BZ * (int)sizeof(Real);
    static constexpr int STAGE_PITCH = (STAGE_BYTES + 127) / 128 * 128;
-   static constexpr int SMEM_BYTES = S * STAGE_PITCH + S * 8 + 128;
+   static constexpr int SMEM_BYTES = S * STAGE_PITCH + 2 * S * 8 + 128;
+   static constexpr int THREADS = (NW + 1) * 32;  // NW consumer warps + 1 TMA producer warp
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------- work decomposition
+// The job "planes [x_begin, x_end) x all y-z tiles" is cut into units of one tile-plane, ordered
+// (x-chunk of XC planes, tile, plane in chunk), and every CTA of a persistent grid (one CTA per
+// resident slot) takes an equal contiguous range of units: all CTAs finish together (no tail), and CTAs
+// running at the same time work on the same x-chunk of neighbouring tiles, so tile halos hit in L2.
+// A CTA's range is a few "segments" (one tile, consecutive planes); each costs two extra plane loads.
+struct AirJob {
+   int x_begin, n, XC, tz, tiles;  // n planes, tiles = tz*ty
+   i64 units;                      // n * tiles
+};
+struct AirSeg {
+   int xa, cnt, z0, y0;
+   i64 next;  // first unit after the segment
+};
+template <int TZ, int TY>
+__device__ __forceinline__ AirSeg air_segment(const AirJob &jb, i64 u, i64 u_end) {
+   const i64 per_chunk = (i64)jb.XC * jb.tiles;
+   const int k = (int)(u / per_chunk);
+   const int len = min(jb.XC, jb.n - k * jb.XC);
+   const i64 up = u - (i64)k * per_chunk;
+   const int t = (int)(up / len), p = (int)(up - (i64)t * len);
+   AirSeg s;
+   s.next = min(u_end, (i64)k * per_chunk + (i64)(t + 1) * len);
+   s.cnt = (int)(s.next - u);
+   s.xa = jb.x_begin + k * jb.XC + p;
+   s.z0 = (t % jb.tz) * TZ;
+   s.y0 = 1 + (t / jb.tz) * TY;
+   return s;
+}
+
 // ---------------------------------------------------------------- the kernel (7-point Cartesian)
-template <typename Real, int RPT, int NW, int S>
-__global__ void __launch_bounds__(NW * 32, 2)
+// Warp-specialised: warp NW is the TMA producer (one lane), warps 0..NW-1 compute.  full[s] flips when
+// the bytes of a plane have landed in stage s, empty[s] when all NW consumer warps are done with it.
+// Loads are numbered consecutively over all segments of the CTA, load i uses stage i % S.
+template <typename Real, int RPT, int NW, int S, int MAXR>
+__global__ void __maxnreg__(MAXR)
     k_air_tma_cart(const __grid_constant__ CUtensorMap map_u1, Real *__restrict__ u0g, const uint32_t *__restrict__ mask, i64 Ny,
-                   i64 Nz, i64 Nzp, int x_begin, int x_end, int XC, Real a1, Real a2) {
+                   i64 Nz, i64 Nzp, AirJob jb, Real a1, Real a2) {
    typedef AirCfg<Real, RPT, NW, S> C;
    typedef Ops<Real> O;
    constexpr int VEC = C::VEC, BZ = C::BZ;
+   constexpr uint32_t VMASK = (1u << VEC) - 1u;
    extern __shared__ unsigned char smem_raw[];
    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
    uint64_t *full = (uint64_t *)(smem + S * C::STAGE_PITCH);
+   uint64_t *empty = full + S;
 
    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-   const int z0 = blockIdx.x * C::TZ;
-   const int y0 = 1 + blockIdx.y * C::TY;
-   const int xa = x_begin + blockIdx.z * XC;
-   const int xe = min(x_end, xa + XC);
-   const int nsteps = xe - xa;
-   if (nsteps <= 0) return;
-   const int L = nsteps + 2;  // planes xa-1 .. xe
-
-   auto stage = [&](int i) -> Real * { return (Real *)(smem + (i % S) * C::STAGE_PITCH); };
-   auto issue = [&](int i) {
-      uint64_t *bar = &full[i % S];
-      mbar_expect_tx(bar, C::STAGE_BYTES);
-      tma_load_3d(stage(i), &map_u1, bar, z0 - VEC, y0 - 1, xa - 1 + i);
-   };
-   auto wait = [&](int i) { mbar_wait(&full[i % S], (uint32_t)((i / S) & 1)); };
+   const i64 u_begin = jb.units * blockIdx.x / gridDim.x, u_end = jb.units * (blockIdx.x + 1) / gridDim.x;
+   if (u_end <= u_begin) return;
 
    if (tid == 0) {
-      for (int s = 0; s < S; s++) mbar_init(&full[s], 1);
+      for (int s = 0; s < S; s++) {
+         mbar_init(&full[s], 1);
+         mbar_init(&empty[s], NW);
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
    }
    __syncthreads();
-   if (tid == 0) {
-      for (int i = 0; i < S && i < L; i++) issue(i);
-   }
 
-   // this thread's strip: rows y0 + w*RPT + r, columns z0 + VEC*lane .. +VEC-1
-   const int zv = z0 + VEC * lane;
-   const int ybase = y0 + w * RPT;
-   const bool zact = zv < Nz - 1;  // vectors entirely in the far halo/padding are never touched
-   const int srow0 = w * RPT + 1;  // shared-memory row of strip row 0 (box row 0 is y0-1)
-   const int scol = VEC + VEC * lane;
-   // mask bits of this thread's vector inside the row's 32-node word
-   const int mword = zv >> 5, mshift = zv & 31;
-
-   Real um[RPT][VEC], uc[RPT][VEC], up[RPT][VEC];
-   wait(0);
-   {
-      const Real *s0 = stage(0);
-#pragma unroll
-      for (int r = 0; r < RPT; r++) ld_vec<Real, VEC>(s0 + (srow0 + r) * BZ + scol, um[r]);
-   }
-   wait(1);
-   {
-      const Real *s1 = stage(1);
-#pragma unroll
-      for (int r = 0; r < RPT; r++) ld_vec<Real, VEC>(s1 + (srow0 + r) * BZ + scol, uc[r]);
-   }
-   __syncthreads();
-   if (tid == 0 && S < L) issue(S);  // stage 0 (plane xa-1) now lives in registers
-
-   // u0 / mask prefetch for the first plane
-   Real u0n[RPT][VEC];
-   uint32_t mkn[RPT];
-   bool ract[RPT];
-#pragma unroll
-   for (int r = 0; r < RPT; r++) ract[r] = zact && (ybase + r) <= Ny - 2;
-   auto fetch = [&](int x) {
-#pragma unroll
-      for (int r = 0; r < RPT; r++) {
-         if (ract[r]) {
-            const i64 row = (i64)x * Ny + (ybase + r);
-            ld_vec<Real, VEC>(u0g + row * Nzp + zv, u0n[r]);
-            mkn[r] = __ldg(mask + row * (Nzp >> 5) + mword) >> mshift;
+   if (w == NW) {
+      // ---------------- producer
+      if (lane == 0) {
+         int i = 0;
+         for (i64 u = u_begin; u < u_end;) {
+            const AirSeg sg = air_segment<C::TZ, C::TY>(jb, u, u_end);
+            for (int q = 0; q < sg.cnt + 2; q++, i++) {  // planes xa-1 .. xa+cnt
+               const int s = i % S;
+               if (i >= S) mbar_wait(&empty[s], (uint32_t)(((i / S) - 1) & 1));
+               mbar_expect_tx(&full[s], C::STAGE_BYTES);
+               tma_load_3d(smem + s * C::STAGE_PITCH, &map_u1, &full[s], sg.z0 - VEC, sg.y0 - 1, sg.xa - 1 + q);
+            }
+            u = sg.next;
          }
       }
-   };
-   fetch(xa);
+      return;
+   }
 
-   for (int j = 0; j < nsteps; j++) {
-      const int x = xa + j;
-      wait(j + 2);
-      const Real *sc = stage(j + 1);
-      const Real *su = stage(j + 2);
-      Real rowm[VEC], rowp[VEC], zl[RPT], zr[RPT];
+   // ---------------- consumers
+   auto stage = [&](int i) -> const Real * { return (const Real *)(smem + (i % S) * C::STAGE_PITCH); };
+   auto wait_full = [&](int i) { mbar_wait(&full[i % S], (uint32_t)((i / S) & 1)); };
+   auto release = [&](int i) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[i % S]);
+   };
+   const int soff = (w * RPT + 1) * BZ + VEC + VEC * lane;  // strip row 0 inside a stage (box row 0 is y0-1)
+   const i64 u0_plane = Ny * Nzp, mk_plane = Ny * (Nzp >> 5), mk_row = Nzp >> 5;
+
+   int base = 0;  // load index of the segment's first plane
+   for (i64 u = u_begin; u < u_end;) {
+      const AirSeg sg = air_segment<C::TZ, C::TY>(jb, u, u_end);
+      u = sg.next;
+      // this thread's strip: rows y0 + w*RPT + r, columns z0 + VEC*lane .. +VEC-1
+      const int zv = sg.z0 + VEC * lane;
+      const int ybase = sg.y0 + w * RPT;
+      const bool zact = zv < Nz - 1;  // vectors entirely in the far halo/padding are never touched
+      const int mshift = zv & 31;
+      int nrow = 0;  // active rows of the strip
 #pragma unroll
-      for (int r = 0; r < RPT; r++) ld_vec<Real, VEC>(su + (srow0 + r) * BZ + scol, up[r]);
-      ld_vec<Real, VEC>(sc + (srow0 - 1) * BZ + scol, rowm);
-      ld_vec<Real, VEC>(sc + (srow0 + RPT) * BZ + scol, rowp);
+      for (int r = 0; r < RPT; r++) nrow += (zact && (ybase + r) <= Ny - 2) ? 1 : 0;
+
+      Real um[RPT][VEC], uc[RPT][VEC], up[RPT][VEC];
+      wait_full(base);
+      {
+         const Real *s0 = stage(base) + soff;
 #pragma unroll
-      for (int r = 0; r < RPT; r++) {
-         zl[r] = sc[(srow0 + r) * BZ + scol - 1];
-         zr[r] = sc[(srow0 + r) * BZ + scol + VEC];
+         for (int r = 0; r < RPT; r++) ld_vec<Real, VEC>(s0 + r * BZ, um[r]);
       }
-      Real u0c[RPT][VEC];
+      release(base);
+      wait_full(base + 1);
+      {
+         const Real *s1 = stage(base + 1) + soff;
+#pragma unroll
+         for (int r = 0; r < RPT; r++) ld_vec<Real, VEC>(s1 + r * BZ, uc[r]);
+      }
+      // u0 / mask of the first plane; afterwards each row's registers are refilled for the next plane as
+      // soon as the row has been stored, so the HBM loads of plane x+1 fly while plane x is computed
+      Real *u0p = u0g + ((i64)sg.xa * Ny + ybase) * Nzp + zv;
+      const uint32_t *mkp = mask + ((i64)sg.xa * Ny + ybase) * mk_row + (zv >> 5);
+      Real u0v[RPT][VEC];
       uint32_t mk[RPT];
 #pragma unroll
       for (int r = 0; r < RPT; r++) {
-         mk[r] = mkn[r];
-#pragma unroll
-         for (int k = 0; k < VEC; k++) u0c[r][k] = u0n[r][k];
+         if (r < nrow) {
+            ld_vec<Real, VEC>(u0p + r * Nzp, u0v[r]);
+            mk[r] = __ldg(mkp + r * mk_row);
+         }
       }
-      if (j + 1 < nsteps) fetch(x + 1);
+
+      for (int j = 0; j < sg.cnt; j++) {
+         wait_full(base + j + 2);
+         const Real *sc = stage(base + j + 1) + soff;
+         const Real *su = stage(base + j + 2) + soff;
+         Real rowm[VEC], rowp[VEC], zl[RPT], zr[RPT];
 #pragma unroll
-      for (int r = 0; r < RPT; r++) {
-         if (ract[r]) {
-            Real o[VEC];
+         for (int r = 0; r < RPT; r++) ld_vec<Real, VEC>(su + r * BZ, up[r]);
+         ld_vec<Real, VEC>(sc - BZ, rowm);
+         ld_vec<Real, VEC>(sc + RPT * BZ, rowp);
+#pragma unroll
+         for (int r = 0; r < RPT; r++) {
+            zl[r] = sc[r * BZ - 1];
+            zr[r] = sc[r * BZ + VEC];
+         }
+         release(base + j + 1);  // plane x's stage may be refilled; x-1 and x+1 live in registers / the next stage
+         const bool more = j + 1 < sg.cnt;
+#pragma unroll
+         for (int r = 0; r < RPT; r++) {
+            if (r < nrow) {
+               const uint32_t m = (mk[r] >> mshift) & VMASK;
+               Real o[VEC];
+#pragma unroll
+               for (int k = 0; k < VEC; k++) {
+                  const Real yp = (r < RPT - 1) ? uc[r + 1][k] : rowp[k];
+                  const Real ym = (r > 0) ? uc[r - 1][k] : rowm[k];
+                  const Real zp = (k < VEC - 1) ? uc[r][k + 1] : zr[r];
+                  const Real zm = (k > 0) ? uc[r][k - 1] : zl[r];
+                  Real p = O::sub(O::mul(a1, uc[r][k]), u0v[r][k]);
+                  p = O::add(p, O::mul(a2, up[r][k]));
+                  p = O::add(p, O::mul(a2, um[r][k]));
+                  p = O::add(p, O::mul(a2, yp));
+                  p = O::add(p, O::mul(a2, ym));
+                  p = O::add(p, O::mul(a2, zp));
+                  p = O::add(p, O::mul(a2, zm));
+                  o[k] = ((m >> k) & 1u) ? u0v[r][k] : p;
+               }
+               if (m != VMASK) st_vec<Real, VEC>(u0p + r * Nzp, o);
+               if (more) {
+                  ld_vec<Real, VEC>(u0p + u0_plane + r * Nzp, u0v[r]);
+                  mk[r] = __ldg(mkp + mk_plane + r * mk_row);
+               }
+            }
+         }
+         u0p += u0_plane;
+         mkp += mk_plane;
+#pragma unroll
+         for (int r = 0; r < RPT; r++) {
 #pragma unroll
             for (int k = 0; k < VEC; k++) {
-               const Real yp = (r < RPT - 1) ? uc[r + 1][k] : rowp[k];
-               const Real ym = (r > 0) ? uc[r - 1][k] : rowm[k];
-               const Real zp = (k < VEC - 1) ? uc[r][k + 1] : zr[r];
-               const Real zm = (k > 0) ? uc[r][k - 1] : zl[r];
-               Real p = O::sub(O::mul(a1, uc[r][k]), u0c[r][k]);
-               p = O::add(p, O::mul(a2, up[r][k]));
-               p = O::add(p, O::mul(a2, um[r][k]));
-               p = O::add(p, O::mul(a2, yp));
-               p = O::add(p, O::mul(a2, ym));
-               p = O::add(p, O::mul(a2, zp));
-               p = O::add(p, O::mul(a2, zm));
-               o[k] = ((mk[r] >> k) & 1u) ? u0c[r][k] : p;
-            }
-            if ((mk[r] & ((1u << VEC) - 1u)) != ((1u << VEC) - 1u)) {
-               const i64 row = (i64)x * Ny + (ybase + r);
-               st_vec<Real, VEC>(u0g + row * Nzp + zv, o);
+               um[r][k] = uc[r][k];
+               uc[r][k] = up[r][k];
             }
          }
       }
-#pragma unroll
-      for (int r = 0; r < RPT; r++) {
-#pragma unroll
-         for (int k = 0; k < VEC; k++) {
-            um[r][k] = uc[r][k];
-            uc[r][k] = up[r][k];
-         }
-      }
-      __syncthreads();  // everyone is done with plane x's stage
-      if (tid == 0 && j + 1 + S < L) issue(j + 1 + S);
+      release(base + sg.cnt + 1);  // the last plane was only ever an "x+1" plane
+      base += sg.cnt + 2;
    }
 }
 
@@ -250,21 +303,48 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// tile shape: 8 warps x 4 rows, 4 planes in flight
-#define PF_AIR_RPT 4
-#define PF_AIR_NW 8
-#define PF_AIR_S 4
+// tile configurations (rows per thread, consumer warps, planes in flight, register cap); cfg 0 is the default
+#define PF_AIR_CONFIGS(X) \
+   X(0, 2, 8, 4, 72)      \
+   X(1, 4, 8, 4, 112)     \
+   X(2, 1, 8, 4, 56)      \
+   X(3, 1, 16, 4, 56)     \
+   X(4, 2, 4, 4, 80)      \
+   X(5, 2, 8, 3, 72)      \
+   X(6, 2, 8, 5, 72)      \
+   X(7, 2, 16, 4, 56)
+#define PF_AIR_NCFG 8
 
 template <typename Real>
-static int air_tma_attr() {
-   typedef AirCfg<Real, PF_AIR_RPT, PF_AIR_NW, PF_AIR_S> C;
-   return (int)cudaFuncSetAttribute(k_air_tma_cart<Real, PF_AIR_RPT, PF_AIR_NW, PF_AIR_S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    C::SMEM_BYTES);
+static int air_tma_attr(int cfg) {
+   cudaError_t rc = cudaErrorInvalidValue;
+#define X(id, RPT, NW, S, MAXR)                                                                                              \
+   if (cfg == id)                                                                                                            \
+      rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                AirCfg<Real, RPT, NW, S>::SMEM_BYTES);
+   PF_AIR_CONFIGS(X)
+#undef X
+   return (int)rc;
 }
 
-static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 Nz, i64 Nzp, void *u_a, void *u_b) {
+static void air_cfg_shape(int cfg, int *rpt, int *nw) {
+   *rpt = 4, *nw = 8;
+#define X(id, RPT, NW, S, MAXR) \
+   if (cfg == id) *rpt = RPT, *nw = NW;
+   PF_AIR_CONFIGS(X)
+#undef X
+}
+
+static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 Nz, i64 Nzp, void *u_a, void *u_b, int cfg = 0) {
    t->ok = false;
    t->precision = precision, t->fcc = fcc, t->Nx = Nx, t->Ny = Ny, t->Nz = Nz, t->Nzp = Nzp;
+   t->base[0] = u_a, t->base[1] = u_b;
+   if (cfg < 0 || cfg >= PF_AIR_NCFG) {
+      t->why = "no such tile configuration";
+      return 1;
+   }
+   t->cfg = cfg;
+   t->slots = 0;
    if (fcc != 0) {
       t->why = "13-point FCC runs on the generic kernel";
       return 1;
@@ -284,13 +364,14 @@ static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 
    EncodeTiledFn encode = (EncodeTiledFn)fn;
    const size_t rs = precision == 1 ? 4 : 8;
    const int VEC = 16 / (int)rs;
+   int rpt, nw;
+   air_cfg_shape(cfg, &rpt, &nw);
    const cuuint64_t gdim[3] = {(cuuint64_t)Nzp, (cuuint64_t)Ny, (cuuint64_t)Nx};
    const cuuint64_t gstr[2] = {(cuuint64_t)Nzp * rs, (cuuint64_t)Ny * Nzp * rs};
-   const cuuint32_t box[3] = {(cuuint32_t)(32 * VEC + 2 * VEC), (cuuint32_t)(PF_AIR_NW * PF_AIR_RPT + 2), 1};
+   const cuuint32_t box[3] = {(cuuint32_t)(32 * VEC + 2 * VEC), (cuuint32_t)(nw * rpt + 2), 1};
    const cuuint32_t estr[3] = {1, 1, 1};
-   void *bases[2] = {u_a, u_b};
    for (int k = 0; k < 2; k++) {
-      CUresult r = encode(&t->map[k], precision == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, bases[k],
+      CUresult r = encode(&t->map[k], precision == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, t->base[k],
                           gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) {
@@ -298,7 +379,7 @@ static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 
          return 1;
       }
    }
-   int rc = precision == 1 ? air_tma_attr<float>() : air_tma_attr<double>();
+   int rc = precision == 1 ? air_tma_attr<float>(cfg) : air_tma_attr<double>(cfg);
    if (rc) {
       cudaGetLastError();
       t->why = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)rc);
@@ -312,29 +393,40 @@ static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 
    return 0;
 }
 
+template <typename Real, int RPT, int NW, int S, int MAXR>
+static int air_tma_launch_cfg(AirTma *t, int cur, Real *u0, const uint32_t *mask, i64 xb, i64 xe, Real a1, Real a2, cudaStream_t s) {
+   typedef AirCfg<Real, RPT, NW, S> C;
+   auto kern = k_air_tma_cart<Real, RPT, NW, S, MAXR>;
+   if (t->slots <= 0) {
+      int per_sm = 0;
+      cudaError_t rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, C::SMEM_BYTES);
+      if (rc != cudaSuccess) return (int)rc;
+      t->slots = std::max(1, per_sm) * t->sm_count;
+   }
+   AirJob jb;
+   jb.x_begin = (int)xb;
+   jb.n = (int)(xe - xb);
+   jb.tz = (int)((t->Nz - 1 + C::TZ - 1) / C::TZ);  // vectors starting at z >= Nz-1 hold no interior node
+   const int ty = (int)((t->Ny - 2 + C::TY - 1) / C::TY);
+   jb.tiles = jb.tz * ty;
+   jb.XC = std::min(jb.n, t->xc > 0 ? t->xc : 64);
+   jb.units = (i64)jb.n * jb.tiles;
+   // one CTA per resident slot, but never less than ~8 tile-planes per CTA
+   const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>(t->slots, jb.units / 8));
+   kern<<<grid, C::THREADS, C::SMEM_BYTES, s>>>(t->map[cur], u0, mask, t->Ny, t->Nz, t->Nzp, jb, a1, a2);
+   return (int)cudaGetLastError();
+}
+
 // planes [xb, xe) of the slab; `cur` = index of the grid that currently is u1
 template <typename Real>
 static int air_tma_launch(AirTma *t, int cur, const Real *u1, Real *u0, const uint32_t *mask, i64 xb, i64 xe, Real a1, Real a2,
                           cudaStream_t s) {
-   typedef AirCfg<Real, PF_AIR_RPT, PF_AIR_NW, PF_AIR_S> C;
    (void)u1;
-   const int n = (int)(xe - xb);
-   const unsigned tz = (unsigned)((t->Nz - 1 + C::TZ - 1) / C::TZ);  // vectors starting at z >= Nz-1 hold no interior node
-   const unsigned ty = (unsigned)((t->Ny - 2 + C::TY - 1) / C::TY);
-   int xc = t->xc;
-   if (xc <= 0) {
-      // enough CTAs for ~4 rounds of 2 resident CTAs per SM, but chunks no shorter than 8 planes (2 extra
-      // plane loads per chunk)
-      const i64 tiles = (i64)tz * ty;
-      i64 chunks = (8LL * t->sm_count + tiles - 1) / tiles;
-      chunks = std::max<i64>(1, std::min<i64>(chunks, std::max(1, n / 8)));
-      xc = (int)((n + chunks - 1) / chunks);
-   }
-   const unsigned nch = (unsigned)((n + xc - 1) / xc);
-   dim3 grd(tz, ty, nch);
-   k_air_tma_cart<Real, PF_AIR_RPT, PF_AIR_NW, PF_AIR_S><<<grd, PF_AIR_NW * 32, C::SMEM_BYTES, s>>>(
-       t->map[cur], u0, mask, t->Ny, t->Nz, t->Nzp, (int)xb, (int)xe, xc, a1, a2);
-   return (int)cudaGetLastError();
+#define X(id, RPT, NW, S, MAXR) \
+   if (t->cfg == id) return air_tma_launch_cfg<Real, RPT, NW, S, MAXR>(t, cur, u0, mask, xb, xe, a1, a2, s);
+   PF_AIR_CONFIGS(X)
+#undef X
+   return (int)cudaErrorInvalidValue;
 }
 
 }  // namespace pf

@@ -410,6 +410,11 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       e->profile_air = value != 0;
    } else if (k == "air_xc") {
       e->tma.xc = (int)value;
+   } else if (k == "air_cfg") {
+      CU(cudaSetDevice(e->device));
+      CU(cudaStreamSynchronize(e->s_main));
+      if (pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->u[0], e->u[1], (int)value))
+         return fail(PFFDTD_EINVAL, "air_cfg %lld: %s", (long long)value, e->tma.why.c_str());
    } else if (k == "manual_halo") {
       e->manual_halo = value != 0;
    } else {
