@@ -89,9 +89,15 @@ int pffdtd_destroy(pffdtd_engine *e);
 int pffdtd_comm_unique_id(void *id128 /* 128 bytes out */);
 int pffdtd_comm_init(pffdtd_engine *e, const void *id128, int rank, int nranks);
 
-/* Options: "air_kernel" (0 generic, 1 tiled/TMA), "use_graph" (0/1), "overlap" (0/1). */
+/* Options: "air_kernel" (0 generic one-thread-per-node, 1 tiled TMA sweep [default for Cartesian grids]),
+ * "fuse" (1 = the tiled kernel also applies the absorbing shell and mirrors the halos on write [default]),
+ * "overlap" (1 = edge planes first, halo exchange overlapped with the interior [default]),
+ * "air_cfg" (tile configuration), "air_xc" (x-chunk length), "profile_air" (CUDA events around every air launch),
+ * "manual_halo" (allow stepping a slab without a communicator; the caller moves the halo planes). */
 int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t value);
-/* Counters/timers: "launches", "air_ms" (CUDA-event time of air kernels since reset), "steps". */
+/* Counters/timers: "launches", "steps", "air_ms" / "air_launches_timed" (CUDA-event time of the air launches
+ * since reset, with profile_air), "timer_start" / "timer_stop_ms" (device stopwatch on the engine's stream),
+ * "fused", "mirror_pairs", "air_kernel", "Nzp". */
 int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out);
 int pffdtd_reset_stats(pffdtd_engine *e);
 
@@ -117,6 +123,11 @@ int pffdtd_read_grid(pffdtd_engine *e, int which, double *out /* Nx*Ny*Nz */);
 int pffdtd_write_grid(pffdtd_engine *e, int which, const double *in /* Nx*Ny*Nz */);
 /* Boundary ODE state (vh1, gh1: [Nbl*PFFDTD_MMB], reference CPU layout nb*MMb+m) for energy checks. */
 int pffdtd_read_boundary_state(pffdtd_engine *e, double *vh1, double *gh1);
+
+/* Device self-test: the fused absorbing-shell update divides by the constants 1 + l*Q with a
+ * reciprocal + one exact-residual correction instead of a general division; this compares the two on
+ * `count` pseudo-random numerators per divisor and returns the number of differing results (must be 0). */
+int pffdtd_selftest(int device, double l, int precision, int64_t count, int64_t *mismatches);
 
 /* Whole-run convenience with the reference's run_sim() shape: create, run Nt steps, write
  * u_out[Nr*Nt], destroy; returns elapsed seconds of the loop through *elapsed_s. */

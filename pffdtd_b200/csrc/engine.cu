@@ -99,7 +99,7 @@ struct EvPair {
 
 struct pffdtd_engine {
    int device = 0, precision = 0, fcc = 0, Nm = 0, NN = 6;
-   i64 Nx = 0, Ny = 0, Nz = 0, Nzp = 0, Nb = 0, Nbl = 0, Nba = 0, Ns = 0, Nr = 0, Nt = 0;
+   i64 Nx = 0, Ny = 0, Nz = 0, Nzp = 0, mwpr = 0, Nb = 0, Nbl = 0, Nba = 0, Ns = 0, Nr = 0, Nt = 0;
    i64 ix0 = 0;
    int x_lo_edge = 1, x_hi_edge = 1;
    double l = 0, a1 = 0, a2 = 0, sl2 = 0, lo2 = 0;
@@ -114,7 +114,14 @@ struct pffdtd_engine {
    int8_t *mat = nullptr, *Q = nullptr, *Mb = nullptr;
    void *ssaf = nullptr, *beta = nullptr, *quads = nullptr, *insig = nullptr, *uout = nullptr;
    void *hist[2] = {nullptr, nullptr}, *u2ba = nullptr, *vh1 = nullptr, *gh1 = nullptr;
+   void *lo2Kbg = nullptr, *facb = nullptr;  // per lossy node constants (k_fd_prep)
+   uint16_t *matmb = nullptr;                // per lossy node: material | Mb << 8
    int serial_src = 0;
+   // fused Cartesian step (tiled air kernel applies the ABC shell and mirrors the halos on write)
+   int fuse_ok = 0;     // the ABC list is the canonical full shell, so the air kernel may apply it
+   int halo_dirty = 0;  // u1's halos were not produced by mirror-on-write: run the mirror kernels first
+   i64 *pair_src = nullptr, *pair_dst = nullptr;  // late halo mirrors (boundary / source nodes at index 2 | N-3)
+   i64 np = 0, np_lo = 0, np_hi = 0;
    // prefix/suffix sizes of the sorted node lists that lie in the first/last owned plane (edge work
    // that must finish before the halo exchange); only valid when `sorted`
    int sorted = 0;
@@ -128,7 +135,7 @@ struct pffdtd_engine {
    void *comm = nullptr;
    int rank = 0, nranks = 1, comm_pending = 0;
    // options
-   int air_kernel = 1, overlap = 1, profile_air = 0, manual_halo = 0;
+   int air_kernel = 1, overlap = 1, profile_air = 0, manual_halo = 0, fuse = 1;
    // stats
    i64 steps_done = 0;  // next time index expected by run_steps
    double launches = 0;
@@ -259,6 +266,7 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    e->Nm = d->Nm;
    e->Nx = d->Nx, e->Ny = d->Ny, e->Nz = d->Nz;
    e->Nzp = (d->Nz + 31) / 32 * 32;
+   e->mwpr = (e->Nzp / 32 + 3) / 4 * 4;  // mask words per row, a multiple of 16 bytes (TMA stride)
    e->Nb = d->Nb, e->Nbl = d->Nbl, e->Nba = d->Nba, e->Ns = d->Ns, e->Nr = d->Nr, e->Nt = d->Nt;
    e->ix0 = d->ix0, e->x_lo_edge = d->x_lo_edge, e->x_hi_edge = d->x_hi_edge;
    e->l = d->l, e->a1 = d->a1, e->a2 = d->a2, e->sl2 = d->sl2, e->lo2 = d->lo2;
@@ -289,7 +297,7 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    const size_t npad = (size_t)(e->Nx * e->Ny * e->Nzp);
    if (dalloc_bytes(e, &e->u[0], npad * e->rs)) return PFFDTD_ECUDA;
    if (dalloc_bytes(e, &e->u[1], npad * e->rs)) return PFFDTD_ECUDA;
-   if (dalloc(e, &e->mask, npad / 32)) return PFFDTD_ECUDA;
+   if (dalloc(e, &e->mask, (size_t)(e->Nx * e->Ny * e->mwpr))) return PFFDTD_ECUDA;
 
    int rc;
    if ((rc = upload_idx(e, &e->bn, d->bn_ixyz, e->Nb, "bn_ixyz", true))) return rc;
@@ -319,6 +327,9 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    if (dalloc_bytes(e, &e->u2ba, (size_t)e->Nba * e->rs)) return PFFDTD_ECUDA;
    if (dalloc_bytes(e, &e->vh1, (size_t)e->Nbl * PFFDTD_MMB * e->rs)) return PFFDTD_ECUDA;
    if (dalloc_bytes(e, &e->gh1, (size_t)e->Nbl * PFFDTD_MMB * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->lo2Kbg, (size_t)e->Nbl * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->facb, (size_t)e->Nbl * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc(e, &e->matmb, (size_t)e->Nbl)) return PFFDTD_ECUDA;
    CU(cudaMallocHost(&e->h_in, std::max<size_t>((size_t)e->Ns * 8, 64)));
    CU(cudaMallocHost(&e->h_out, std::max<size_t>((size_t)e->Nr * 8, 64)));
 
@@ -339,14 +350,82 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
       edge_counts(d->in_ixyz, e->Ns, 2 * P, (e->Nx - 2) * P, &e->ns_lo, &e->ns_hi);
    }
 
-   // mask
-   {
-      const i64 words = (i64)(npad / 32);
-      pf::k_mask_init<<<(unsigned)((words + 255) / 256), 256, 0, e->s_main>>>(e->mask, e->Nx, e->Ny, e->Nz, e->Nzp, e->fcc, e->ix0);
-      if (e->Nb) pf::k_mask_nodes<<<(unsigned)((e->Nb + 255) / 256), 256, 0, e->s_main>>>(e->mask, e->bn, e->Nb);
+   // per-node constants of the frequency-dependent boundary
+   if (e->Nbl) {
+      pf::MatTable mt{e->quads, e->beta, e->Mb};
+      const unsigned g = (unsigned)((e->Nbl + 127) / 128);
+      if (e->precision == 1)
+         pf::k_fd_prep<float><<<g, 128, 0, e->s_main>>>(e->mat, (const float *)e->ssaf, e->Nbl, (float)e->lo2, mt, (float *)e->lo2Kbg,
+                                                        (float *)e->facb, e->matmb);
+      else
+         pf::k_fd_prep<double><<<g, 128, 0, e->s_main>>>(e->mat, (const double *)e->ssaf, e->Nbl, e->lo2, mt, (double *)e->lo2Kbg,
+                                                         (double *)e->facb, e->matmb);
       CU(cudaGetLastError());
    }
-   if ((rc = pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->u[0], e->u[1]))) {
+   // can the tiled kernel apply the absorbing shell itself?  Only if the list handed in is exactly the
+   // canonical shell of this slab (fdtd_data.h:620-675) -- every interior node with an index of 1 or N-2.
+   if (e->fcc == 0) {
+      const i64 Nx = e->Nx, Ny = e->Ny, Nz = e->Nz;
+      auto qx = [&](i64 ix) { return ((e->x_lo_edge && ix == 1) || (e->x_hi_edge && ix == Nx - 2)) ? 1 : 0; };
+      i64 expect = 0;
+      for (i64 ix = 1; ix <= Nx - 2; ix++) {
+         const i64 inner = (Ny - 4) * (Nz - 4);  // nodes of the plane with neither y nor z on the shell
+         expect += qx(ix) ? (Ny - 2) * (Nz - 2) : (Ny - 2) * (Nz - 2) - std::max<i64>(inner, 0);
+      }
+      bool ok = (Ny >= 4 && Nz >= 4) && expect == e->Nba && ascending(d->bna_ixyz, e->Nba);
+      for (i64 i = 0; ok && i < e->Nba; i++) {
+         const i64 v = d->bna_ixyz[i], row = v / Nz, iz = v - row * Nz, ix = row / Ny, iy = row - ix * Ny;
+         const int Q = qx(ix) + ((iy == 1 || iy == Ny - 2) ? 1 : 0) + ((iz == 1 || iz == Nz - 2) ? 1 : 0);
+         ok = Q > 0 && Q == d->Q_bna[i];
+      }
+      e->fuse_ok = ok;
+   }
+   // late halo mirrors: nodes written after the air kernel (boundary, source) whose value belongs in a halo
+   if (e->fcc == 0) {
+      std::vector<std::pair<i64, i64>> pr;  // (src, dst) in the padded layout
+      auto add_node = [&](i64 v) {
+         const i64 row = v / e->Nz, iz = v - row * e->Nz, ix = row / e->Ny, iy = row - ix * e->Ny;
+         i64 ox[3], oy[3], oz[3];
+         int nx = 0, ny = 0, nz = 0;
+         ox[nx++] = ix;
+         if (e->x_lo_edge && ix == 2) ox[nx++] = 0;
+         if (e->x_hi_edge && ix == e->Nx - 3) ox[nx++] = e->Nx - 1;
+         oy[ny++] = iy;
+         if (iy == 2) oy[ny++] = 0;
+         if (iy == e->Ny - 3) oy[ny++] = e->Ny - 1;
+         oz[nz++] = iz;
+         if (iz == 2) oz[nz++] = 0;
+         if (iz == e->Nz - 3) oz[nz++] = e->Nz - 1;
+         const i64 src = (ix * e->Ny + iy) * e->Nzp + iz;
+         for (int a = 0; a < nx; a++)
+            for (int b = 0; b < ny; b++)
+               for (int c = 0; c < nz; c++)
+                  if (a | b | c) pr.push_back({src, (ox[a] * e->Ny + oy[b]) * e->Nzp + oz[c]});
+      };
+      for (i64 i = 0; i < e->Nb; i++) add_node(d->bn_ixyz[i]);
+      for (i64 i = 0; i < e->Ns; i++) add_node(d->in_ixyz[i]);
+      std::sort(pr.begin(), pr.end());
+      pr.erase(std::unique(pr.begin(), pr.end()), pr.end());
+      e->np = (i64)pr.size();
+      std::vector<i64> ps(pr.size()), pd(pr.size());
+      const i64 P = e->Ny * e->Nzp;
+      for (size_t i = 0; i < pr.size(); i++) {
+         ps[i] = pr[i].first, pd[i] = pr[i].second;
+         if (pr[i].first < 2 * P) e->np_lo++;
+         if (pr[i].first >= (e->Nx - 2) * P) e->np_hi++;
+      }
+      if ((rc = upload_raw(e, &e->pair_src, ps.data(), e->np, "pair_src"))) return rc;
+      if ((rc = upload_raw(e, &e->pair_dst, pd.data(), e->np, "pair_dst"))) return rc;
+   }
+
+   // mask
+   {
+      const i64 words = e->Nx * e->Ny * e->mwpr;
+      pf::k_mask_init<<<(unsigned)((words + 255) / 256), 256, 0, e->s_main>>>(e->mask, e->Nx, e->Ny, e->Nz, e->mwpr, e->fcc, e->ix0);
+      if (e->Nb) pf::k_mask_nodes<<<(unsigned)((e->Nb + 255) / 256), 256, 0, e->s_main>>>(e->mask, e->bn, e->Nb, e->Nzp, e->mwpr);
+      CU(cudaGetLastError());
+   }
+   if ((rc = pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask))) {
       // not fatal: fall back to the generic kernel, remember why
       e->air_kernel = 0;
    }
@@ -404,6 +483,10 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       if (value == 1 && !e->tma.ok) return fail(PFFDTD_ESTATE, "tiled air kernel unavailable: %s", e->tma.why.c_str());
       if (value < 0 || value > 1) return fail(PFFDTD_EINVAL, "air_kernel must be 0 or 1");
       e->air_kernel = (int)value;
+      e->halo_dirty = 1;
+   } else if (k == "fuse") {
+      e->fuse = value != 0;
+      e->halo_dirty = 1;
    } else if (k == "overlap") {
       e->overlap = value != 0;
    } else if (k == "profile_air") {
@@ -413,7 +496,7 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
    } else if (k == "air_cfg") {
       CU(cudaSetDevice(e->device));
       CU(cudaStreamSynchronize(e->s_main));
-      if (pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->u[0], e->u[1], (int)value))
+      if (pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask, (int)value))
          return fail(PFFDTD_EINVAL, "air_cfg %lld: %s", (long long)value, e->tma.why.c_str());
    } else if (k == "manual_halo") {
       e->manual_halo = value != 0;
@@ -459,6 +542,8 @@ extern "C" int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out) {
       *out = ms;
    } else if (k == "air_kernel") *out = e->air_kernel;
    else if (k == "Nzp") *out = (double)e->Nzp;
+   else if (k == "fused") *out = (e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok) ? 1 : 0;
+   else if (k == "mirror_pairs") *out = (double)e->np;
    else return fail(PFFDTD_EINVAL, "unknown stat %s", key);
    return PFFDTD_OK;
 }
@@ -480,7 +565,8 @@ static inline unsigned nblk(i64 n, int b) { return (unsigned)((n + b - 1) / b); 
 
 // a contiguous piece of one step's work: x-planes [xb,xe) and the node-list ranges that live in them
 struct Part {
-   i64 xb, xe, b0, nb, l0, nbl, a0, nba, s0, ns;
+   i64 xb, xe, b0, nb, l0, nbl, a0, nba, s0, ns, p0, np;
+   bool recv;  // this part also reads the receivers
 };
 
 template <typename Real>
@@ -489,6 +575,7 @@ struct Step {
    Real *u1, *u0;
    cudaStream_t s;
    i64 n;
+   bool fused;
 
    // 4. air update of planes [xb, xe)
    int air(i64 xb, i64 xe) {
@@ -510,25 +597,32 @@ struct Step {
          CU(cudaEventRecord(ev->a, s));
       }
       if (e->air_kernel == 1) {
-         int rc = pf::air_tma_launch<Real>(&e->tma, e->cur, u1, u0, e->mask, xb, xe, (Real)e->a1, (Real)e->a2, s);
+         pf::AirEdge<Real> eg;
+         memset(&eg, 0, sizeof eg);
+         eg.fuse = fused, eg.x_lo = e->x_lo_edge, eg.x_hi = e->x_hi_edge, eg.Nx = (int)e->Nx;
+         // cpu_engine.h:226-228: Real lQ = l*Q; ... /(1.0 + lQ)
+         eg.lQ1 = (Real)((Real)e->l * (Real)1), eg.lQ2 = (Real)((Real)e->l * (Real)2), eg.lQ3 = (Real)((Real)e->l * (Real)3);
+         eg.den1 = 1.0 + (double)eg.lQ1, eg.den2 = 1.0 + (double)eg.lQ2, eg.den3 = 1.0 + (double)eg.lQ3;
+         eg.rden1 = 1.0 / eg.den1, eg.rden2 = 1.0 / eg.den2, eg.rden3 = 1.0 / eg.den3;
+         int rc = pf::air_tma_launch<Real>(&e->tma, e->cur, u0, xb, xe, (Real)e->a1, (Real)e->a2, eg, s);
          if (rc) return fail(PFFDTD_ECUDA, "tiled air kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
       } else {
          dim3 blk(64, 4, 1);
          dim3 grd(nblk(e->Nzp, 64), nblk(e->Ny, 4), (unsigned)(xe - xb));
          if (e->fcc)
-            pf::k_air_generic<Real, 12><<<grd, blk, 0, s>>>(u1, u0, e->mask, e->Ny, e->Nzp, xb, (Real)e->a1, (Real)e->a2, e->off);
+            pf::k_air_generic<Real, 12><<<grd, blk, 0, s>>>(u1, u0, e->mask, e->Ny, e->Nzp, e->mwpr, xb, (Real)e->a1, (Real)e->a2, e->off);
          else
-            pf::k_air_generic<Real, 6><<<grd, blk, 0, s>>>(u1, u0, e->mask, e->Ny, e->Nzp, xb, (Real)e->a1, (Real)e->a2, e->off);
+            pf::k_air_generic<Real, 6><<<grd, blk, 0, s>>>(u1, u0, e->mask, e->Ny, e->Nzp, e->mwpr, xb, (Real)e->a1, (Real)e->a2, e->off);
       }
       e->launches += 1;
       if (timed) CU(cudaEventRecord(ev->b, s));
       return 0;
    }
-   // 4-7 and 9 for one part, in the reference's order: air, ABC, rigid, FD, sources
+   // steps 4-9 for one part, in the reference's order: air, ABC, rigid, FD, receivers/sources, late mirrors
    int part(const Part &p) {
       int rc = air(p.xb, p.xe);
       if (rc) return rc;
-      if (p.nba > 0) {
+      if (!fused && p.nba > 0) {
          pf::k_abc<Real><<<nblk(p.nba, 128), 128, 0, s>>>(u0, e->bna, e->Q, (const Real *)e->u2ba, p.a0, p.nba, (Real)e->l);
          e->launches += 1;
       }
@@ -540,18 +634,41 @@ struct Step {
          e->launches += 1;
       }
       if (p.nbl > 0) {
-         pf::MatTable mt{e->quads, e->beta, e->Mb};
-         pf::k_fd<Real, PFFDTD_MMB><<<nblk(p.nbl, 128), 128, 0, s>>>(u0, e->bnl, e->mat, (const Real *)e->ssaf, (Real *)e->hist[n & 1],
-                                                                    (Real *)e->vh1, (Real *)e->gh1, p.l0, p.nbl, e->Nbl, (Real)e->lo2, mt);
+         pf::k_fd<Real, PFFDTD_MMB><<<nblk(p.nbl, 128), 128, 0, s>>>(u0, e->bnl, e->matmb, (const Real *)e->lo2Kbg, (const Real *)e->facb,
+                                                                    (Real *)e->hist[n & 1], (Real *)e->vh1, (Real *)e->gh1, p.l0, p.nbl,
+                                                                    e->Nbl, (const Real *)e->quads);
          e->launches += 1;
       }
-      if (p.ns > 0) {
-         pf::k_src<Real><<<nblk(p.ns, 128), 128, 0, s>>>(u0, e->in, (const Real *)e->insig + n * e->Ns, p.s0, p.ns, e->serial_src);
+      const i64 nr = p.recv ? e->Nr : 0;
+      if (nr > 0 || p.ns > 0) {
+         pf::k_io<Real><<<nblk(std::max(nr, p.ns), 128), 128, 0, s>>>(u1, u0, e->out, (Real *)e->uout + n * e->Nr, nr, e->in,
+                                                                     (const Real *)e->insig + n * e->Ns, p.s0, p.ns, e->serial_src);
+         e->launches += 1;
+      }
+      if (fused && p.np > 0) {
+         pf::k_pairs<Real><<<nblk(p.np, 128), 128, 0, s>>>(u0, e->pair_src, e->pair_dst, p.p0, p.np);
          e->launches += 1;
       }
       return 0;
    }
 };
+
+// the reference's mirror pass on one grid (cpu_engine.h:135-172): seam row, then z, y, x faces in that order
+template <typename Real>
+static void mirror_pass(pffdtd_engine *e, Real *u, cudaStream_t s) {
+   const i64 Nx = e->Nx, Ny = e->Ny, Nz = e->Nz, Nzp = e->Nzp;
+   if (e->fcc == 2) {
+      pf::k_fold_seam<Real><<<dim3(nblk(Nz, 128), (unsigned)Nx), 128, 0, s>>>(u, Nx, Ny, Nz, Nzp);
+      e->launches += 1;
+   }
+   pf::k_flip_z<Real><<<nblk(Nx * Ny, 128), 128, 0, s>>>(u, Nx * Ny, Nz, Nzp);
+   pf::k_flip_y<Real><<<dim3(nblk(Nz, 128), (unsigned)Nx), 128, 0, s>>>(u, Nx, Ny, Nz, Nzp, e->fcc != 2);
+   e->launches += 2;
+   if (e->x_lo_edge || e->x_hi_edge) {
+      pf::k_flip_x<Real><<<dim3(nblk(Nz, 128), (unsigned)Ny), 128, 0, s>>>(u, Nx, Ny, Nz, Nzp, e->x_lo_edge, e->x_hi_edge);
+      e->launches += 1;
+   }
+}
 
 // exchange of the new state's edge planes (unew = u0 before the swap):
 // plane 1 -> lower neighbour's plane Nx-1, plane Nx-2 -> upper neighbour's plane 0.
@@ -576,10 +693,11 @@ static int exchange(pffdtd_engine *e, void *unew, cudaStream_t s) {
 template <typename Real>
 static int step_impl(pffdtd_engine *e, i64 n) {
    if (n < 0 || n >= e->Nt) return fail(PFFDTD_EINVAL, "step %lld outside [0,%lld)", (long long)n, (long long)e->Nt);
-   Step<Real> st{e, (Real *)e->u[e->cur], (Real *)e->u[e->cur ^ 1], e->s_main, n};
+   const bool fused = e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok;
+   Step<Real> st{e, (Real *)e->u[e->cur], (Real *)e->u[e->cur ^ 1], e->s_main, n, fused};
    Real *u1 = st.u1, *u0 = st.u0;
    cudaStream_t s = e->s_main;
-   const i64 Nx = e->Nx, Ny = e->Ny, Nz = e->Nz, Nzp = e->Nzp;
+   const i64 Nx = e->Nx;
    int rc;
 
    // the halo planes of u1 come from the previous step's exchange
@@ -587,36 +705,25 @@ static int step_impl(pffdtd_engine *e, i64 n) {
       CU(cudaStreamWaitEvent(s, e->ev_comm, 0));
       e->comm_pending = 0;
    }
-   // 1. previous-state values at the ABC nodes
-   if (e->Nba) {
-      pf::k_gather<Real><<<nblk(e->Nba, 128), 128, 0, s>>>(u0, e->bna, (Real *)e->u2ba, e->Nba);
-      e->launches += 1;
-   }
-   // 2. folded FCC seam row
-   if (e->fcc == 2) {
-      pf::k_fold_seam<Real><<<dim3(nblk(Nz, 128), (unsigned)Nx), 128, 0, s>>>(u1, Nx, Ny, Nz, Nzp);
-      e->launches += 1;
-   }
-   // 3. halo mirrors z, y, x
-   pf::k_flip_z<Real><<<nblk(Nx * Ny, 128), 128, 0, s>>>(u1, Nx * Ny, Nz, Nzp);
-   pf::k_flip_y<Real><<<dim3(nblk(Nz, 128), (unsigned)Nx), 128, 0, s>>>(u1, Nx, Ny, Nz, Nzp, e->fcc != 2);
-   e->launches += 2;
-   if (e->x_lo_edge || e->x_hi_edge) {
-      pf::k_flip_x<Real><<<dim3(nblk(Nz, 128), (unsigned)Ny), 128, 0, s>>>(u1, Nx, Ny, Nz, Nzp, e->x_lo_edge, e->x_hi_edge);
-      e->launches += 1;
-   }
-   // 8. receivers read the current state
-   if (e->Nr) {
-      pf::k_gather<Real><<<nblk(e->Nr, 128), 128, 0, s>>>(u1, e->out, (Real *)e->uout + n * e->Nr, e->Nr);
-      e->launches += 1;
+   if (!fused) {
+      // 1. previous-state values at the ABC nodes; 2.+3. seam row and halo mirrors of u1
+      if (e->Nba) {
+         pf::k_gather<Real><<<nblk(e->Nba, 128), 128, 0, s>>>(u0, e->bna, (Real *)e->u2ba, e->Nba);
+         e->launches += 1;
+      }
+      mirror_pass<Real>(e, u1, s);
+      e->halo_dirty = 1;  // the state this step produces has no mirrored halos yet
+   } else if (e->halo_dirty) {
+      mirror_pass<Real>(e, u1, s);
+      e->halo_dirty = 0;
    }
    const bool lo = e->comm && !e->x_lo_edge, hi = e->comm && !e->x_hi_edge;
    const bool split = (lo || hi) && e->overlap && e->sorted && Nx >= 5;
    if (split) {
       // planes the neighbours need first, then the exchange on the comm stream while the interior runs
-      if (lo && (rc = st.part(Part{1, 2, 0, e->nb_lo, 0, e->nbl_lo, 0, e->nba_lo, 0, e->ns_lo}))) return rc;
+      if (lo && (rc = st.part(Part{1, 2, 0, e->nb_lo, 0, e->nbl_lo, 0, e->nba_lo, 0, e->ns_lo, 0, e->np_lo, false}))) return rc;
       if (hi && (rc = st.part(Part{Nx - 2, Nx - 1, e->Nb - e->nb_hi, e->nb_hi, e->Nbl - e->nbl_hi, e->nbl_hi, e->Nba - e->nba_hi,
-                                   e->nba_hi, e->Ns - e->ns_hi, e->ns_hi})))
+                                   e->nba_hi, e->Ns - e->ns_hi, e->ns_hi, e->np - e->np_hi, e->np_hi, false})))
          return rc;
       CU(cudaGetLastError());
       CU(cudaEventRecord(e->ev_edge, s));
@@ -626,12 +733,13 @@ static int step_impl(pffdtd_engine *e, i64 n) {
       e->comm_pending = 1;
       const i64 b0 = lo ? e->nb_lo : 0, b1 = hi ? e->nb_hi : 0, l0 = lo ? e->nbl_lo : 0, l1 = hi ? e->nbl_hi : 0;
       const i64 a0 = lo ? e->nba_lo : 0, a1 = hi ? e->nba_hi : 0, s0 = lo ? e->ns_lo : 0, s1 = hi ? e->ns_hi : 0;
+      const i64 p0 = lo ? e->np_lo : 0, p1 = hi ? e->np_hi : 0;
       if ((rc = st.part(Part{lo ? 2 : 1, hi ? Nx - 2 : Nx - 1, b0, e->Nb - b0 - b1, l0, e->Nbl - l0 - l1, a0, e->Nba - a0 - a1, s0,
-                             e->Ns - s0 - s1})))
+                             e->Ns - s0 - s1, p0, e->np - p0 - p1, true})))
          return rc;
       CU(cudaGetLastError());
    } else {
-      if ((rc = st.part(Part{1, Nx - 1, 0, e->Nb, 0, e->Nbl, 0, e->Nba, 0, e->Ns}))) return rc;
+      if ((rc = st.part(Part{1, Nx - 1, 0, e->Nb, 0, e->Nbl, 0, e->Nba, 0, e->Ns, 0, e->np, true}))) return rc;
       CU(cudaGetLastError());
       if ((rc = exchange(e, u0, s))) return rc;
    }
@@ -742,6 +850,7 @@ extern "C" int pffdtd_write_grid(pffdtd_engine *e, int which, const double *in) 
    CU(cudaSetDevice(e->device));
    int rc = pffdtd_sync(e);
    if (rc) return rc;
+   e->halo_dirty = 1;
    return e->precision == 1 ? grid_io<float>(e, which, (double *)in, false) : grid_io<double>(e, which, (double *)in, false);
 }
 
@@ -761,6 +870,28 @@ extern "C" int pffdtd_read_boundary_state(pffdtd_engine *e, double *vh1, double 
          vh1[dst] = e->precision == 1 ? (double)((float *)tv.data())[src] : ((double *)tv.data())[src];
          gh1[dst] = e->precision == 1 ? (double)((float *)tg.data())[src] : ((double *)tg.data())[src];
       }
+   return PFFDTD_OK;
+}
+
+// device self-test of the constant-divisor division used by the fused absorbing shell: compares
+// div_by_const with __ddiv_rn on `count` pseudo-random numerators for divisor 1 + l*Q; *mismatches out
+extern "C" int pffdtd_selftest(int device, double l, int precision, int64_t count, int64_t *mismatches) {
+   if (!mismatches || count < 0) return fail(PFFDTD_EINVAL, "bad selftest arguments");
+   CU(cudaSetDevice(device));
+   unsigned long long *bad = nullptr, h = 0;
+   CU(cudaMalloc((void **)&bad, 8));
+   CU(cudaMemset(bad, 0, 8));
+   const int per_thread = 256, threads = 256;
+   const unsigned blocks = (unsigned)std::max<int64_t>(1, count / (3LL * per_thread * threads));
+   for (int Q = 1; Q <= 3; Q++) {
+      const double lQ = precision == 1 ? (double)((float)l * (float)Q) : l * (double)Q;
+      const double b = 1.0 + lQ;
+      pf::k_selftest_div<<<blocks, threads>>>(b, 1.0 / b, 0x1234567ull * Q, per_thread, precision == 1, bad);
+   }
+   CU(cudaGetLastError());
+   CU(cudaMemcpy(&h, bad, 8, cudaMemcpyDeviceToHost));
+   cudaFree(bad);
+   *mismatches = (int64_t)h;
    return PFFDTD_OK;
 }
 

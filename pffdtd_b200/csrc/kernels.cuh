@@ -7,7 +7,8 @@
 // Device layout: grids are [Nx][Ny][Nzp], z contiguous, Nzp = Nz rounded up to 32 elements so that
 // every row starts on a 128-byte (fp32) / 256-byte (fp64) line and 16-byte vectors / TMA strides are
 // legal.  All node lists are re-linearised to that pitch at create time.  `mask` has one bit per
-// padded node, 32 nodes per word (LSB first, the reference's convention fdtd_data.h:567-572 extended):
+// padded node, 32 nodes per word, `mwpr` words per row (Nzp/32 rounded up to 4 words so that a row of the
+// mask is a legal TMA stride) (LSB first, the reference's convention fdtd_data.h:567-572 extended):
 // a set bit means "the air update must not write this node": boundary nodes, the outer halo layer,
 // the z padding and -- for the checkerboard FCC layout (fcc_flag 1) -- the unused odd-parity nodes.
 #pragma once
@@ -41,12 +42,11 @@ struct Offsets {
 // mask construction (create time)
 // ------------------------------------------------------------------------------------------------
 // one thread per 32-node word: halo layer, z padding, odd parity for fcc_flag==1
-__global__ void k_mask_init(uint32_t *mask, i64 Nx, i64 Ny, i64 Nz, i64 Nzp, int fcc_flag, i64 ix0) {
-   const i64 wpr = Nzp >> 5;  // words per row
+__global__ void k_mask_init(uint32_t *mask, i64 Nx, i64 Ny, i64 Nz, i64 mwpr, int fcc_flag, i64 ix0) {
    const i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-   if (w >= Nx * Ny * wpr) return;
-   const i64 row = w / wpr;
-   const i64 z0 = (w - row * wpr) << 5;
+   if (w >= Nx * Ny * mwpr) return;
+   const i64 row = w / mwpr;
+   const i64 z0 = (w - row * mwpr) << 5;
    const i64 ix = row / Ny, iy = row - ix * Ny;
    uint32_t bits = 0;
    const bool edge_row = (ix == 0) || (ix == Nx - 1) || (iy == 0) || (iy == Ny - 1);
@@ -59,11 +59,12 @@ __global__ void k_mask_init(uint32_t *mask, i64 Nx, i64 Ny, i64 Nz, i64 Nzp, int
    mask[w] = bits;
 }
 
-__global__ void k_mask_nodes(uint32_t *mask, const i64 *bn, i64 Nb) {
+__global__ void k_mask_nodes(uint32_t *mask, const i64 *bn, i64 Nb, i64 Nzp, i64 mwpr) {
    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= Nb) return;
    const i64 c = bn[i];
-   atomicOr(&mask[c >> 5], 1u << (c & 31));
+   const i64 row = c / Nzp, iz = c - row * Nzp;
+   atomicOr(&mask[row * mwpr + (iz >> 5)], 1u << (iz & 31));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -125,7 +126,7 @@ __global__ void k_flip_x(Real *u1, i64 Nx, i64 Ny, i64 Nz, i64 Nzp, int lo, int 
 // ------------------------------------------------------------------------------------------------
 template <typename Real, int NN>
 __global__ void __launch_bounds__(256) k_air_generic(const Real *__restrict__ u1, Real *__restrict__ u0,
-                                                      const uint32_t *__restrict__ mask, i64 Ny, i64 Nzp, i64 x_begin,
+                                                      const uint32_t *__restrict__ mask, i64 Ny, i64 Nzp, i64 mwpr, i64 x_begin,
                                                       Real a1, Real a2, Offsets off) {
    typedef Ops<Real> O;
    const i64 iz = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(256) k_air_generic(const Real *__restrict__ u1
    const i64 ix = x_begin + blockIdx.z;
    if (iz >= Nzp || iy >= Ny) return;
    const i64 c = (ix * Ny + iy) * Nzp + iz;
-   if ((mask[c >> 5] >> (c & 31)) & 1u) return;
+   if ((mask[(ix * Ny + iy) * mwpr + (iz >> 5)] >> (iz & 31)) & 1u) return;
    Real p = O::sub(O::mul(a1, u1[c]), u0[c]);
 #pragma unroll
    for (int j = 0; j < NN; j++) p = O::add(p, O::mul(a2, u1[c + off.o[j]]));
@@ -185,6 +186,11 @@ __global__ void k_rigid(const Real *__restrict__ u1, Real *__restrict__ u0, cons
 // step 7: frequency-dependent (RLC branch) boundary nodes      (cpu_engine.h:290-301, 363-405)
 // State vh1/gh1 is stored branch-major [m][Nbl] so that a warp's accesses coalesce.
 // hist = the node's value two steps back on entry (u2b), this step's value on exit (u0b -> u2b of n+2).
+// The per-node constants of the reference's loop head,
+//     lo2Kbg = lo2*ssaf*beta[k]        fac = 2*lo2*ssaf / (1 + lo2Kbg)
+// never change, so k_fd_prep evaluates them once (same operations, same order, same bits) and packs
+// (material, Mb) into one 16-bit word: the hot kernel then starts its 2*Mb state loads after ONE
+// dependent load instead of three.
 // ------------------------------------------------------------------------------------------------
 struct MatTable {
    const void *quads;  // Real [Nm][MMB][4] = b, bd, bDh, bFh
@@ -192,36 +198,57 @@ struct MatTable {
    const int8_t *Mb;   // [Nm]
 };
 
+template <typename Real>
+__global__ void k_fd_prep(const int8_t *__restrict__ mat_bnl, const Real *__restrict__ ssaf_bnl, i64 Nbl, Real lo2, MatTable mt,
+                          Real *__restrict__ lo2Kbg_out, Real *__restrict__ fac_out, uint16_t *__restrict__ matmb) {
+   typedef Ops<Real> O;
+   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= Nbl) return;
+   const Real one = (Real)1.0, two = (Real)2.0;
+   const int k = mat_bnl[i];
+   const Real ssaf = ssaf_bnl[i];
+   const Real lo2Kbg = O::mul(O::mul(lo2, ssaf), ((const Real *)mt.beta)[k]);
+   lo2Kbg_out[i] = lo2Kbg;
+   fac_out[i] = O::div(O::mul(O::mul(two, lo2), ssaf), O::add(one, lo2Kbg));
+   matmb[i] = (uint16_t)((unsigned)k | ((unsigned)mt.Mb[k] << 8));
+}
+
 template <typename Real, int MMB>
-__global__ void k_fd(Real *__restrict__ u0, const i64 *__restrict__ bnl, const int8_t *__restrict__ mat_bnl,
-                     const Real *__restrict__ ssaf_bnl, Real *__restrict__ hist, Real *__restrict__ vh1,
-                     Real *__restrict__ gh1, i64 i0, i64 n, i64 Nbl, Real lo2, MatTable mt) {
+__global__ void __launch_bounds__(128) k_fd(Real *__restrict__ u0, const i64 *__restrict__ bnl, const uint16_t *__restrict__ matmb,
+                                            const Real *__restrict__ lo2Kbg_bnl, const Real *__restrict__ fac_bnl,
+                                            Real *__restrict__ hist, Real *__restrict__ vh1, Real *__restrict__ gh1, i64 i0, i64 n,
+                                            i64 Nbl, const Real *__restrict__ quads) {
    typedef Ops<Real> O;
    const i64 i = i0 + (i64)blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= i0 + n) return;
    const Real one = (Real)1.0, two = (Real)2.0;
-   const int k = mat_bnl[i];
-   const Real *q = (const Real *)mt.quads + (i64)k * MMB * 4;
-   const Real beta = ((const Real *)mt.beta)[k];
-   const int Mb = mt.Mb[k];
-   const i64 c = bnl[i];
-   const Real ssaf = ssaf_bnl[i];
-   const Real lo2Kbg = O::mul(O::mul(lo2, ssaf), beta);
-   const Real den = O::add(one, lo2Kbg);
-   const Real fac = O::div(O::mul(O::mul(two, lo2), ssaf), den);
-   const Real u2 = hist[i];
-   Real u = O::div(O::add(u0[c], O::mul(lo2Kbg, u2)), den);
+   const unsigned mm = matmb[i];
+   const int Mb = (int)(mm >> 8);
+   const Real *q = quads + (i64)(mm & 0xffu) * MMB * 4;
+   // everything this node needs from memory is requested up front
    Real v1[MMB], g1[MMB];
 #pragma unroll
    for (int m = 0; m < MMB; m++) {
       if (m < Mb) {
          v1[m] = vh1[(i64)m * Nbl + i];
          g1[m] = gh1[(i64)m * Nbl + i];
+      }
+   }
+   const i64 c = bnl[i];
+   const Real lo2Kbg = lo2Kbg_bnl[i], fac = fac_bnl[i];
+   const Real u2 = hist[i];
+   const Real den = O::add(one, lo2Kbg);
+   Real u = O::div(O::add(u0[c], O::mul(lo2Kbg, u2)), den);
+#pragma unroll
+   for (int m = 0; m < MMB; m++) {
+      if (m < Mb) {
          const Real bDh = q[4 * m + 2], bFh = q[4 * m + 3];
          u = O::sub(u, O::mul(fac, O::sub(O::mul(O::mul(two, bDh), v1[m]), O::mul(bFh, g1[m]))));
       }
    }
    const Real du = O::sub(u, u2);
+   hist[i] = u;
+   u0[c] = u;
 #pragma unroll
    for (int m = 0; m < MMB; m++) {
       if (m < Mb) {
@@ -231,8 +258,6 @@ __global__ void k_fd(Real *__restrict__ u0, const i64 *__restrict__ bnl, const i
          vh1[(i64)m * Nbl + i] = v0;
       }
    }
-   hist[i] = u;
-   u0[c] = u;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -251,6 +276,29 @@ __global__ void k_src(Real *__restrict__ u0, const i64 *__restrict__ in_ixyz, co
    } else if (i < ns) {
       u0[in_ixyz[s0 + i]] = O::add(u0[in_ixyz[s0 + i]], in_row[s0 + i]);
    }
+}
+
+// steps 8+9 in one launch: receivers (threads [0,Nr)) and sources (threads [0,ns)) touch different grids
+template <typename Real>
+__global__ void k_io(const Real *__restrict__ u1, Real *__restrict__ u0, const i64 *__restrict__ out_ixyz, Real *__restrict__ out_row,
+                     i64 Nr, const i64 *__restrict__ in_ixyz, const Real *__restrict__ in_row, i64 s0, i64 ns, int serial_src) {
+   typedef Ops<Real> O;
+   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < Nr) out_row[i] = u1[out_ixyz[i]];
+   if (serial_src) {
+      if (i == 0)
+         for (i64 s = s0; s < s0 + ns; s++) u0[in_ixyz[s]] = O::add(u0[in_ixyz[s]], in_row[s]);
+   } else if (i < ns) {
+      u0[in_ixyz[s0 + i]] = O::add(u0[in_ixyz[s0 + i]], in_row[s0 + i]);
+   }
+}
+
+// halo mirrors of nodes that were written AFTER the fused air kernel (boundary and source nodes sitting
+// at index 2 / N-3 of an axis): u[dst] = u[src] for a precomputed list; usually empty
+template <typename Real>
+__global__ void k_pairs(Real *__restrict__ u, const i64 *__restrict__ src, const i64 *__restrict__ dst, i64 i0, i64 n) {
+   const i64 i = i0 + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < i0 + n) u[dst[i]] = u[src[i]];
 }
 
 // ------------------------------------------------------------------------------------------------

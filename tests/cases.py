@@ -12,6 +12,9 @@ CASES = {
     "cart_ragged": (dict(Nx=19, Ny=41, Nz=131, Nt=40, nmat=1, mb=4), "cart"),
     "cart_wide": (dict(Nx=17, Ny=70, Nz=270, Nt=30, nmat=2, mb=2), "cart"),
     "cart_hann": (dict(Nx=22, Ny=22, Nz=22, Nt=60, nmat=1, mb=5, sig="hann10"), "cart"),
+    # walls one node from the absorbing shell: boundary nodes sit at index 2 / N-3 (late halo mirrors) and next to the shell
+    "cart_tight": (dict(Nx=21, Ny=23, Nz=34, Nt=80, nmat=2, mb=3, wall_offset=1), "cart"),
+    "cart_tight0": (dict(Nx=16, Ny=15, Nz=14, Nt=80, nmat=1, mb=2, wall_offset=0), "cart"),
     "fcc1_lossy": (dict(Nx=24, Ny=20, Nz=18, Nt=50, fcc=True, nmat=2, mb=3), "fcc1"),
     "fcc2_lossy": (dict(Nx=24, Ny=20, Nz=18, Nt=50, fcc=True, nmat=2, mb=3), "fcc2"),
     "fcc2_rigid": (dict(Nx=26, Ny=24, Nz=40, Nt=40, fcc=True, rigid=True), "fcc2"),
