@@ -153,14 +153,20 @@ __device__ __forceinline__ AirSeg air_segment(const AirJob &jb, int u, int u_end
 // Fused extras of the Cartesian step (all optional, `fuse` = 0 gives the plain masked air update):
 //  * the absorbing shell (cpu_engine.h:225-229): a node with Q = #{axes on which its index is 1 or
 //    N-2} > 0 becomes (v + lQ*u0_old)/(1.0 + lQ), v = the fresh air value (or the untouched old value
-//    of a masked node, exactly what the reference's ABC loop sees); lQ = l*Q in Real and
-//    den = 1.0 + lQ in DOUBLE are precomputed on the host with the reference's expressions;
+//    of a masked node, exactly what the reference's ABC loop sees).  The air kernel only STASHES u0_old of
+//    the shell nodes (it has it in registers; a list-driven gather would cost a DRAM line per node) and
+//    k_abc_faces finishes them; that keeps every row of the sweep equally cheap, which matters because
+//    the persistent partition assumes equal cost per tile-plane;
 //  * the halo mirrors (cpu_engine.h:145-172) are applied when a value is WRITTEN instead of before it is
 //    read: whoever stores index 2 (N-3) of an axis also stores it to index 0 (N-1).  The new state then
 //    leaves the kernel with its face halos complete and the next step needs no mirror pass.
 template <typename Real>
 struct AirEdge {
    int fuse, x_lo, x_hi, Nx;
+   // pre-update values of the shell nodes, for k_abc_faces:
+   Real *zold;  // [Nx][Ny][2]    z=1 / z=Nz-2 of every row
+   Real *yold;  // [Nx][2][Nzp]   rows y=1 / y=Ny-2
+   Real *xold;  // [2][Ny][Nzp]   planes x=1 / x=Nx-2 (global ends only)
    Real lQ1, lQ2, lQ3;
    double den1, den2, den3;     // 1.0 + lQ
    double rden1, rden2, rden3;  // RN(1/den)
@@ -205,6 +211,68 @@ __global__ void k_selftest_div(double b, double rb, unsigned long long seed, int
    if (nbad) atomicAdd(bad, nbad);
 }
 
+// The absorbing shell (cpu_engine.h:225-229) for the fused step.  The air kernel leaves the plain air value
+// in u0 and stashes the pre-update value of every shell node; this kernel finishes them,
+//     u0 = (u0 + lQ*old)/(1.0 + lQ),   lQ = l*Q,  Q = number of axes on which the index is 1 or N-2,
+// and repeats the halo mirror of every node it changes.  Thread classes over the planes [xb,xe):
+//   X: all interior nodes of the planes on the x shell            (old values in xold, coalesced)
+//   Y: rows y=1, y=Ny-2 of the other planes                       (old values in yold, coalesced)
+//   Z: z=1, z=Nz-2 of the remaining rows                          (old values in zold, one node per row end)
+template <typename Real>
+struct FacesArgs {
+   Real *u0;
+   const Real *zold, *yold, *xold;
+   int Nx, Ny, Nz, Nzp, xb, xe, x_lo, x_hi;
+   Real lQ1, lQ2, lQ3;
+};
+template <typename Real>
+__global__ void k_abc_faces(const FacesArgs<Real> a) {
+   typedef Ops<Real> O;
+   const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   const int nx = a.xe - a.xb;
+   const i64 nZ = (i64)nx * a.Ny * 2, nY = (i64)nx * 2 * a.Nz, nX = (i64)2 * a.Ny * a.Nz;
+   int x, y, z;
+   Real old;
+   auto on_xshell = [&](int xx) { return (a.x_lo && xx == 1) || (a.x_hi && xx == a.Nx - 2); };
+   if (t < nZ) {
+      const i64 row = t >> 1;
+      x = a.xb + (int)(row / a.Ny), y = (int)(row % a.Ny), z = (t & 1) ? a.Nz - 2 : 1;
+      if (y < 2 || y > a.Ny - 3 || on_xshell(x)) return;
+      old = a.zold[((i64)x * a.Ny + y) * 2 + (t & 1)];
+   } else if (t < nZ + nY) {
+      const i64 q = t - nZ;
+      const int side = (int)((q / a.Nz) & 1);
+      x = a.xb + (int)(q / (2 * (i64)a.Nz)), y = side ? a.Ny - 2 : 1, z = (int)(q % a.Nz);
+      if (z < 1 || z > a.Nz - 2 || on_xshell(x)) return;
+      old = a.yold[((i64)x * 2 + side) * a.Nzp + z];
+   } else if (t < nZ + nY + nX) {
+      const i64 q = t - nZ - nY;
+      const int side = (int)(q / ((i64)a.Ny * a.Nz));
+      x = side ? a.Nx - 2 : 1;
+      if (!(side ? a.x_hi : a.x_lo) || x < a.xb || x >= a.xe) return;
+      const i64 rq = q - (i64)side * a.Ny * a.Nz;
+      y = (int)(rq / a.Nz), z = (int)(rq % a.Nz);
+      if (y < 1 || y > a.Ny - 2 || z < 1 || z > a.Nz - 2) return;
+      old = a.xold[((i64)side * a.Ny + y) * a.Nzp + z];
+   } else {
+      return;
+   }
+   const int Q = (on_xshell(x) ? 1 : 0) + ((y == 1 || y == a.Ny - 2) ? 1 : 0) + ((z == 1 || z == a.Nz - 2) ? 1 : 0);
+   const Real lQ = Q == 1 ? a.lQ1 : (Q == 2 ? a.lQ2 : a.lQ3);
+   const i64 P = (i64)a.Ny * a.Nzp;
+   Real *p = a.u0 + ((i64)x * a.Ny + y) * a.Nzp + z;
+   const Real num = O::add(*p, O::mul(lQ, old));
+   const Real v = (Real)__ddiv_rn((double)num, __dadd_rn(1.0, (double)lQ));
+   *p = v;
+   // halo mirrors of the changed node (faces only; the 7-point stencil never reads halo edges)
+   if (z == 2) p[-2] = v;
+   if (z == a.Nz - 3) p[2] = v;
+   if (y == 2) p[-2 * (i64)a.Nzp] = v;
+   if (y == a.Ny - 3) p[2 * (i64)a.Nzp] = v;
+   if (a.x_lo && x == 2) p[-2 * P] = v;
+   if (a.x_hi && x == a.Nx - 3) p[2 * P] = v;
+}
+
 // ---------------------------------------------------------------- the kernel (7-point Cartesian)
 // full[s] flips when all bytes of a plane have landed in stage s, empty[s] when all NW consumer warps
 // are done with it.  Loads are numbered consecutively over all segments of the CTA; load i uses stage
@@ -240,14 +308,15 @@ __global__ void __maxnreg__(MAXR)
    if (w == NW) {
       // ---------------- producer
       if (lane == 0) {
-         int i = 0;
+         int s = 0;
+         uint32_t ph = 1u;  // parity of the "previous round released" phase; the first round needs no wait
+         bool first = true;
          for (int u = u_begin; u < u_end;) {
             const AirSeg sg = air_segment<C::TZ, C::TY>(jb, u, u_end);
-            for (int q = 0; q < sg.cnt + 2; q++, i++) {  // planes xa-1 .. xa+cnt
-               const int s = i % S;
+            for (int q = 0; q < sg.cnt + 2; q++) {  // planes xa-1 .. xa+cnt
                unsigned char *st = smem + s * C::STAGE_PITCH;
                const bool centre = q >= 1 && q <= sg.cnt;
-               if (i >= S) mbar_wait(&empty[s], (uint32_t)(((i / S) - 1) & 1));
+               if (!first) mbar_wait(&empty[s], ph);
                mbar_expect_tx(&full[s], centre ? C::U1_BYTES + C::U0_BYTES + C::MK_BYTES : C::U1_BYTES);
                const int x = sg.xa - 1 + q;
                tma_load_3d(st, &map_u1, &full[s], sg.z0 - VEC, sg.y0 - 1, x);
@@ -255,6 +324,7 @@ __global__ void __maxnreg__(MAXR)
                   tma_load_3d(st + C::U0_OFF, &map_u0, &full[s], sg.z0, sg.y0, x);
                   tma_load_3d(st + C::MK_OFF, &map_mk, &full[s], (sg.z0 >> 7) << 2, sg.y0, x);  // box start must be 16-byte aligned
                }
+               if (++s == S) s = 0, ph ^= 1u, first = false;
             }
             u = sg.next;
          }
@@ -263,18 +333,27 @@ __global__ void __maxnreg__(MAXR)
    }
 
    // ---------------- consumers
-   auto stage = [&](int i) -> const unsigned char * { return smem + (i % S) * C::STAGE_PITCH; };
-   auto wait_full = [&](int i) { mbar_wait(&full[i % S], (uint32_t)((i / S) & 1)); };
-   auto release = [&](int i) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[i % S]);
+   // ring position of a load: stage index and phase parity, advanced incrementally (no div/mod in the loop)
+   struct Ring {
+      int s;
+      uint32_t ph;
+      __device__ __forceinline__ void next() {
+         if (++s == S) s = 0, ph ^= 1u;
+      }
    };
-   const int soff = (w * RPT + 1) * BZ + VEC + VEC * lane;      // strip row 0 inside the u1 box (box row 0 is y0-1)
+   auto wait_full = [&](const Ring &g) { mbar_wait(&full[g.s], g.ph); };
+   auto release = [&](const Ring &g) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[g.s]);
+   };
+   auto stage = [&](const Ring &g) -> const unsigned char * { return smem + g.s * C::STAGE_PITCH; };
+   const int soff = (w * RPT + 1) * BZ + VEC + VEC * lane;  // strip row 0 inside the u1 box (box row 0 is y0-1)
    const int u0off = C::U0_OFF + ((w * RPT) * TZ + VEC * lane) * (int)sizeof(Real);
    const int mshift = (VEC * lane) & 31;
    const int Ny = jb.Ny, Nz = jb.Nz, Nzp = jb.Nzp;
+   const bool fuse = eg.fuse != 0;
 
-   int base = 0;  // load index of the segment's first plane
+   Ring g0{0, 0u};  // first plane of the current segment
    for (int u = u_begin; u < u_end;) {
       const AirSeg sg = air_segment<C::TZ, C::TY>(jb, u, u_end);
       u = sg.next;
@@ -285,39 +364,54 @@ __global__ void __maxnreg__(MAXR)
       int nrow = 0;  // active rows of the strip; vectors entirely in the far halo/padding are never touched
 #pragma unroll
       for (int r = 0; r < RPT; r++) nrow += (zv < Nz - 1 && (ybase + r) <= Ny - 2) ? 1 : 0;
-      // rows / lanes that need the slow path of the fused extras (details are recomputed there)
-      const bool fuse = eg.fuse != 0;
-      const bool zthread = fuse && (zv <= 2 || zv + VEC > Nz - 3);  // holds a z-shell node or a z-mirror source
-      unsigned yspec = 0;
+      // Roles of the fused step:
+      //   zlo_tile / zhi_tile (warp-uniform): the tile holds the low / high z end;
+      //   khs, khm (per thread): position of z=Nz-2 (shell) and z=Nz-3 (mirror source) in this vector, else -1;
+      //   yrole (per row, 3 bits each): bit0 row on the y shell, bit1 y==2, bit2 y==Ny-3 (mirror sources)
+      const bool zlo_tile = fuse && sg.z0 == 0;
+      const bool zhi_tile = fuse && sg.z0 + TZ > Nz - 3;
+      const int khs = (unsigned)(Nz - 2 - zv) < (unsigned)VEC ? Nz - 2 - zv : -1;
+      const int khm = (unsigned)(Nz - 3 - zv) < (unsigned)VEC ? Nz - 3 - zv : -1;
+      unsigned yrole = 0;
+      if (fuse) {
 #pragma unroll
-      for (int r = 0; r < RPT; r++) {
-         const int y = ybase + r;
-         yspec |= (fuse && (y <= 2 || y >= Ny - 3)) ? (1u << r) : 0u;
+         for (int r = 0; r < RPT; r++) {
+            const int y = ybase + r;
+            yrole |= (((y == 1 || y == Ny - 2) ? 1u : 0u) | (y == 2 ? 2u : 0u) | (y == Ny - 3 ? 4u : 0u)) << (3 * r);
+         }
       }
 
       Real um[RPT][VEC], uc[RPT][VEC], up[RPT][VEC];
-      wait_full(base);
+      Ring gc = g0;  // plane xa-1
+      wait_full(gc);
       {
-         const Real *s0 = (const Real *)stage(base) + soff;
+         const Real *s0 = (const Real *)stage(gc) + soff;
 #pragma unroll
          for (int r = 0; r < RPT; r++) ld_vec<Real, VEC>(s0 + r * BZ, um[r]);
       }
-      release(base);
-      wait_full(base + 1);
+      release(gc);
+      gc.next();  // plane xa: the first centre plane
+      wait_full(gc);
       {
-         const Real *s1 = (const Real *)stage(base + 1) + soff;
+         const Real *s1 = (const Real *)stage(gc) + soff;
 #pragma unroll
          for (int r = 0; r < RPT; r++) ld_vec<Real, VEC>(s1 + r * BZ, uc[r]);
       }
       Real *u0p = u0g + ((i64)sg.xa * Ny + ybase) * Nzp + zv;
+      Real *zop = eg.zold + ((i64)sg.xa * Ny + ybase) * 2;  // stash of the z-shell values of this strip's rows
 
       for (int j = 0; j < sg.cnt; j++) {
          const int x = sg.xa + j;
-         const bool xspec = fuse && ((eg.x_lo && x <= 2) || (eg.x_hi && x >= eg.Nx - 3));
-         wait_full(base + j + 2);
-         const unsigned char *stc = stage(base + j + 1);
+         // bit0 plane on the x shell, bit1 x==2, bit2 x==Nx-3 (mirror sources), only at the global x ends
+         const unsigned xrole = !fuse ? 0u
+                                      : ((((eg.x_lo && x == 1) || (eg.x_hi && x == eg.Nx - 2)) ? 1u : 0u) | ((eg.x_lo && x == 2) ? 2u : 0u) |
+                                         ((eg.x_hi && x == eg.Nx - 3) ? 4u : 0u));
+         Ring gu = gc;
+         gu.next();
+         wait_full(gu);
+         const unsigned char *stc = stage(gc);
          const Real *sc = (const Real *)stc + soff;
-         const Real *su = (const Real *)stage(base + j + 2) + soff;
+         const Real *su = (const Real *)stage(gu) + soff;
          Real rowm[VEC], rowp[VEC], zl[RPT], zr[RPT];
 #pragma unroll
          for (int r = 0; r < RPT; r++) ld_vec<Real, VEC>(su + r * BZ, up[r]);
@@ -351,83 +445,59 @@ __global__ void __maxnreg__(MAXR)
                   o[k] = ((m >> k) & 1u) ? u0v[k] : p;
                }
                Real *dst = u0p + (i64)r * Nzp;
-               if (!(zthread || xspec || ((yspec >> r) & 1u))) {
-                  if (m != VMASK) st_vec<Real, VEC>(dst, o);  // the common case
-               } else if (!(xspec || ((yspec >> r) & 1u))) {
-                  // only the z ends are special: this thread holds z=1 / z=Nz-2 (shell, Q = 1) and/or
-                  // z=2 / z=Nz-3 (mirror sources).  Kept lean: one lane of every edge warp comes through here.
-                  const int kl = 2 - zv, kh = Nz - 3 - zv;
-                  bool keep = m != VMASK;
+               const unsigned rrole = ((yrole >> (3 * r)) & 7u) | xrole;  // warp-uniform
+               // Fused extras.  Everything lane-dependent below is written as selects / single predicated stores:
+               // a divergent branch here would make the one lane at a z end run the rest of the step on its own.
+               const bool shell = (rrole & 1u) != 0;
+               if (shell) {
+                  // row / plane on the absorbing shell: keep the plain air value, stash the pre-update values for
+                  // k_abc_faces (one extra vector store; the planes on the x shell take precedence)
+                  Real *sp = (xrole & 1u) ? eg.xold + (((i64)(x == 1 ? 0 : 1) * Ny + (ybase + r)) * Nzp + zv)
+                                          : eg.yold + ((((i64)x * 2 + ((ybase + r) == 1 ? 0 : 1)) * Nzp) + zv);
+                  st_vec<Real, VEC>(sp, u0v);
+               }
+               if (zlo_tile) {  // warp-uniform: the tile starts at z = 0
+                  // lane 0 holds z=1 (shell): stash its pre-update value; z=2 -> z=0 mirror
+                  if (lane == 0 && !shell) zop[2 * r] = u0v[1];
+                  if constexpr (VEC >= 4) o[0] = (lane == 0) ? o[2] : o[0];
+               }
+               Real vm = o[0];  // value of z = Nz-3 if this thread holds it
+               if (zhi_tile) {  // warp-uniform: the tile contains z = Nz-3 .. Nz-1
+                  Real vs = u0v[0];
 #pragma unroll
-                  for (int k = 0; k < VEC; k++) {
-                     if (zv + k == 1 || zv + k == Nz - 2) {
-                        o[k] = abc_apply<Real>(o[k], u0v[k], eg.lQ1, eg.den1, eg.rden1);
-                        keep = true;
-                     }
+                  for (int k = 1; k < VEC; k++) {
+                     vs = (k == khs) ? u0v[k] : vs;
+                     vm = (k == khm) ? o[k] : vm;
                   }
+                  if (khs >= 0 && !shell) zop[2 * r + 1] = vs;  // z = Nz-2 (shell)
 #pragma unroll
-                  for (int k = 0; k < VEC; k++) {
-                     if (k >= 2 && k == kl) o[k - 2] = o[k];
-                     if (k + 2 < VEC && k == kh) o[k + 2] = o[k];
-                  }
-                  if (keep) {
-                     st_vec<Real, VEC>(dst, o);
-#pragma unroll
-                     for (int k = 0; k < VEC; k++) {
-                        if (k < 2 && k == kl) dst[k - 2] = o[k];
-                        if (k + 2 >= VEC && k == kh) dst[k + 2] = o[k];
-                     }
-                  }
-               } else {
-                  // rows / planes on the shell or next to a y / x halo (a vanishing share of the grid)
+                  for (int k = 0; k + 2 < VEC; k++) o[k + 2] = (k == khm) ? o[k] : o[k + 2];  // z=Nz-3 -> z=Nz-1 inside the vector
+               }
+               if (m != VMASK) {
+                  st_vec<Real, VEC>(dst, o);
+                  if (VEC < 4 && zlo_tile && lane == 1) dst[-2] = o[0];                  // fp64: z=2 sits in the second vector
+                  if (zhi_tile && khm >= 0 && khm + 2 >= VEC) dst[khm + 2] = vm;  // mirror target in the next vector
+               }
+               if (rrole & 6u) {
+                  // mirror source of a y / x halo: the same row goes there as well (warp-uniform, a few rows / planes)
                   const int y = ybase + r;
-                  const int kl = 2 - zv, kh = Nz - 3 - zv;
-                  const int qrow = (((eg.x_lo && x == 1) || (eg.x_hi && x == eg.Nx - 2)) ? 1 : 0) + ((y == 1 || y == Ny - 2) ? 1 : 0);
-                  const bool xmlo = eg.x_lo && x == 2, xmhi = eg.x_hi && x == eg.Nx - 3;
-                  bool keep = m != VMASK;
 #pragma unroll 1
-                  for (int k = 0; k < VEC; k++) {
-                     const int z = zv + k;
-                     const int Q = qrow + ((z == 1 || z == Nz - 2) ? 1 : 0);
-                     if (Q > 0 && z >= 1 && z <= Nz - 2) {
-                        const Real lQ = Q == 1 ? eg.lQ1 : (Q == 2 ? eg.lQ2 : eg.lQ3);
-                        const double den = Q == 1 ? eg.den1 : (Q == 2 ? eg.den2 : eg.den3);
-                        const double rden = Q == 1 ? eg.rden1 : (Q == 2 ? eg.rden2 : eg.rden3);
-                        Real v = o[0], old = u0v[0];
-#pragma unroll
-                        for (int kk = 1; kk < VEC; kk++)
-                           if (kk == k) v = o[kk], old = u0v[kk];
-                        v = abc_apply<Real>(v, old, lQ, den, rden);
-#pragma unroll
-                        for (int kk = 0; kk < VEC; kk++)
-                           if (kk == k) o[kk] = v;
-                        keep = true;
-                     }
-                  }
-#pragma unroll
-                  for (int k = 0; k < VEC; k++) {
-                     if (k >= 2 && k == kl) o[k - 2] = o[k];
-                     if (k + 2 < VEC && k == kh) o[k + 2] = o[k];
-                  }
-                  // the row itself, then the same row into the y / x halos it is the mirror source of
-#pragma unroll 1
-                  for (int t = 0; t < 5; t++) {
-                     const bool on = t == 0 ? keep : t == 1 ? (y == 2) : t == 2 ? (y == Ny - 3) : t == 3 ? xmlo : xmhi;
+                  for (int t = 1; t < 5; t++) {
+                     const bool on = t == 1 ? y == 2 : t == 2 ? y == Ny - 3 : t == 3 ? (xrole & 2u) != 0 : (xrole & 4u) != 0;
                      if (on) {
-                        Real *d = dst + (t == 1 ? -2 * (i64)Nzp : t == 2 ? 2 * (i64)Nzp : t == 3 ? -2 * jb.plane : t == 4 ? 2 * jb.plane : 0);
+                        Real *d = dst + (t == 1 ? -2 * (i64)Nzp : t == 2 ? 2 * (i64)Nzp : t == 3 ? -2 * jb.plane : 2 * jb.plane);
                         st_vec<Real, VEC>(d, o);
-#pragma unroll
-                        for (int k = 0; k < VEC; k++) {
-                           if (k < 2 && k == kl) d[k - 2] = o[k];
-                           if (k + 2 >= VEC && k == kh) d[k + 2] = o[k];
-                        }
+                        if (VEC < 4 && zlo_tile && lane == 1) d[-2] = o[0];
+                        if (zhi_tile && khm >= 0 && khm + 2 >= VEC) d[khm + 2] = vm;
                      }
                   }
                }
             }
          }
-         release(base + j + 1);  // plane x's stage may be refilled; x-1 and x+1 live in registers / the next stage
+         release(gc);  // plane x's stage may be refilled; x-1 and x+1 live in registers / the next stage
+         gc = gu;
          u0p += jb.plane;
+         zop += 2 * Ny;
 #pragma unroll
          for (int r = 0; r < RPT; r++) {
 #pragma unroll
@@ -437,8 +507,9 @@ __global__ void __maxnreg__(MAXR)
             }
          }
       }
-      release(base + sg.cnt + 1);  // the last plane was only ever an "x+1" plane
-      base += sg.cnt + 2;
+      release(gc);  // the last plane was only ever an "x+1" plane
+      g0 = gc;
+      g0.next();
    }
 }
 
@@ -449,19 +520,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 // tile configurations (id, rows per thread, consumer warps, stages, register cap); cfg 0 is the default
 #define PF_AIR_CONFIGS(X) \
-   X(0, 2, 8, 4, 72)      \
-   X(1, 4, 8, 3, 112)     \
-   X(2, 1, 8, 4, 56)      \
-   X(3, 1, 16, 4, 56)     \
-   X(4, 2, 4, 4, 80)      \
-   X(5, 2, 8, 3, 72)      \
-   X(6, 2, 8, 5, 72)      \
-   X(7, 2, 16, 3, 56)     \
-   X(8, 2, 7, 4, 80)      \
-   X(9, 2, 7, 4, 64)      \
-   X(10, 1, 15, 4, 64)    \
-   X(11, 2, 7, 3, 80)
-#define PF_AIR_NCFG 12
+   X(0, 1, 15, 4, 64)     \
+   X(1, 2, 8, 4, 72)      \
+   X(2, 2, 8, 6, 112)     \
+   X(3, 1, 15, 6, 64)     \
+   X(4, 4, 8, 3, 112)     \
+   X(5, 1, 11, 6, 80)     \
+   X(6, 2, 12, 4, 72)     \
+   X(7, 1, 8, 6, 80)
+#define PF_AIR_NCFG 8
 
 template <typename Real>
 static int air_tma_attr(int cfg) {

@@ -115,6 +115,7 @@ struct pffdtd_engine {
    void *ssaf = nullptr, *beta = nullptr, *quads = nullptr, *insig = nullptr, *uout = nullptr;
    void *hist[2] = {nullptr, nullptr}, *u2ba = nullptr, *vh1 = nullptr, *gh1 = nullptr;
    void *lo2Kbg = nullptr, *facb = nullptr;  // per lossy node constants (k_fd_prep)
+   void *zold = nullptr, *yold = nullptr, *xold = nullptr;  // pre-update values of the shell nodes (fused step)
    uint16_t *matmb = nullptr;                // per lossy node: material | Mb << 8
    int serial_src = 0;
    // fused Cartesian step (tiled air kernel applies the ABC shell and mirrors the halos on write)
@@ -330,6 +331,9 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    if (dalloc_bytes(e, &e->lo2Kbg, (size_t)e->Nbl * e->rs)) return PFFDTD_ECUDA;
    if (dalloc_bytes(e, &e->facb, (size_t)e->Nbl * e->rs)) return PFFDTD_ECUDA;
    if (dalloc(e, &e->matmb, (size_t)e->Nbl)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->zold, (size_t)(e->Nx * e->Ny * 2) * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->yold, (size_t)(e->Nx * 2 * e->Nzp) * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->xold, (size_t)(2 * e->Ny * e->Nzp) * e->rs)) return PFFDTD_ECUDA;
    CU(cudaMallocHost(&e->h_in, std::max<size_t>((size_t)e->Ns * 8, 64)));
    CU(cudaMallocHost(&e->h_out, std::max<size_t>((size_t)e->Nr * 8, 64)));
 
@@ -600,6 +604,7 @@ struct Step {
          pf::AirEdge<Real> eg;
          memset(&eg, 0, sizeof eg);
          eg.fuse = fused, eg.x_lo = e->x_lo_edge, eg.x_hi = e->x_hi_edge, eg.Nx = (int)e->Nx;
+         eg.zold = (Real *)e->zold, eg.yold = (Real *)e->yold, eg.xold = (Real *)e->xold;
          // cpu_engine.h:226-228: Real lQ = l*Q; ... /(1.0 + lQ)
          eg.lQ1 = (Real)((Real)e->l * (Real)1), eg.lQ2 = (Real)((Real)e->l * (Real)2), eg.lQ3 = (Real)((Real)e->l * (Real)3);
          eg.den1 = 1.0 + (double)eg.lQ1, eg.den2 = 1.0 + (double)eg.lQ2, eg.den3 = 1.0 + (double)eg.lQ3;
@@ -616,6 +621,17 @@ struct Step {
       }
       e->launches += 1;
       if (timed) CU(cudaEventRecord(ev->b, s));
+      if (fused && e->air_kernel == 1) {
+         // the absorbing shell, from the values the air kernel stashed (see k_abc_faces)
+         pf::FacesArgs<Real> fa;
+         fa.u0 = u0, fa.zold = (const Real *)e->zold, fa.yold = (const Real *)e->yold, fa.xold = (const Real *)e->xold;
+         fa.Nx = (int)e->Nx, fa.Ny = (int)e->Ny, fa.Nz = (int)e->Nz, fa.Nzp = (int)e->Nzp, fa.xb = (int)xb, fa.xe = (int)xe;
+         fa.x_lo = e->x_lo_edge, fa.x_hi = e->x_hi_edge;
+         fa.lQ1 = (Real)((Real)e->l * (Real)1), fa.lQ2 = (Real)((Real)e->l * (Real)2), fa.lQ3 = (Real)((Real)e->l * (Real)3);
+         const i64 nt = (xe - xb) * e->Ny * 2 + (xe - xb) * 2 * e->Nz + 2 * e->Ny * e->Nz;
+         pf::k_abc_faces<Real><<<nblk(nt, 256), 256, 0, s>>>(fa);
+         e->launches += 1;
+      }
       return 0;
    }
    // steps 4-9 for one part, in the reference's order: air, ABC, rigid, FD, receivers/sources, late mirrors
