@@ -94,14 +94,16 @@ def sort(files: dict) -> dict:
     """ascending node lists + out_reorder (rotate_sim_data.py:131-189)"""
     f = copy.copy(files)
     v, m = dict(f["vox_out"]), dict(f["comms_out"])
-    k = np.argsort(v["bn_ixyz"], kind="stable")
+    # the same numpy calls as the reference (default sort kind), so that ties between receiver nodes that share
+    # a grid node come out in the same order
+    k = np.argsort(v["bn_ixyz"])
     for n in ("bn_ixyz", "adj_bn", "mat_bn", "saf_bn"):
         v[n] = np.ascontiguousarray(v[n][k])
-    k = np.argsort(m["in_ixyz"], kind="stable")
+    k = np.argsort(m["in_ixyz"])
     m["in_ixyz"], m["in_sigs"] = m["in_ixyz"][k], np.ascontiguousarray(m["in_sigs"][k])
-    k = np.argsort(m["out_ixyz"], kind="stable")
+    k = np.argsort(m["out_ixyz"])
     m["out_ixyz"] = m["out_ixyz"][k]
-    m["out_reorder"] = np.argsort(k, kind="stable").astype(np.int64)
+    m["out_reorder"] = np.argsort(k).astype(np.int64)
     f["vox_out"], f["comms_out"] = v, m
     return f
 

@@ -1,0 +1,68 @@
+"""Host-side plumbing for the slab decomposition: one process per GPU (torchrun), `torch.distributed` only for
+the bootstrap (sharing the NCCL unique id) and for collecting the receiver rows at the end.  The per-step
+halo exchange itself happens inside libpffdtd_b200.so (ncclSend/ncclRecv on the engine's streams), replacing the
+reference's single-process cudaMemcpyPeerAsync waves (c_cuda/gpu_engine.h:1086-1126)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def dist_env():
+    """(rank, world_size, local_rank) from the torchrun environment, (0, 1, 0) when run plainly"""
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init(backend="gloo"):
+    """join the default process group if WORLD_SIZE > 1 and nobody did yet; returns torch.distributed or None"""
+    rank, world, _ = dist_env()
+    if world == 1:
+        return None
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        dist.init_process_group(backend, rank=rank, world_size=world)
+    return dist
+
+
+def broadcast_bytes(payload, src=0):
+    """`payload` (bytes) from rank `src` to everyone"""
+    dist = init()
+    if dist is None:
+        return payload
+    box = [payload if dist.get_rank() == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def gather_rows(u: np.ndarray) -> np.ndarray:
+    """concatenate each rank's receiver rows in rank order (== the sorted receiver order of the whole grid,
+    because slabs are contiguous in x and the lists are sorted, gpu_engine.h:562-661)"""
+    dist = init()
+    if dist is None:
+        return u
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, u)
+    return np.concatenate(parts, axis=0)
+
+
+def exchange_planes(send_lo, send_hi, rank, world):
+    """CPU stand-in of the halo exchange, used by the gloo tests with the oracle as the per-rank engine:
+    send plane 1 down / plane Nx-2 up, receive the neighbours' into plane Nx-1 / 0.  Returns (from_lo, from_hi)."""
+    import torch
+    dist = init()
+    from_lo = from_hi = None
+    reqs = []
+    if rank > 0:
+        t = torch.from_numpy(np.ascontiguousarray(send_lo))
+        r = torch.empty_like(t)
+        reqs += [dist.isend(t, rank - 1), dist.irecv(r, rank - 1)]
+        from_lo = r
+    if rank < world - 1:
+        t2 = torch.from_numpy(np.ascontiguousarray(send_hi))
+        r2 = torch.empty_like(t2)
+        reqs += [dist.isend(t2, rank + 1), dist.irecv(r2, rank + 1)]
+        from_hi = r2
+    for q in reqs:
+        q.wait()
+    return (None if from_lo is None else from_lo.numpy()), (None if from_hi is None else from_hi.numpy())

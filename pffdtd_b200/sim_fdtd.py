@@ -24,13 +24,9 @@ from pathlib import Path
 
 import numpy as np
 
-from . import folder_prep
+from . import parallel
 from .engine import Engine, comm_unique_id
 from .sim_data import SimData
-
-
-def _dist_env():
-    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
 class SimEngine:
@@ -39,7 +35,7 @@ class SimEngine:
         if energy_on:
             raise NotImplementedError("the energy balance (sim_fdtd.py:587-620) is not part of the GPU step yet")
         self.precision = int(precision)
-        self.rank, self.world, local = _dist_env()
+        self.rank, self.world, local = parallel.dist_env()
         self.device = local if device is None else int(device)
         self.scale = scale
         self.quiet = quiet or self.rank != 0
@@ -87,12 +83,8 @@ class SimEngine:
         pass  # SimData.from_arrays and pffdtd_create validate the description
 
     def _comm_init(self):
-        import torch.distributed as dist
-        if not dist.is_initialized():
-            dist.init_process_group("gloo", rank=self.rank, world_size=self.world)
-        box = [comm_unique_id() if self.rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        self.eng.comm_init(box[0], self.rank, self.world)
+        uid = parallel.broadcast_bytes(comm_unique_id() if self.rank == 0 else None, src=0)
+        self.eng.comm_init(uid, self.rank, self.world)
 
     # ---- running ----------------------------------------------------------------------------------
     def run_steps(self, nstart, nsteps):
@@ -112,12 +104,7 @@ class SimEngine:
         self._collect()
 
     def _collect(self):
-        u = self.eng.read_outputs(0, self.Nt)
-        if self.world > 1:
-            import torch.distributed as dist
-            parts = [None] * self.world
-            dist.all_gather_object(parts, u)
-            u = np.concatenate(parts, axis=0)  # rank order == sorted receiver order
+        u = parallel.gather_rows(self.eng.read_outputs(0, self.Nt))  # rank order == sorted receiver order
         if self.scale:
             u = self.sd_full.rescale_output(u)  # fdtd_data.h:912-925
         self.u_out = u

@@ -1,0 +1,75 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/pffdtd_b200.h declares; the ctypes
+mirror of pffdtd_desc has the C layout; without a CUDA device the product fails loudly (no CPU fallback)."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from cases import make_sim_data
+from pffdtd_b200 import engine
+from pffdtd_b200.sim_data import pffdtd_desc
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "pffdtd_b200.h").read_text()
+
+
+def declared_functions():
+    names = re.findall(r"^\s*(?:const\s+)?(?:int|char|void)\s*\*?\s*(pffdtd_\w+)\s*\(", HEADER, flags=re.M)
+    assert len(names) >= 15
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol():
+    L = engine.lib()
+    for fn in declared_functions():
+        assert hasattr(L, fn), f"{fn} declared in the header but not exported"
+    assert b"sm_100a" in L.pffdtd_version()
+
+
+def test_desc_layout_matches_the_header():
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "pffdtd_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(pffdtd_desc), ' \
+          'offsetof(pffdtd_desc, Nx), offsetof(pffdtd_desc, ix0), offsetof(pffdtd_desc, mat_quads));return 0;}\n'
+    tmp = Path(subprocess.run(["mktemp", "-d"], capture_output=True, text=True).stdout.strip())
+    (tmp / "t.c").write_text(src)
+    subprocess.run(["/usr/bin/gcc", "-I", str(ROOT / "include"), str(tmp / "t.c"), "-o", str(tmp / "t")], check=True)
+    size, o_nx, o_ix0, o_quads = map(int, subprocess.run([str(tmp / "t")], capture_output=True, text=True).stdout.split())
+    assert C.sizeof(pffdtd_desc) == size
+    assert pffdtd_desc.Nx.offset == o_nx and pffdtd_desc.ix0.offset == o_ix0 and pffdtd_desc.mat_quads.offset == o_quads
+
+
+def test_kernels_are_sm_100a_tma_code():
+    """the shipped library holds sm_100a SASS with TMA tensor loads (UTMALDG) for the air kernel"""
+    out = subprocess.run(["cuobjdump", "-sass", str(engine.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "UTMALDG" in out and "k_air_tma_cart" in out
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU behaviour")
+def test_no_gpu_means_an_error_not_a_fallback():
+    sd = make_sim_data("cart_rigid", 2)
+    with pytest.raises(engine.PffdtdError) as ei:
+        engine.Engine(sd)
+    assert ei.value.code == engine.ECUDA
+    with pytest.raises(engine.PffdtdError):
+        engine.run_sim(sd)
+
+
+def test_bad_descriptions_are_rejected_before_touching_the_device():
+    sd = make_sim_data("cart_rigid", 2)
+    d = sd.desc()
+    d.struct_size = 8
+    h = C.c_void_p()
+    assert engine.lib().pffdtd_create(C.byref(d), 0, C.byref(h)) == engine.EINVAL
+    assert b"size mismatch" in engine.lib().pffdtd_last_error()
+    d = sd.desc()
+    d.precision = 3
+    assert engine.lib().pffdtd_create(C.byref(d), 0, C.byref(h)) == engine.EINVAL

@@ -134,3 +134,19 @@ def test_constant_divisor_division_is_exact(precision):
     for l in (0.999 / np.sqrt(3.0), 0.5, 0.3141592653589793, 0.57):
         _check(L.pffdtd_selftest(0, float(l), precision, 100_000_000, C.byref(bad)))
         assert bad.value == 0, f"l={l}: {bad.value} mismatches"
+
+
+@pytest.mark.parametrize("name,precision", (("cart_lossy_mb11", 1), ("cart_ragged", 2), ("fcc2_lossy", 1), ("fcc1_lossy", 2)))
+def test_folder_in_sim_outs_out_equals_reference_files(tmp_path, name, precision):
+    """the drop-in contract end to end: four .h5 files in (chunked + deflate, as sim_setup writes them),
+    sim_outs.h5 out, equal to what the unmodified reference CPU engine wrote for the same folder"""
+    from pathlib import Path
+    from cases import make_files
+    from pffdtd_b200 import h5lite, shoebox
+    from pffdtd_b200.sim_fdtd import run_folder
+    gold = np.load(Path(__file__).parent / "golden" / "traces_ref_cpu_engine.npz")[f"{name}_p{precision}"]
+    shoebox.write_folder(make_files(name), tmp_path, compress=3)
+    u = run_folder(tmp_path, precision=precision)
+    assert np.array_equal(u, gold)
+    on_disk = h5lite.File(tmp_path / "sim_outs.h5")["u_out"][...]
+    assert on_disk.dtype == np.float64 and np.array_equal(on_disk, gold)

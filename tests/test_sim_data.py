@@ -1,0 +1,108 @@
+"""Host prep (pffdtd_b200/sim_data.py) vs the unmodified reference loader (load_sim_data + scale_input,
+c_cuda/fdtd_data.h:99-718, 879-909), field by field and bit for bit; plus the slab partition rules."""
+import tempfile
+
+import numpy as np
+import pytest
+
+from cases import CASES, make_files, make_sim_data
+from oracle import Reference
+from pffdtd_b200 import shoebox
+from pffdtd_b200.sim_data import SimData, abc_count, abc_nodes
+
+needs_ref = pytest.mark.skipif(not Reference.available(), reason="oracle/_ref not built and /root/reference absent")
+
+ARRAYS = ("bn_ixyz", "bnl_ixyz", "bna_ixyz", "Q_bna", "in_ixyz", "out_ixyz", "out_reorder", "adj_bn", "ssaf_bnl", "mat_bnl",
+          "Mb", "mat_beta", "in_sigs")
+SCALARS = ("Nx", "Ny", "Nz", "Nt", "l", "l2", "a1", "a2", "sl2", "lo2", "infac")
+
+
+@needs_ref
+@pytest.mark.parametrize("precision", (1, 2))
+@pytest.mark.parametrize("name", ("cart_lossy_mb11", "cart_tight", "cart_ragged", "fcc1_lossy", "fcc2_lossy", "fcc2_rigid"))
+def test_fields_equal_reference_loader(name, precision, capfd):
+    files = make_files(name)
+    d = tempfile.mkdtemp(prefix="sd_")
+    shoebox.write_folder(files, d)
+    ref = Reference(precision, files, d)
+    ref.L.refdrv_scale_input()
+    sd = SimData.load(d, precision).scale_input()  # through the on-disk .h5 files
+    capfd.readouterr()
+    for f in SCALARS:
+        assert float(getattr(sd, f)) == float(ref.field(f)), f
+    for f in ARRAYS:
+        a, b = np.asarray(getattr(sd, f)).ravel(), ref.field(f).ravel()
+        assert a.shape == b.shape and np.array_equal(a.astype(b.dtype), b), f
+    q = ref.field("mat_quads").reshape(-1, 12, 4)
+    assert np.array_equal(sd.mat_quads.astype(q.dtype), q)
+    assert np.array_equal(sd.K_bn, ref.field("K_bn"))
+    assert np.array_equal(sd.bn_mask, ref.field("bn_mask"))
+
+
+@pytest.mark.parametrize("dims", ((9, 8, 7), (20, 18, 16), (5, 5, 5), (12, 31, 6)))
+@pytest.mark.parametrize("fcc_flag", (0, 1))
+def test_abc_shell_count_and_structure(dims, fcc_flag):
+    Nx, Ny, Nz = dims
+    if fcc_flag and (Nx % 2 or Ny % 2 or Nz % 2):
+        pytest.skip("FCC grids have even dims")
+    bna, Q = abc_nodes(Nx, Ny, Nz, fcc_flag)
+    assert bna.size == abc_count(Nx, Ny, Nz, fcc_flag) == Q.size
+    ix, iy, iz = bna // (Ny * Nz), (bna // Nz) % Ny, bna % Nz
+    q = ((ix == 1) | (ix == Nx - 2)).astype(int) + ((iy == 1) | (iy == Ny - 2)) + ((iz == 1) | (iz == Nz - 2))
+    assert np.array_equal(q, Q) and Q.min() >= 1 and np.unique(bna).size == bna.size
+    lo, hi = abc_nodes(Nx, Ny, Nz, fcc_flag, ix_range=(0, Nx // 2)), abc_nodes(Nx, Ny, Nz, fcc_flag, ix_range=(Nx // 2, Nx))
+    assert np.array_equal(np.concatenate([lo[0], hi[0]]), bna) and np.array_equal(np.concatenate([lo[1], hi[1]]), Q)
+
+
+def test_scale_input_is_a_power_of_two_over_the_peak():
+    for p, want in ((1, 4.0), (2, 4.0)):
+        sd = make_sim_data("cart_lossy", p, scale=False)
+        peak = np.abs(sd.in_sigs).max()
+        sd.scale_input()
+        assert np.isclose(np.abs(sd.in_sigs).max(), want) and np.isclose(sd.infac, peak / want)
+
+
+@pytest.mark.parametrize("nranks", (2, 3, 5))
+def test_slab_partition_covers_everything_once(nranks):
+    sd = make_sim_data("cart_lossy_mb11", 2).sorted()
+    starts, sizes = SimData.slab_planes(sd.Nx, nranks)
+    assert sum(sizes) == sd.Nx and starts[0] == 0 and max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    P = sd.Ny * sd.Nz
+    seen = {k: [] for k in ("bn_ixyz", "bnl_ixyz", "bna_ixyz", "in_ixyz", "out_ixyz")}
+    for r in range(nranks):
+        s = sd.slab(r, nranks)
+        assert s.Nx == sizes[r] + (r > 0) + (r < nranks - 1)
+        assert s.x_lo_edge == (r == 0) and s.x_hi_edge == (r == nranks - 1) and s.ix0 == starts[r] - (r > 0)
+        for k in seen:
+            a = getattr(s, k)
+            if a.size:
+                assert a.min() >= P and a.max() < (s.Nx - 1) * P or k == "out_ixyz"
+            seen[k].append(a + s.ix0 * P)
+        assert s.in_sigs.shape == (s.Ns, sd.Nt) and s.adj_bn.size == s.Nb and s.Q_bna.size == s.Nba
+    for k, parts in seen.items():
+        assert np.array_equal(np.concatenate(parts), getattr(sd, k)), k
+
+
+def test_slab_needs_sorted_lists_and_enough_planes():
+    sd = make_sim_data("cart_lossy", 2)
+    shuffled = make_sim_data("cart_lossy", 2)
+    shuffled.bn_ixyz = shuffled.bn_ixyz[::-1].copy()
+    with pytest.raises(ValueError):
+        shuffled.slab(0, 2)
+    with pytest.raises(ValueError):
+        sd.sorted().slab(0, sd.Nx)
+
+
+def test_inconsistent_inputs_are_rejected():
+    files = make_files("cart_lossy")
+    v = dict(files["vox_out"])
+    v["adj_bn"] = np.ones_like(v["adj_bn"])  # a "boundary" node with all links open
+    with pytest.raises(ValueError):
+        shoebox.sim_data_from_files(dict(files, vox_out=v), 2)
+    c = dict(files["sim_consts"])
+    c["l"], c["l2"] = np.float64(0.9), np.float64(0.81)  # above the Cartesian CFL limit
+    with pytest.raises(ValueError):
+        shoebox.sim_data_from_files(dict(files, sim_consts=c), 2)
+    m = dict(files["comms_out"], diff=np.int8(0))
+    with pytest.raises(ValueError):
+        shoebox.sim_data_from_files(dict(files, comms_out=m), 1)  # fp32 needs a differentiated source
