@@ -48,13 +48,19 @@ WORKLOADS = {
     "small": dict(N=(128, 96, 64), precision=1, fcc=False, nmat=1, mb=11, rigid=False, desc="smoke-sized shoebox"),
 }
 BYTES_PER_NODE = {1: 12.125, 2: 24.125}  # u1 read + u0 read + u0 write + 1 mask bit
+# CPU-arm sample grids for workloads whose full grid would take the CPU engine minutes per step
+CPU_SAMPLE_GRID = {
+    "c5": ((258, 2048, 1024), "one of the eight x-slabs of the c5 grid (256 planes + 2 halo planes, 258x2048x1024)"),
+    "c4": ((130, 1024, 1024), "one eighth of the c4 grid (130x1024x1024)"),
+}
 
 
-def build_problem(wl, Nt):
+def build_problem(wl, Nt, x_range=None):
     from pffdtd_b200 import folder_prep, shoebox
     w = WORKLOADS[wl]
     Nx, Ny, Nz = w["N"]
-    files = shoebox.make_shoebox(Nx, Ny, Nz, Nt, fcc=w["fcc"], nmat=w["nmat"], mb=max(w["mb"], 1), rigid=w["rigid"], diff=True)
+    files = shoebox.make_shoebox(Nx, Ny, Nz, Nt, fcc=w["fcc"], nmat=w["nmat"], mb=max(w["mb"], 1), rigid=w["rigid"], diff=True,
+                                 x_range=x_range)
     if w["fcc"]:
         files = folder_prep.gpu_folder(files)
     return files
@@ -124,7 +130,13 @@ def run_reference_cpu(wl, steps, warmup, budget_s=120.0, threads=None):
     from oracle import Reference
     w = WORKLOADS[wl]
     cores = threads or os.cpu_count() or 1
-    Npts = int(np.prod(w["N"])) // (2 if w["fcc"] else 1)
+    sample_note = f"the full {wl} grid"
+    if wl in CPU_SAMPLE_GRID:  # the grid is too large for a CPU run of a few minutes: time one slab of it
+        WORKLOADS[wl + "_cpu_sample"] = dict(w, N=CPU_SAMPLE_GRID[wl][0])
+        sample_note = CPU_SAMPLE_GRID[wl][1]
+        wl = wl + "_cpu_sample"
+        w = WORKLOADS[wl]
+    Npts = int(np.prod(w["N"]))
     if w["fcc"]:
         Npts = w["N"][0] * (w["N"][1] // 2 + 1) * w["N"][2]
     # bound the sample: assume >= 0.15 Gvox/s to size it, then report what was actually run
@@ -149,7 +161,7 @@ def run_reference_cpu(wl, steps, warmup, budget_s=120.0, threads=None):
         os.dup2(saved, 1)
         os.close(devnull)
         os.close(saved)
-    return Npts * k / t_run / 1e9, cores, k, t_run, "reference"
+    return Npts * k / t_run / 1e9, cores, k, t_run, "reference", sample_note
 
 
 def main():
@@ -183,12 +195,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        v, cores, k, t, kind = run_reference_cpu(wl, K, W)
+        v, cores, k, t, kind, note = run_reference_cpu(wl, K, W)
         line = {"impl": "reference", "metric": "Gvoxel-updates/s", "value": v, "unit": "Gvox/s", "n_gpus": N, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * t / k, "higher_is_better": True, "scaling": "strong" if N > 1 else "weak", "vs_baseline": None,
                 "dtype": "f32" if w["precision"] == 1 else "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "Gvox/s", "cores": cores, "kind": kind,
-                                 "sample": f"{k} time steps of the full {wl} grid (of the {K} requested), unmodified c_cuda/cpu_engine.h run_sim, OpenMP"},
+                                 "sample": f"{k} time steps (of the {K} requested) on {note}, unmodified c_cuda/cpu_engine.h run_sim, OpenMP {cores} threads"},
                 "e2e": {"value": v, "unit": "Gvox/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line), flush=True)
         return
@@ -206,8 +218,15 @@ def main():
 
     Nt = W + K
     t_prep = time.perf_counter()
-    files = build_problem(wl, Nt)
-    sd_full = shoebox.sim_data_from_files(files, w["precision"]).scale_input()
+    # a rank only generates the boundary / shell nodes of its own slab (+ halo planes): the node lists of the
+    # 2048x2048x1024 grid have 5e7 entries
+    xr = None
+    if world > 1 and not w["fcc"]:
+        from pffdtd_b200.sim_data import SimData
+        starts, sizes = SimData.slab_planes(Nx, world)
+        xr = (max(0, starts[rank] - 1), min(Nx, starts[rank] + sizes[rank] + 1))
+    files = build_problem(wl, Nt, x_range=xr)
+    sd_full = shoebox.sim_data_from_files(files, w["precision"], abc_x_range=xr).scale_input()
     del files
     sd = sd_full.slab(rank, world) if world > 1 else sd_full
     eng = Engine(sd, local)
@@ -295,9 +314,9 @@ def main():
     # ---- the reference's CPU engine on this box's cores (rank 0, N=1 only)
     if rank == 0 and N == 1 and not args.no_cpu:
         try:
-            v, cores, k, t, kind = run_reference_cpu(wl, 40, 3, budget_s=25.0)
+            v, cores, k, t, kind, note = run_reference_cpu(wl, 40, 3, budget_s=25.0)
             line["cpu_baseline"] = {"value": v, "unit": "Gvox/s", "cores": cores, "kind": kind,
-                                    "sample": f"{k} time steps of the full {wl} grid, unmodified c_cuda/cpu_engine.h run_sim, OpenMP {cores} threads, {t:.1f} s"}
+                                    "sample": f"{k} time steps on {note}, unmodified c_cuda/cpu_engine.h run_sim, OpenMP {cores} threads, {t:.1f} s"}
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "Gvox/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex!r}"}
     if rank == 0:

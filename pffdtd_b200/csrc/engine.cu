@@ -62,10 +62,13 @@ struct Id128 {
 static Nccl g_nccl;
 static int nccl_load() {
    if (g_nccl.lib) return 0;
+   // Prefer an NCCL that is already in the process (the host's torch brings its own and must not get a second,
+   // older one forced on it); never export its symbols (RTLD_LOCAL).
    const char *names[] = {getenv("PFFDTD_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
-   void *h = nullptr;
+   void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_LOCAL);
    for (const char *n : names) {
-      if (n && *n && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+      if (h) break;
+      if (n && *n) h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
    }
    if (!h) return fail(PFFDTD_ENCCL, "cannot load libnccl.so.2 (set PFFDTD_NCCL_LIB): %s", dlerror());
 #define SYM(field, name)                                                                      \

@@ -77,7 +77,25 @@ def _check(rc):
         raise PffdtdError(rc, lib().pffdtd_last_error().decode(errors="replace"))
 
 
+def _prefer_torch_nccl():
+    """The library binds NCCL at run time.  When torch is in the process its bundled libnccl must be the one (and
+    must be loaded first): a different libnccl.so.2 loaded earlier would break `import torch`."""
+    if os.environ.get("PFFDTD_NCCL_LIB"):
+        return
+    try:
+        import torch  # noqa: F401  (loads libtorch_cuda and with it the bundled NCCL)
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            cand = Path(list(spec.submodule_search_locations)[0]) / "lib" / "libnccl.so.2"
+            if cand.exists():
+                os.environ["PFFDTD_NCCL_LIB"] = str(cand)
+    except Exception:  # noqa: BLE001 -- no torch: the system NCCL is used
+        pass
+
+
 def comm_unique_id() -> bytes:
+    _prefer_torch_nccl()
     buf = C.create_string_buffer(128)
     _check(lib().pffdtd_comm_unique_id(buf))
     return buf.raw
@@ -117,6 +135,7 @@ class Engine:
 
     # -- configuration
     def comm_init(self, uid: bytes, rank: int, nranks: int):
+        _prefer_torch_nccl()
         buf = C.create_string_buffer(uid, 128)
         _check(self.L.pffdtd_comm_init(self.h, buf, rank, nranks))
 

@@ -19,9 +19,11 @@ def init(backend="gloo"):
     rank, world, _ = dist_env()
     if world == 1:
         return None
+    import datetime
     import torch.distributed as dist
     if not dist.is_initialized():
-        dist.init_process_group(backend, rank=rank, world_size=world)
+        dist.init_process_group(backend, rank=rank, world_size=world,
+                                timeout=datetime.timedelta(seconds=int(os.environ.get("PFFDTD_DIST_TIMEOUT", "600"))))
     return dist
 
 

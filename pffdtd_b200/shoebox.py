@@ -64,11 +64,14 @@ def _boundary_nodes(N, lo, hi, offs, fcc):
     return lin, ~cut, ins, c
 
 
-def _cart_boundary_fast(N, lo, hi):
-    """same result as _boundary_nodes for the Cartesian scheme, built face by face (large grids)"""
+def _cart_boundary_fast(N, lo, hi, x_range=None):
+    """same result as _boundary_nodes for the Cartesian scheme, built face by face (large grids);
+    `x_range=(x0,x1)` keeps only the nodes of planes x0 <= ix < x1 (one rank's slab of a huge grid)"""
     Nx, Ny, Nz = N
     idx, clr, ins = [], [], []
+    x0, x1 = (0, Nx) if x_range is None else x_range
     r = [np.arange(lo[a], hi[a] + 1, dtype=np.int64) for a in range(3)]
+    r[0] = r[0][(r[0] >= x0) & (r[0] < x1)]
     strides = (Ny * Nz, Nz, 1)
     for a in range(3):
         o1, o2 = [b for b in range(3) if b != a]
@@ -77,9 +80,12 @@ def _cart_boundary_fast(N, lo, hi):
         for side, (pin, pout) in enumerate(((lo[a], lo[a] - 1), (hi[a], hi[a] + 1))):
             toward_out = 2 * a + (1 if side == 0 else 0)     # bit of the cut link seen from inside
             toward_in = 2 * a + (0 if side == 0 else 1)
-            idx.append(face + pin * strides[a]); clr.append(np.full(face.size, 1 << toward_out, np.uint16)); ins.append(np.ones(face.size, bool))
-            if 1 <= pout <= N[a] - 2:
+            if a != 0 or x0 <= pin < x1:
+                idx.append(face + pin * strides[a]); clr.append(np.full(face.size, 1 << toward_out, np.uint16)); ins.append(np.ones(face.size, bool))
+            if 1 <= pout <= N[a] - 2 and (a != 0 or x0 <= pout < x1):
                 idx.append(face + pout * strides[a]); clr.append(np.full(face.size, 1 << toward_in, np.uint16)); ins.append(np.zeros(face.size, bool))
+    if not idx:
+        return np.zeros(0, np.int64), np.zeros((0, 6), bool), np.zeros(0, bool)
     idx, clr, ins = np.concatenate(idx), np.concatenate(clr), np.concatenate(ins)
     k = np.argsort(idx, kind="stable")
     idx, clr, ins = idx[k], clr[k], ins[k]
@@ -92,7 +98,7 @@ def _cart_boundary_fast(N, lo, hi):
 
 
 def make_shoebox(Nx, Ny, Nz, Nt, *, fcc=False, wall_offset=3, nmat=1, mb=11, rigid=False, diff=True,
-                 h=0.05, c=343.0, nrec=3, sig="impulse", fast=None):
+                 h=0.05, c=343.0, nrec=3, sig="impulse", fast=None, x_range=None):
     """-> dict of the four files' datasets: {'sim_consts': {...}, 'vox_out': {...}, 'comms_out': {...}, 'sim_mats': {...}}"""
     N = (int(Nx), int(Ny), int(Nz))
     w = int(wall_offset)
@@ -108,8 +114,10 @@ def make_shoebox(Nx, Ny, Nz, Nt, *, fcc=False, wall_offset=3, nmat=1, mb=11, rig
     offs = FCC_OFFS if fcc else CART_OFFS
     if fast is None:
         fast = not fcc
+    if x_range is not None and (fcc or not fast):
+        raise ValueError("x_range needs the fast Cartesian builder")
     if fast and not fcc:
-        bn, adj, ins = _cart_boundary_fast(N, lo, hi)
+        bn, adj, ins = _cart_boundary_fast(N, lo, hi, x_range)
     else:
         bn, adj, ins, _ = _boundary_nodes(N, lo, hi, offs, fcc)
     k = np.argsort(bn, kind="stable")
@@ -196,7 +204,7 @@ def write_folder(files: dict, data_dir, compress=None):
     return d
 
 
-def sim_data_from_files(files: dict, precision: int):
+def sim_data_from_files(files: dict, precision: int, abc_x_range=None):
     """SimData straight from the in-memory dict (skips the disk round trip for large benchmarks)"""
     from .sim_data import SimData
     c, v, m, t = files["sim_consts"], files["vox_out"], files["comms_out"], files["sim_mats"]
@@ -204,4 +212,5 @@ def sim_data_from_files(files: dict, precision: int):
     return SimData.from_arrays(precision, fcc_flag=c["fcc_flag"], Nx=v["Nx"], Ny=v["Ny"], Nz=v["Nz"], l=c["l"], l2=c["l2"],
                                Ts=c["Ts"], bn_ixyz=v["bn_ixyz"], adj_bn=v["adj_bn"], mat_bn=v["mat_bn"], saf_bn=v["saf_bn"],
                                in_ixyz=m["in_ixyz"], out_ixyz=m["out_ixyz"], out_reorder=m["out_reorder"], in_sigs=m["in_sigs"],
-                               Mb=t["Mb"], DEF=[t[f"mat_{i:02d}_DEF"] for i in range(nm)], diff=bool(m["diff"]))
+                               Mb=t["Mb"], DEF=[t[f"mat_{i:02d}_DEF"] for i in range(nm)], diff=bool(m["diff"]),
+                               abc_x_range=abc_x_range)

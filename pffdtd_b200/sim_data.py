@@ -174,8 +174,10 @@ class SimData:
     # ---- construction
     @classmethod
     def from_arrays(cls, precision, *, fcc_flag, Nx, Ny, Nz, l, l2, Ts, bn_ixyz, adj_bn, mat_bn, saf_bn,
-                    in_ixyz, out_ixyz, out_reorder, in_sigs, Mb, DEF, diff=True):
-        """Everything load_sim_data derives, from the raw file contents."""
+                    in_ixyz, out_ixyz, out_reorder, in_sigs, Mb, DEF, diff=True, abc_x_range=None):
+        """Everything load_sim_data derives, from the raw file contents.
+        `abc_x_range=(x0,x1)` builds the absorbing-shell list for those planes only (a rank that will keep just
+        its slab of a very large grid need not enumerate the whole shell)."""
         R = real_dtype(precision)
         fcc_flag = int(fcc_flag)
         if not 0 <= fcc_flag <= 2:
@@ -256,8 +258,8 @@ class SimData:
             beta[i] = acc
         if lossy.any() and int(mat_bn.max()) >= Nm:
             raise ValueError("material id out of range")
-        bna, Q = abc_nodes(Nx, Ny, Nz, fcc_flag)
-        assert bna.size == abc_count(Nx, Ny, Nz, fcc_flag)
+        bna, Q = abc_nodes(Nx, Ny, Nz, fcc_flag, ix_range=abc_x_range)
+        assert abc_x_range is not None or bna.size == abc_count(Nx, Ny, Nz, fcc_flag)
         in_sigs = np.ascontiguousarray(in_sigs, np.float64)
         in_ixyz = np.ascontiguousarray(in_ixyz, np.int64)
         Nt = int(in_sigs.shape[1]) if in_sigs.ndim == 2 else 0

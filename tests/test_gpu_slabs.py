@@ -79,9 +79,16 @@ def test_multi_gpu_nccl_halo_exchange(tmp_path, name, precision, overlap):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     procs = []
     for r in range(world):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   PFFDTD_DIST_TIMEOUT="60")
         procs.append(subprocess.Popen([sys.executable, str(script), str(tmp_path / "data"), str(precision), str(overlap), str(tmp_path / "u.npy")],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
-    logs = [p.communicate(timeout=600)[0] for p in procs]
+    logs = []
+    try:
+        logs = [p.communicate(timeout=120)[0] for p in procs]
+    finally:
+        for p in procs:  # never leave a rank behind (a hung rank would hold the GPU box until the outer timeout)
+            if p.poll() is None:
+                p.kill()
     assert all(p.returncode == 0 for p in procs), "\n".join(logs)
     assert np.array_equal(np.load(tmp_path / "u.npy"), GOLD[f"{name}_p{precision}"])
