@@ -42,9 +42,10 @@ struct AirTma {
    void *base[2] = {nullptr, nullptr};
    void *mask = nullptr;
    int cfg = 0;         // tile configuration, see PF_AIR_CONFIGS
-   int xc = 0;          // planes per x-chunk of the work order, 0 = automatic
+   int xc = 0;          // planes per (long) x-chunk of the work order, 0 = default
    int sm_count = 148;
    int slots = 0;       // resident CTAs of the chosen configuration on this device
+   int *ctr = nullptr;  // device: {next item, CTAs done}, zero between launches
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -115,36 +116,34 @@ struct AirCfg {
    static constexpr int U0_OFF = (U1_BYTES + 127) / 128 * 128;
    static constexpr int MK_OFF = U0_OFF + U0_BYTES;
    static constexpr int STAGE_PITCH = (MK_OFF + MK_BYTES + 127) / 128 * 128;
-   static constexpr int SMEM_BYTES = S * STAGE_PITCH + 2 * S * 8 + 128;
+   static constexpr int SMEM_BYTES = S * STAGE_PITCH + 2 * S * 8 + S * 16 + 128;  // stages, full/empty barriers, item headers
    static constexpr int THREADS = (NW + 1) * 32;  // NW consumer warps + 1 TMA producer warp
 };
 
 // ---------------------------------------------------------------- work decomposition
-// The job "planes [x_begin, x_begin+n) x all y-z tiles" is cut into units of one tile-plane, ordered
-// (x-chunk of XC planes, tile, plane in chunk), and every CTA of a persistent grid (one CTA per
-// resident slot) takes an equal contiguous range of units: all CTAs finish together (no tail), and CTAs
-// running at the same time work on the same x-chunk of neighbouring tiles, so tile halos hit in L2.
-// A CTA's range is a few "segments" (one tile, consecutive planes); each costs two extra u1 plane loads.
+// The job "planes [x_begin, x_begin+n) x all y-z tiles" is cut into ITEMS = (x-chunk, tile): consecutive planes
+// of one tile.  A persistent grid (one CTA per resident slot) pulls items from an atomic counter, in the order
+// (chunk, tile): CTAs running at the same time work on neighbouring tiles of the same x-chunk, so tile halos
+// hit in L2.  Chunks get shorter towards the end of the job (guided self-scheduling), so that all CTAs finish
+// within a few planes of each other whatever the per-tile cost; every item costs two extra u1 plane loads.
+#define PF_AIR_MAXCH 96
 struct AirJob {
-   int x_begin, n, XC, tz, tiles;  // n planes, tiles = tz*ty
-   int units;                      // n * tiles
+   int x_begin, n, tz, tiles;  // n planes, tiles = tz*ty
+   int nch, n_items;           // chunks, items = nch*tiles
    int Ny, Nz, Nzp;
-   i64 plane;  // Ny*Nzp
+   i64 plane;                  // Ny*Nzp
+   int *ctr;                   // {next item, CTAs done}; left at {0,0} by the last CTA
+   short bounds[PF_AIR_MAXCH + 1];  // chunk k covers planes [bounds[k], bounds[k+1]) of the job
 };
 struct AirSeg {
-   int xa, cnt, z0, y0, next;  // next = first unit after the segment
+   int xa, cnt, z0, y0;
 };
 template <int TZ, int TY>
-__device__ __forceinline__ AirSeg air_segment(const AirJob &jb, int u, int u_end) {
-   const int per_chunk = jb.XC * jb.tiles;
-   const int k = u / per_chunk;
-   const int len = min(jb.XC, jb.n - k * jb.XC);
-   const int up = u - k * per_chunk;
-   const int t = up / len, p = up - t * len;
+__device__ __forceinline__ AirSeg air_item(const AirJob &jb, int item) {
+   const int k = item / jb.tiles, t = item - k * jb.tiles;
    AirSeg s;
-   s.next = min(u_end, k * per_chunk + (t + 1) * len);
-   s.cnt = s.next - u;
-   s.xa = jb.x_begin + k * jb.XC + p;
+   s.xa = jb.x_begin + jb.bounds[k];
+   s.cnt = jb.bounds[k + 1] - jb.bounds[k];
    s.z0 = (t % jb.tz) * TZ;
    s.y0 = 1 + (t / jb.tz) * TY;
    return s;
@@ -291,9 +290,9 @@ __global__ void __maxnreg__(MAXR)
    uint64_t *full = (uint64_t *)(smem + S * C::STAGE_PITCH);
    uint64_t *empty = full + S;
 
+   int4 *hdr = (int4 *)(empty + S);  // per stage: the item (xa, cnt, z0, y0) whose first plane it holds; cnt < 0 = stop
+
    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-   const int u_begin = (int)((i64)jb.units * blockIdx.x / gridDim.x), u_end = (int)((i64)jb.units * (blockIdx.x + 1) / gridDim.x);
-   if (u_end <= u_begin) return;
 
    if (tid == 0) {
       for (int s = 0; s < S; s++) {
@@ -306,27 +305,43 @@ __global__ void __maxnreg__(MAXR)
    __syncthreads();
 
    if (w == NW) {
-      // ---------------- producer
+      // ---------------- producer: fetch items, stream their planes
       if (lane == 0) {
          int s = 0;
          uint32_t ph = 1u;  // parity of the "previous round released" phase; the first round needs no wait
          bool first = true;
-         for (int u = u_begin; u < u_end;) {
-            const AirSeg sg = air_segment<C::TZ, C::TY>(jb, u, u_end);
-            for (int q = 0; q < sg.cnt + 2; q++) {  // planes xa-1 .. xa+cnt
+         for (;;) {
+            const int item = atomicAdd(&jb.ctr[0], 1);
+            const bool stop = item >= jb.n_items;
+            AirSeg sg = {0, -1, 0, 0};
+            if (!stop) sg = air_item<C::TZ, C::TY>(jb, item);
+            const int nq = stop ? 1 : sg.cnt + 2;  // planes xa-1 .. xa+cnt, or the stop marker
+            for (int q = 0; q < nq; q++) {
                unsigned char *st = smem + s * C::STAGE_PITCH;
-               const bool centre = q >= 1 && q <= sg.cnt;
                if (!first) mbar_wait(&empty[s], ph);
-               mbar_expect_tx(&full[s], centre ? C::U1_BYTES + C::U0_BYTES + C::MK_BYTES : C::U1_BYTES);
-               const int x = sg.xa - 1 + q;
-               tma_load_3d(st, &map_u1, &full[s], sg.z0 - VEC, sg.y0 - 1, x);
-               if (centre) {
-                  tma_load_3d(st + C::U0_OFF, &map_u0, &full[s], sg.z0, sg.y0, x);
-                  tma_load_3d(st + C::MK_OFF, &map_mk, &full[s], (sg.z0 >> 7) << 2, sg.y0, x);  // box start must be 16-byte aligned
+               if (q == 0) hdr[s] = make_int4(sg.xa, sg.cnt, sg.z0, sg.y0);
+               if (stop) {
+                  mbar_arrive(&full[s]);
+               } else {
+                  const bool centre = q >= 1 && q <= sg.cnt;
+                  mbar_expect_tx(&full[s], centre ? C::U1_BYTES + C::U0_BYTES + C::MK_BYTES : C::U1_BYTES);
+                  const int x = sg.xa - 1 + q;
+                  tma_load_3d(st, &map_u1, &full[s], sg.z0 - VEC, sg.y0 - 1, x);
+                  if (centre) {
+                     tma_load_3d(st + C::U0_OFF, &map_u0, &full[s], sg.z0, sg.y0, x);
+                     tma_load_3d(st + C::MK_OFF, &map_mk, &full[s], (sg.z0 >> 7) << 2, sg.y0, x);  // box start must be 16-byte aligned
+                  }
                }
                if (++s == S) s = 0, ph ^= 1u, first = false;
             }
-            u = sg.next;
+            if (stop) break;
+         }
+         // the last CTA out re-arms the counters for the next launch
+         __threadfence();
+         if (atomicAdd(&jb.ctr[1], 1) == (int)gridDim.x - 1) {
+            jb.ctr[0] = 0;
+            jb.ctr[1] = 0;
+            __threadfence();
          }
       }
       return;
@@ -353,10 +368,12 @@ __global__ void __maxnreg__(MAXR)
    const int Ny = jb.Ny, Nz = jb.Nz, Nzp = jb.Nzp;
    const bool fuse = eg.fuse != 0;
 
-   Ring g0{0, 0u};  // first plane of the current segment
-   for (int u = u_begin; u < u_end;) {
-      const AirSeg sg = air_segment<C::TZ, C::TY>(jb, u, u_end);
-      u = sg.next;
+   Ring g0{0, 0u};  // first plane of the current item
+   for (;;) {
+      wait_full(g0);
+      const int4 h = hdr[g0.s];
+      if (h.y < 0) break;  // stop marker
+      const AirSeg sg = {h.x, h.y, h.z, h.w};
       // this thread's strip: rows y0 + w*RPT + r, columns z0 + VEC*lane .. +VEC-1
       const int zv = sg.z0 + VEC * lane;
       const int ybase = sg.y0 + w * RPT;
@@ -382,8 +399,7 @@ __global__ void __maxnreg__(MAXR)
       }
 
       Real um[RPT][VEC], uc[RPT][VEC], up[RPT][VEC];
-      Ring gc = g0;  // plane xa-1
-      wait_full(gc);
+      Ring gc = g0;  // plane xa-1 (already waited for)
       {
          const Real *s0 = (const Real *)stage(gc) + soff;
 #pragma unroll
@@ -456,10 +472,19 @@ __global__ void __maxnreg__(MAXR)
                                           : eg.yold + ((((i64)x * 2 + ((ybase + r) == 1 ? 0 : 1)) * Nzp) + zv);
                   st_vec<Real, VEC>(sp, u0v);
                }
+               // Mirror targets that live in ANOTHER active lane's vector are delivered by a shuffle (that lane stores
+               // its whole vector; a scalar store from here would race with it); only a target in a vector nobody
+               // stores (the row's far padding) is written directly.
+               const unsigned am = __activemask();  // the lanes of this warp whose vector holds interior nodes
                if (zlo_tile) {  // warp-uniform: the tile starts at z = 0
                   // lane 0 holds z=1 (shell): stash its pre-update value; z=2 -> z=0 mirror
                   if (lane == 0 && !shell) zop[2 * r] = u0v[1];
-                  if constexpr (VEC >= 4) o[0] = (lane == 0) ? o[2] : o[0];
+                  if constexpr (VEC >= 4) {
+                     o[0] = (lane == 0) ? o[2] : o[0];
+                  } else {
+                     const Real t = __shfl_down_sync(am, o[0], 1);  // fp64: z=2 is the first element of lane 1
+                     o[0] = (lane == 0) ? t : o[0];
+                  }
                }
                Real vm = o[0];  // value of z = Nz-3 if this thread holds it
                if (zhi_tile) {  // warp-uniform: the tile contains z = Nz-3 .. Nz-1
@@ -472,11 +497,13 @@ __global__ void __maxnreg__(MAXR)
                   if (khs >= 0 && !shell) zop[2 * r + 1] = vs;  // z = Nz-2 (shell)
 #pragma unroll
                   for (int k = 0; k + 2 < VEC; k++) o[k + 2] = (k == khm) ? o[k] : o[k + 2];  // z=Nz-3 -> z=Nz-1 inside the vector
+                  // a vector that starts at z=Nz-2 holds z=Nz-1 as element 1 and finds z=Nz-3 at the end of the previous lane's
+                  const Real t = __shfl_up_sync(am, o[VEC - 1], 1);
+                  o[1] = (khs == 0) ? t : o[1];
                }
                if (m != VMASK) {
                   st_vec<Real, VEC>(dst, o);
-                  if (VEC < 4 && zlo_tile && lane == 1) dst[-2] = o[0];                  // fp64: z=2 sits in the second vector
-                  if (zhi_tile && khm >= 0 && khm + 2 >= VEC) dst[khm + 2] = vm;  // mirror target in the next vector
+                  if (zhi_tile && khm + 2 == VEC) dst[VEC] = vm;  // z=Nz-1 opens the next vector, which nobody stores
                }
                if (rrole & 6u) {
                   // mirror source of a y / x halo: the same row goes there as well (warp-uniform, a few rows / planes)
@@ -487,8 +514,7 @@ __global__ void __maxnreg__(MAXR)
                      if (on) {
                         Real *d = dst + (t == 1 ? -2 * (i64)Nzp : t == 2 ? 2 * (i64)Nzp : t == 3 ? -2 * jb.plane : 2 * jb.plane);
                         st_vec<Real, VEC>(d, o);
-                        if (VEC < 4 && zlo_tile && lane == 1) d[-2] = o[0];
-                        if (zhi_tile && khm >= 0 && khm + 2 >= VEC) d[khm + 2] = vm;
+                        if (zhi_tile && khm + 2 == VEC) d[VEC] = vm;
                      }
                   }
                }
@@ -520,10 +546,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 // tile configurations (id, rows per thread, consumer warps, stages, register cap); cfg 0 is the default
 #define PF_AIR_CONFIGS(X) \
-   X(0, 1, 15, 4, 64)     \
+   X(0, 1, 15, 6, 64)     \
    X(1, 2, 8, 4, 72)      \
    X(2, 2, 8, 6, 112)     \
-   X(3, 1, 15, 6, 64)     \
+   X(3, 1, 15, 4, 64)     \
    X(4, 4, 8, 3, 112)     \
    X(5, 1, 11, 6, 80)     \
    X(6, 2, 12, 4, 72)     \
@@ -637,14 +663,30 @@ static int air_tma_launch_cfg(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real
    jb.tz = (int)((t->Nz - 1 + C::TZ - 1) / C::TZ);  // vectors starting at z >= Nz-1 hold no interior node
    const int ty = (int)((t->Ny - 2 + C::TY - 1) / C::TY);
    jb.tiles = jb.tz * ty;
-   jb.XC = std::min(jb.n, t->xc > 0 ? t->xc : 64);
-   const i64 units = (i64)jb.n * jb.tiles;
-   if (units > 0x7fffffff) return (int)cudaErrorInvalidValue;
-   jb.units = (int)units;
    jb.Ny = (int)t->Ny, jb.Nz = (int)t->Nz, jb.Nzp = (int)t->Nzp;
    jb.plane = t->Ny * t->Nzp;
-   // one CTA per resident slot, but never less than ~8 tile-planes per CTA
-   const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>(t->slots, units / 8));
+   jb.ctr = t->ctr;
+   if (jb.n > 32767) return (int)cudaErrorInvalidValue;
+   // chunk lengths: chunks of xc planes (default 16) for most of the job, then halving down to 4, so that the
+   // items handed out last are small
+   {
+      const int xc = std::max(4, t->xc > 0 ? t->xc : 16);
+      int k = 0, x = 0;
+      jb.bounds[0] = 0;
+      const int tail_from = jb.n - std::min(jb.n / 4, 2 * xc);
+      while (x < jb.n && k < PF_AIR_MAXCH - 1) {
+         int len = xc;
+         if (x >= tail_from) len = std::max(4, std::min(xc, (jb.n - x + 1) / 2));
+         if (k == PF_AIR_MAXCH - 2) len = jb.n - x;
+         x = std::min(jb.n, x + len);
+         jb.bounds[++k] = (short)x;
+      }
+      jb.nch = k;
+   }
+   const i64 items = (i64)jb.nch * jb.tiles;
+   if (items > 0x7fffffff) return (int)cudaErrorInvalidValue;
+   jb.n_items = (int)items;
+   const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>(t->slots, items));
    kern<<<grid, C::THREADS, C::SMEM_BYTES, s>>>(t->map_u1[cur], t->map_u0[cur ^ 1], t->map_mk, u0, jb, a1, a2, eg);
    return (int)cudaGetLastError();
 }

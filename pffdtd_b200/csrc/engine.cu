@@ -432,6 +432,7 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
       if (e->Nb) pf::k_mask_nodes<<<(unsigned)((e->Nb + 255) / 256), 256, 0, e->s_main>>>(e->mask, e->bn, e->Nb, e->Nzp, e->mwpr);
       CU(cudaGetLastError());
    }
+   if (dalloc(e, &e->tma.ctr, 2)) return PFFDTD_ECUDA;
    if ((rc = pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask))) {
       // not fatal: fall back to the generic kernel, remember why
       e->air_kernel = 0;

@@ -15,6 +15,11 @@ CASES = {
     # walls one node from the absorbing shell: boundary nodes sit at index 2 / N-3 (late halo mirrors) and next to the shell
     "cart_tight": (dict(Nx=21, Ny=23, Nz=34, Nt=80, nmat=2, mb=3, wall_offset=1), "cart"),
     "cart_tight0": (dict(Nx=16, Ny=15, Nz=14, Nt=80, nmat=1, mb=2, wall_offset=0), "cart"),
+    # every alignment of the high z end inside a 16-byte vector (fp32: Nz mod 4, fp64: Nz mod 2), > 1 z tile
+    "cart_nz_a": (dict(Nx=16, Ny=21, Nz=133, Nt=40, nmat=1, mb=2), "cart"),
+    "cart_nz_b": (dict(Nx=16, Ny=19, Nz=134, Nt=40, nmat=1, mb=2), "cart"),
+    "cart_nz_c": (dict(Nx=16, Ny=18, Nz=135, Nt=40, nmat=1, mb=2), "cart"),
+    "cart_nz_d": (dict(Nx=16, Ny=20, Nz=68, Nt=40, nmat=1, mb=2), "cart"),
     "fcc1_lossy": (dict(Nx=24, Ny=20, Nz=18, Nt=50, fcc=True, nmat=2, mb=3), "fcc1"),
     "fcc2_lossy": (dict(Nx=24, Ny=20, Nz=18, Nt=50, fcc=True, nmat=2, mb=3), "fcc2"),
     "fcc2_rigid": (dict(Nx=26, Ny=24, Nz=40, Nt=40, fcc=True, rigid=True), "fcc2"),

@@ -42,7 +42,8 @@ def test_traces_bit_exact(name, precision):
 
 
 @pytest.mark.parametrize("precision", (2, 1))
-@pytest.mark.parametrize("name", ("cart_lossy", "cart_ragged", "fcc1_lossy", "fcc2_lossy"))
+@pytest.mark.parametrize("name", ("cart_lossy", "cart_ragged", "cart_tight", "cart_tight0", "cart_nz_a", "cart_nz_b", "cart_nz_c", "cart_nz_d",
+                                  "fcc1_lossy", "fcc2_lossy"))
 def test_full_state_bit_exact_from_noise(name, precision):
     """whole grids + boundary ODE state after 25 steps from a random initial state: exercises every
     interior node, the halo mirrors, the ABC shell and the lossy walls at once"""
