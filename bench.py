@@ -298,8 +298,16 @@ def main():
     n_air_per_step = max(1.0, air_n / K)
     air_ms_per_step = air_ms / K
     achieved = BYTES_PER_NODE[w["precision"]] * nodes_per_launch / (air_ms_per_step * 1e-3) / 1e9 if air_ms > 0 else None
+    traffic = None
+    try:  # DRAM bytes per launch of this kernel from the committed ncu --set full capture of the same workload
+        tr = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(wl)
+        if tr and args.air_kernel == 1 and world == 1:
+            traffic = tr["traffic_bytes"]
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "hbm", "kernel": "k_air_tma_cart" if args.air_kernel == 1 and not w["fcc"] else "k_air_generic",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "algorithmic_bytes_per_launch": BYTES_PER_NODE[w["precision"]] * nodes_per_launch,
                 "peak_source": peak_src, "bytes_per_node": BYTES_PER_NODE[w["precision"]], "nodes_per_launch": int(nodes_per_launch),
                 "air_ms_per_step": air_ms_per_step, "air_launches_per_step": n_air_per_step, "air_share_of_step": air_ms_per_step / (ms / K)}
 
