@@ -285,8 +285,10 @@ __global__ void __maxnreg__(MAXR)
    typedef Ops<Real> O;
    constexpr int VEC = C::VEC, BZ = C::BZ, TZ = C::TZ;
    constexpr uint32_t VMASK = (1u << VEC) - 1u;
-   extern __shared__ unsigned char smem_raw[];
-   unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+   // no integer round trip on this pointer: it must stay a SHARED-space pointer so that the tile reads compile to
+   // LDS (a pointer rebuilt from an integer becomes generic: LD.E with 64-bit address arithmetic).  There is no
+   // static shared memory in this kernel, so the dynamic window starts at offset 0 of the CTA's shared memory.
+   extern __shared__ __align__(1024) unsigned char smem[];
    uint64_t *full = (uint64_t *)(smem + S * C::STAGE_PITCH);
    uint64_t *empty = full + S;
 
