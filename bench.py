@@ -216,7 +216,7 @@ def main():
     from pffdtd_b200 import shoebox
     from pffdtd_b200.engine import Engine, comm_unique_id
 
-    Nt = W + K
+    Nt = W + 2 * K  # warm-up, the timed K steps, the K steps of the roofline pass
     t_prep = time.perf_counter()
     # a rank only generates the boundary / shell nodes of its own slab (+ halo planes): the node lists of the
     # 2048x2048x1024 grid have 5e7 entries
@@ -251,14 +251,21 @@ def main():
     sampler = ClockSampler(nvml_index(local))
     sampler.start()
     eng.reset_stats()
-    eng.set_option("profile_air", 1)
     eng.stat("timer_start")
     eng.run_steps(W, K)
     ms = eng.stat("timer_stop_ms")
     barrier()
+    launches = eng.stat("launches")
+    # roofline pass: the next K steps with CUDA events around every air launch (events cannot sit inside the
+    # replayed CUDA graph of the pass above, so this pass launches kernel by kernel; same kernels, same data)
+    eng.set_option("profile_air", 1)
+    eng.reset_stats()
+    eng.stat("timer_start")
+    eng.run_steps(W + K, K)
+    ms_prof = eng.stat("timer_stop_ms")
+    barrier()
     eng.set_option("profile_air", 0)
     clocks = sampler.result()
-    launches = eng.stat("launches")
     air_ms = eng.stat("air_ms")
     air_n = eng.stat("air_launches_timed")
     if dist is not None:
@@ -309,7 +316,9 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "algorithmic_bytes_per_launch": BYTES_PER_NODE[w["precision"]] * nodes_per_launch,
                 "peak_source": peak_src, "bytes_per_node": BYTES_PER_NODE[w["precision"]], "nodes_per_launch": int(nodes_per_launch),
-                "air_ms_per_step": air_ms_per_step, "air_launches_per_step": n_air_per_step, "air_share_of_step": air_ms_per_step / (ms / K)}
+                "air_ms_per_step": air_ms_per_step, "air_launches_per_step": n_air_per_step, "air_share_of_step": air_ms_per_step / (ms_prof / K),
+                "note": "air launches timed with CUDA events in a second pass of K steps launched kernel by kernel (%.4f ms/step); "
+                        "the `value` pass replays the step as a CUDA graph when it can" % (ms_prof / K)}
 
     line = {"metric": "Gvoxel-updates/s", "value": value, "unit": "Gvox/s", "n_gpus": N, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "strong" if N > 1 else "weak", "vs_baseline": None,

@@ -227,9 +227,12 @@ struct FacesArgs {
 template <typename Real>
 __global__ void k_abc_faces(const FacesArgs<Real> a) {
    typedef Ops<Real> O;
-   const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
    const int nx = a.xe - a.xb;
    const i64 nZ = (i64)nx * a.Ny * 2, nY = (i64)nx * 2 * a.Nz, nX = (i64)2 * a.Ny * a.Nz;
+   // descending x within each class: the planes the air kernel wrote last are still in L2
+   i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+   if (t < nZ) t = nZ - 1 - t;
+   else if (t < nZ + nY) t = nZ + (nY - 1 - (t - nZ));
    int x, y, z;
    Real old;
    auto on_xshell = [&](int xx) { return (a.x_lo && xx == 1) || (a.x_hi && xx == a.Nx - 2); };

@@ -121,6 +121,12 @@ struct pffdtd_engine {
    void *zold = nullptr, *yold = nullptr, *xold = nullptr;  // pre-update values of the shell nodes (fused step)
    uint16_t *matmb = nullptr;                // per lossy node: material | Mb << 8
    int serial_src = 0;
+   i64 *d_n = nullptr;   // device step counter read by k_io / k_fd
+   i64 n_dev = -1;       // value the host knows it holds (-1 unknown)
+   cudaGraphExec_t graph[2] = {nullptr, nullptr};  // two consecutive steps starting with cur = 0 / 1
+   double graph_launches[2] = {0, 0};
+   int use_graph = 1;
+   i64 steps_plain = 0;  // steps launched kernel by kernel so far
    // fused Cartesian step (tiled air kernel applies the ABC shell and mirrors the halos on write)
    int fuse_ok = 0;     // the ABC list is the canonical full shell, so the air kernel may apply it
    int halo_dirty = 0;  // u1's halos were not produced by mirror-on-write: run the mirror kernels first
@@ -239,6 +245,8 @@ extern "C" int pffdtd_destroy(pffdtd_engine *e) {
       cudaEventDestroy(p.a);
       cudaEventDestroy(p.b);
    }
+   for (int c = 0; c < 2; c++)
+      if (e->graph[c]) cudaGraphExecDestroy(e->graph[c]);
    if (e->ev_edge) cudaEventDestroy(e->ev_edge);
    if (e->ev_comm) cudaEventDestroy(e->ev_comm);
    if (e->ev_step) cudaEventDestroy(e->ev_step);
@@ -433,6 +441,7 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
       CU(cudaGetLastError());
    }
    if (dalloc(e, &e->tma.ctr, 2)) return PFFDTD_ECUDA;
+   if (dalloc(e, &e->d_n, 1)) return PFFDTD_ECUDA;
    if ((rc = pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask))) {
       // not fatal: fall back to the generic kernel, remember why
       e->air_kernel = 0;
@@ -487,7 +496,16 @@ extern "C" int pffdtd_comm_init(pffdtd_engine *e, const void *id128, int rank, i
 extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t value) {
    if (!e || !key) return fail(PFFDTD_EINVAL, "NULL argument");
    std::string k(key);
-   if (k == "air_kernel") {
+   // any option may change what a step launches: drop the captured graphs
+   for (int c = 0; c < 2; c++)
+      if (e->graph[c]) {
+         cudaGraphExecDestroy(e->graph[c]);
+         e->graph[c] = nullptr;
+      }
+   e->steps_plain = 0;
+   if (k == "use_graph") {
+      e->use_graph = value != 0;
+   } else if (k == "air_kernel") {
       if (value == 1 && !e->tma.ok) return fail(PFFDTD_ESTATE, "tiled air kernel unavailable: %s", e->tma.why.c_str());
       if (value < 0 || value > 1) return fail(PFFDTD_EINVAL, "air_kernel must be 0 or 1");
       e->air_kernel = (int)value;
@@ -655,14 +673,14 @@ struct Step {
       }
       if (p.nbl > 0) {
          pf::k_fd<Real, PFFDTD_MMB><<<nblk(p.nbl, 128), 128, 0, s>>>(u0, e->bnl, e->matmb, (const Real *)e->lo2Kbg, (const Real *)e->facb,
-                                                                    (Real *)e->hist[n & 1], (Real *)e->vh1, (Real *)e->gh1, p.l0, p.nbl,
-                                                                    e->Nbl, (const Real *)e->quads);
+                                                                    (Real *)e->hist[0], (Real *)e->hist[1], (Real *)e->vh1, (Real *)e->gh1,
+                                                                    p.l0, p.nbl, e->Nbl, (const Real *)e->quads, e->d_n);
          e->launches += 1;
       }
       const i64 nr = p.recv ? e->Nr : 0;
       if (nr > 0 || p.ns > 0) {
-         pf::k_io<Real><<<nblk(std::max(nr, p.ns), 128), 128, 0, s>>>(u1, u0, e->out, (Real *)e->uout + n * e->Nr, nr, e->in,
-                                                                     (const Real *)e->insig + n * e->Ns, p.s0, p.ns, e->serial_src);
+         pf::k_io<Real><<<nblk(std::max(nr, p.ns), 128), 128, 0, s>>>(u1, u0, e->out, (Real *)e->uout, nr, e->Nr, e->in,
+                                                                     (const Real *)e->insig, e->Ns, p.s0, p.ns, e->serial_src, e->d_n);
          e->launches += 1;
       }
       if (fused && p.np > 0) {
@@ -720,6 +738,11 @@ static int step_impl(pffdtd_engine *e, i64 n) {
    const i64 Nx = e->Nx;
    int rc;
 
+   if (e->n_dev != n) {
+      pf::k_set_n<<<1, 1, 0, s>>>(e->d_n, n);
+      e->launches += 1;
+      e->n_dev = n;
+   }
    // the halo planes of u1 come from the previous step's exchange
    if (e->comm_pending) {
       CU(cudaStreamWaitEvent(s, e->ev_comm, 0));
@@ -763,7 +786,10 @@ static int step_impl(pffdtd_engine *e, i64 n) {
       CU(cudaGetLastError());
       if ((rc = exchange(e, u0, s))) return rc;
    }
-   // 10. swap (the boundary history rotates through hist[n&1])
+   // 10. advance the device step counter, swap (the boundary history rotates with the counter's parity)
+   pf::k_tick<<<1, 1, 0, s>>>(e->d_n);
+   e->launches += 1;
+   e->n_dev = n + 1;
    e->cur ^= 1;
    e->steps_done = n + 1;
    return PFFDTD_OK;
@@ -778,9 +804,46 @@ extern "C" int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps
    if ((!e->x_lo_edge || !e->x_hi_edge) && !e->comm && !e->manual_halo)
       return fail(PFFDTD_ESTATE, "slab engine without communicator: call pffdtd_comm_init");
    CU(cudaSetDevice(e->device));
-   for (i64 n = nstart; n < nstart + nsteps; n++) {
+   i64 n = nstart;
+   const i64 nend = nstart + nsteps;
+   while (n < nend) {
+      // two steps bring `cur` back: a captured pair replays as one CUDA graph (single GPU, fused or not,
+      // once the halos are clean and the first plain steps have sized the launches)
+      const bool graph_ok = e->use_graph && !e->comm && !e->profile_air && !e->manual_halo && nend - n >= 2 && e->steps_plain >= 2 &&
+                            !(e->halo_dirty && e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok);
+      if (graph_ok) {
+         const int c = e->cur;
+         if (e->n_dev != n) {
+            pf::k_set_n<<<1, 1, 0, e->s_main>>>(e->d_n, n);
+            e->n_dev = n;
+         }
+         if (!e->graph[c]) {
+            cudaGraph_t g = nullptr;
+            const double l0 = e->launches;
+            const i64 nd = e->n_dev, sd = e->steps_done;
+            CU(cudaStreamBeginCapture(e->s_main, cudaStreamCaptureModeThreadLocal));
+            int rc = step_any(e, n);
+            if (rc == PFFDTD_OK) rc = step_any(e, n + 1);
+            cudaError_t ce = cudaStreamEndCapture(e->s_main, &g);
+            e->graph_launches[c] = e->launches - l0;
+            e->launches = l0, e->n_dev = nd, e->steps_done = sd;  // nothing ran yet
+            if (rc) return rc;
+            if (ce != cudaSuccess) return fail(PFFDTD_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&e->graph[c], g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) return fail(PFFDTD_ECUDA, "graph instantiate: %s", cudaGetErrorString(ce));
+         }
+         CU(cudaGraphLaunch(e->graph[c], e->s_main));
+         e->launches += e->graph_launches[c];
+         n += 2;
+         e->n_dev = n;
+         e->steps_done = n;
+         continue;
+      }
       int rc = step_any(e, n);
       if (rc) return rc;
+      e->steps_plain++;
+      n++;
    }
    return PFFDTD_OK;
 }

@@ -167,8 +167,9 @@ template <typename Real, int NN>
 __global__ void k_rigid(const Real *__restrict__ u1, Real *__restrict__ u0, const i64 *__restrict__ bn,
                         const uint16_t *__restrict__ adj_bn, i64 i0, i64 n, Real sl2, Real a2, Offsets off) {
    typedef Ops<Real> O;
-   const i64 i = i0 + (i64)blockIdx.x * blockDim.x + threadIdx.x;
-   if (i >= i0 + n) return;
+   // descending order: the air kernel swept x upwards, so the lines it touched last are the ones still in L2
+   const i64 i = i0 + n - 1 - ((i64)blockIdx.x * blockDim.x + threadIdx.x);
+   if (i < i0) return;
    const i64 c = bn[i];
    const unsigned adj = adj_bn[i];
    const Real K = (Real)__popc(adj);
@@ -216,12 +217,14 @@ __global__ void k_fd_prep(const int8_t *__restrict__ mat_bnl, const Real *__rest
 template <typename Real, int MMB>
 __global__ void __launch_bounds__(128) k_fd(Real *__restrict__ u0, const i64 *__restrict__ bnl, const uint16_t *__restrict__ matmb,
                                             const Real *__restrict__ lo2Kbg_bnl, const Real *__restrict__ fac_bnl,
-                                            Real *__restrict__ hist, Real *__restrict__ vh1, Real *__restrict__ gh1, i64 i0, i64 n,
-                                            i64 Nbl, const Real *__restrict__ quads) {
+                                            Real *__restrict__ hist0, Real *__restrict__ hist1, Real *__restrict__ vh1,
+                                            Real *__restrict__ gh1, i64 i0, i64 n, i64 Nbl, const Real *__restrict__ quads,
+                                            const i64 *__restrict__ d_n) {
    typedef Ops<Real> O;
-   const i64 i = i0 + (i64)blockIdx.x * blockDim.x + threadIdx.x;
-   if (i >= i0 + n) return;
+   const i64 i = i0 + n - 1 - ((i64)blockIdx.x * blockDim.x + threadIdx.x);  // descending, see k_rigid
+   if (i < i0) return;
    const Real one = (Real)1.0, two = (Real)2.0;
+   Real *hist = (*d_n & 1) ? hist1 : hist0;  // the value two steps back lives in the buffer of the step's parity
    const unsigned mm = matmb[i];
    const int Mb = (int)(mm >> 8);
    const Real *q = quads + (i64)(mm & 0xffu) * MMB * 4;
@@ -278,11 +281,17 @@ __global__ void k_src(Real *__restrict__ u0, const i64 *__restrict__ in_ixyz, co
    }
 }
 
-// steps 8+9 in one launch: receivers (threads [0,Nr)) and sources (threads [0,ns)) touch different grids
+// steps 8+9 in one launch: receivers (threads [0,Nr)) and sources (threads [0,ns)) touch different grids.
+// The time index comes from a device counter (so that a captured step can be replayed as a CUDA graph); `nr` = 0
+// for the parts of a step that do not read the receivers.
 template <typename Real>
-__global__ void k_io(const Real *__restrict__ u1, Real *__restrict__ u0, const i64 *__restrict__ out_ixyz, Real *__restrict__ out_row,
-                     i64 Nr, const i64 *__restrict__ in_ixyz, const Real *__restrict__ in_row, i64 s0, i64 ns, int serial_src) {
+__global__ void k_io(const Real *__restrict__ u1, Real *__restrict__ u0, const i64 *__restrict__ out_ixyz, Real *__restrict__ uout,
+                     i64 Nr, i64 nr_all, const i64 *__restrict__ in_ixyz, const Real *__restrict__ insig, i64 Ns_all, i64 s0, i64 ns,
+                     int serial_src, const i64 *__restrict__ d_n) {
    typedef Ops<Real> O;
+   const i64 n = *d_n;
+   Real *out_row = uout + n * nr_all;
+   const Real *in_row = insig + n * Ns_all;
    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
    if (i < Nr) out_row[i] = u1[out_ixyz[i]];
    if (serial_src) {
@@ -292,6 +301,10 @@ __global__ void k_io(const Real *__restrict__ u1, Real *__restrict__ u0, const i
       u0[in_ixyz[s0 + i]] = O::add(u0[in_ixyz[s0 + i]], in_row[s0 + i]);
    }
 }
+
+// device step counter: set at the start of a batch of steps, advanced at the end of every step
+__global__ void k_set_n(i64 *d_n, i64 v) { *d_n = v; }
+__global__ void k_tick(i64 *d_n) { *d_n += 1; }
 
 // halo mirrors of nodes that were written AFTER the fused air kernel (boundary and source nodes sitting
 // at index 2 / N-3 of an axis): u[dst] = u[src] for a precomputed list; usually empty
