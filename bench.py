@@ -234,7 +234,8 @@ def main():
         box = [comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         eng.comm_init(box[0], rank, world)
-    eng.set_option("air_kernel", args.air_kernel)
+    if not w["fcc"]:  # the 13-point FCC update runs on the generic kernel only
+        eng.set_option("air_kernel", args.air_kernel)
     if args.xc:
         eng.set_option("air_xc", args.xc)
     t_prep = time.perf_counter() - t_prep

@@ -228,7 +228,9 @@ __global__ void __launch_bounds__(128) k_fd(Real *__restrict__ u0, const i64 *__
    const unsigned mm = matmb[i];
    const int Mb = (int)(mm >> 8);
    const Real *q = quads + (i64)(mm & 0xffu) * MMB * 4;
-   // everything this node needs from memory is requested up front
+   // everything this node needs from memory is requested up front; the dependent gather (index -> u0) first
+   const i64 c = bnl[i];
+   const Real u0c = u0[c];
    Real v1[MMB], g1[MMB];
 #pragma unroll
    for (int m = 0; m < MMB; m++) {
@@ -237,11 +239,10 @@ __global__ void __launch_bounds__(128) k_fd(Real *__restrict__ u0, const i64 *__
          g1[m] = gh1[(i64)m * Nbl + i];
       }
    }
-   const i64 c = bnl[i];
    const Real lo2Kbg = lo2Kbg_bnl[i], fac = fac_bnl[i];
    const Real u2 = hist[i];
    const Real den = O::add(one, lo2Kbg);
-   Real u = O::div(O::add(u0[c], O::mul(lo2Kbg, u2)), den);
+   Real u = O::div(O::add(u0c, O::mul(lo2Kbg, u2)), den);
 #pragma unroll
    for (int m = 0; m < MMB; m++) {
       if (m < Mb) {
