@@ -234,8 +234,7 @@ def main():
         box = [comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         eng.comm_init(box[0], rank, world)
-    if not w["fcc"]:  # the 13-point FCC update runs on the generic kernel only
-        eng.set_option("air_kernel", args.air_kernel)
+    eng.set_option("air_kernel", args.air_kernel)
     if args.xc:
         eng.set_option("air_xc", args.xc)
     t_prep = time.perf_counter() - t_prep
@@ -313,7 +312,7 @@ def main():
             traffic = tr["traffic_bytes"]
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"bound": "hbm", "kernel": "k_air_tma_cart" if args.air_kernel == 1 and not w["fcc"] else "k_air_generic",
+    roofline = {"bound": "hbm", "kernel": ("k_air_tma_cart<FCC>" if w["fcc"] else "k_air_tma_cart") if args.air_kernel == 1 else "k_air_generic",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "algorithmic_bytes_per_launch": BYTES_PER_NODE[w["precision"]] * nodes_per_launch,
                 "peak_source": peak_src, "bytes_per_node": BYTES_PER_NODE[w["precision"]], "nodes_per_launch": int(nodes_per_launch),

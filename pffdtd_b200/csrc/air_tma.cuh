@@ -279,7 +279,7 @@ __global__ void k_abc_faces(const FacesArgs<Real> a) {
 // full[s] flips when all bytes of a plane have landed in stage s, empty[s] when all NW consumer warps
 // are done with it.  Loads are numbered consecutively over all segments of the CTA; load i uses stage
 // i % S.  A segment of cnt planes loads planes xa-1 .. xa+cnt: the first and the last only as u1.
-template <typename Real, int RPT, int NW, int S, int MAXR>
+template <typename Real, int RPT, int NW, int S, int MAXR, bool FCC>
 __global__ void __maxnreg__(MAXR)
     k_air_tma_cart(const __grid_constant__ CUtensorMap map_u1, const __grid_constant__ CUtensorMap map_u0,
                    const __grid_constant__ CUtensorMap map_mk, Real *__restrict__ u0g, const AirJob jb, const Real a1, const Real a2,
@@ -403,6 +403,73 @@ __global__ void __maxnreg__(MAXR)
          }
       }
 
+      if constexpr (FCC) {
+         // ---- 13-point FCC (cpu_engine.h:205-216; the same stencil on the checkerboard and on the folded grid):
+         // the taps of the planes x-1 and x+1 are (y+-1, z) and (y, z+-1), those of plane x are (y+-1, z+-1), so all
+         // three planes stay in shared memory and every tap is an LDS; the sum runs in the reference's order.
+         Ring gm = g0;  // plane x-1
+         Ring gc = g0;  // plane x
+         gc.next();
+         wait_full(gc);
+         Real *u0p = u0g + ((i64)sg.xa * Ny + ybase) * Nzp + zv;
+         for (int j = 0; j < sg.cnt; j++) {
+            Ring gu = gc;  // plane x+1
+            gu.next();
+            wait_full(gu);
+            const unsigned char *stc = stage(gc);
+            const Real *sm = (const Real *)stage(gm) + soff;
+            const Real *sc = (const Real *)stc + soff;
+            const Real *su = (const Real *)stage(gu) + soff;
+#pragma unroll
+            for (int r = 0; r < RPT; r++) {
+               if (r < nrow) {
+                  // rows y-1, y, y+1 of the three planes, with the z-1 / z+1 end taps where the stencil needs them
+                  Real m0[VEC], m1[VEC], m2[VEC], c0[VEC], c1[VEC], c2[VEC], p0[VEC], p1[VEC], p2[VEC], u0v[VEC];
+                  ld_vec<Real, VEC>(sm + (r - 1) * BZ, m0);
+                  ld_vec<Real, VEC>(sm + r * BZ, m1);
+                  ld_vec<Real, VEC>(sm + (r + 1) * BZ, m2);
+                  ld_vec<Real, VEC>(sc + (r - 1) * BZ, c0);
+                  ld_vec<Real, VEC>(sc + r * BZ, c1);
+                  ld_vec<Real, VEC>(sc + (r + 1) * BZ, c2);
+                  ld_vec<Real, VEC>(su + (r - 1) * BZ, p0);
+                  ld_vec<Real, VEC>(su + r * BZ, p1);
+                  ld_vec<Real, VEC>(su + (r + 1) * BZ, p2);
+                  const Real m1l = sm[r * BZ - 1], m1r = sm[r * BZ + VEC], p1l = su[r * BZ - 1], p1r = su[r * BZ + VEC];
+                  const Real c0l = sc[(r - 1) * BZ - 1], c0r = sc[(r - 1) * BZ + VEC], c2l = sc[(r + 1) * BZ - 1], c2r = sc[(r + 1) * BZ + VEC];
+                  ld_vec<Real, VEC>((const Real *)(stc + u0off) + r * TZ, u0v);
+                  const uint32_t m = (*(const uint32_t *)(stc + mkoff + r * C::MKW * 4) >> mshift) & VMASK;
+                  Real o[VEC];
+#pragma unroll
+                  for (int k = 0; k < VEC; k++) {
+                     Real p = O::sub(O::mul(a1, c1[k]), u0v[k]);
+                     p = O::add(p, O::mul(a2, p2[k]));                                  // +x +y
+                     p = O::add(p, O::mul(a2, m0[k]));                                  // -x -y
+                     p = O::add(p, O::mul(a2, (k < VEC - 1) ? c2[k + 1] : c2r));        // +y +z
+                     p = O::add(p, O::mul(a2, (k > 0) ? c0[k - 1] : c0l));              // -y -z
+                     p = O::add(p, O::mul(a2, (k < VEC - 1) ? p1[k + 1] : p1r));        // +x +z
+                     p = O::add(p, O::mul(a2, (k > 0) ? m1[k - 1] : m1l));              // -x -z
+                     p = O::add(p, O::mul(a2, p0[k]));                                  // +x -y
+                     p = O::add(p, O::mul(a2, m2[k]));                                  // -x +y
+                     p = O::add(p, O::mul(a2, (k > 0) ? c2[k - 1] : c2l));              // +y -z
+                     p = O::add(p, O::mul(a2, (k < VEC - 1) ? c0[k + 1] : c0r));        // -y +z
+                     p = O::add(p, O::mul(a2, (k > 0) ? p1[k - 1] : p1l));              // +x -z
+                     p = O::add(p, O::mul(a2, (k < VEC - 1) ? m1[k + 1] : m1r));        // -x +z
+                     o[k] = ((m >> k) & 1u) ? u0v[k] : p;
+                  }
+                  if (m != VMASK) st_vec<Real, VEC>(u0p + (i64)r * Nzp, o);
+               }
+            }
+            release(gm);
+            gm = gc;
+            gc = gu;
+            u0p += jb.plane;
+         }
+         release(gm);  // the two planes still held: the last centre plane and the last "x+1" plane
+         release(gc);
+         g0 = gc;
+         g0.next();
+         continue;
+      }
       Real um[RPT][VEC], uc[RPT][VEC], up[RPT][VEC];
       Ring gc = g0;  // plane xa-1 (already waited for)
       {
@@ -565,9 +632,13 @@ template <typename Real>
 static int air_tma_attr(int cfg) {
    cudaError_t rc = cudaErrorInvalidValue;
 #define X(id, RPT, NW, S, MAXR)                                                                                     \
-   if (cfg == id)                                                                                                   \
-      rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                AirCfg<Real, RPT, NW, S>::SMEM_BYTES);
+   if (cfg == id) {                                                                                                        \
+      rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                AirCfg<Real, RPT, NW, S>::SMEM_BYTES);                                                       \
+      if (rc == cudaSuccess)                                                                                               \
+         rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   AirCfg<Real, RPT, NW, S>::SMEM_BYTES);                                                    \
+   }
    PF_AIR_CONFIGS(X)
 #undef X
    return (int)rc;
@@ -592,10 +663,6 @@ static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 
    }
    t->cfg = cfg;
    t->slots = 0;
-   if (fcc != 0) {
-      t->why = "13-point FCC runs on the generic kernel";
-      return 1;
-   }
    if (Nx > 0x7fffffff || Ny > 0x7fffffff || Nzp > 0x7fffffff) {
       t->why = "grid dimension exceeds 2^31";
       return 1;
@@ -655,7 +722,7 @@ static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 
 template <typename Real, int RPT, int NW, int S, int MAXR>
 static int air_tma_launch_cfg(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real a1, Real a2, const AirEdge<Real> &eg, cudaStream_t s) {
    typedef AirCfg<Real, RPT, NW, S> C;
-   auto kern = k_air_tma_cart<Real, RPT, NW, S, MAXR>;
+   auto kern = t->fcc ? k_air_tma_cart<Real, RPT, NW, S, MAXR, true> : k_air_tma_cart<Real, RPT, NW, S, MAXR, false>;
    if (t->slots <= 0) {
       int per_sm = 0;
       cudaError_t rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, C::SMEM_BYTES);

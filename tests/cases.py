@@ -22,6 +22,8 @@ CASES = {
     "cart_nz_d": (dict(Nx=16, Ny=20, Nz=68, Nt=40, nmat=1, mb=2), "cart"),
     "fcc1_lossy": (dict(Nx=24, Ny=20, Nz=18, Nt=50, fcc=True, nmat=2, mb=3), "fcc1"),
     "fcc2_lossy": (dict(Nx=24, Ny=20, Nz=18, Nt=50, fcc=True, nmat=2, mb=3), "fcc2"),
+    "fcc2_wide": (dict(Nx=18, Ny=44, Nz=150, Nt=30, fcc=True, nmat=1, mb=2), "fcc2"),
+    "fcc1_wide": (dict(Nx=16, Ny=38, Nz=140, Nt=30, fcc=True, nmat=1, mb=2), "fcc1"),
     "fcc2_rigid": (dict(Nx=26, Ny=24, Nz=40, Nt=40, fcc=True, rigid=True), "fcc2"),
 }
 

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 def _kernels(sd):
     """(air_kernel, fuse): generic kernel; tiled kernel with separate ABC / mirror kernels; tiled kernel with the
     absorbing shell and the halo mirrors fused in (the default)"""
-    return ((0, 0), (1, 0), (1, 1)) if sd.fcc_flag == 0 else ((0, 0),)
+    return ((0, 0), (1, 0), (1, 1)) if sd.fcc_flag == 0 else ((0, 0), (1, 0))  # FCC: generic and tiled 13-point kernels
 
 
 def _engine(sd, ak, fuse):
@@ -43,7 +43,7 @@ def test_traces_bit_exact(name, precision):
 
 @pytest.mark.parametrize("precision", (2, 1))
 @pytest.mark.parametrize("name", ("cart_lossy", "cart_ragged", "cart_tight", "cart_tight0", "cart_nz_a", "cart_nz_b", "cart_nz_c", "cart_nz_d",
-                                  "fcc1_lossy", "fcc2_lossy"))
+                                  "fcc1_lossy", "fcc2_lossy", "fcc1_wide", "fcc2_wide"))
 def test_full_state_bit_exact_from_noise(name, precision):
     """whole grids + boundary ODE state after 25 steps from a random initial state: exercises every
     interior node, the halo mirrors, the ABC shell and the lossy walls at once"""
