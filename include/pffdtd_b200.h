@@ -97,7 +97,7 @@ int pffdtd_comm_init(pffdtd_engine *e, const void *id128, int rank, int nranks);
 int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t value);
 /* Counters/timers: "launches", "steps", "air_ms" / "air_launches_timed" (CUDA-event time of the air launches
  * since reset, with profile_air), "timer_start" / "timer_stop_ms" (device stopwatch on the engine's stream),
- * "fused", "mirror_pairs", "air_kernel", "Nzp". */
+ * "fused", "mirror_pairs", "air_kernel", "Nzp", "energy". */
 int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out);
 int pffdtd_reset_stats(pffdtd_engine *e);
 
@@ -123,6 +123,25 @@ int pffdtd_read_grid(pffdtd_engine *e, int which, double *out /* Nx*Ny*Nz */);
 int pffdtd_write_grid(pffdtd_engine *e, int which, const double *in /* Nx*Ny*Nz */);
 /* Boundary ODE state (vh1, gh1: [Nbl*PFFDTD_MMB], reference CPU layout nb*MMb+m) for energy checks. */
 int pffdtd_read_boundary_state(pffdtd_engine *e, double *vh1, double *gh1);
+
+/* Energy balance of the reference's Python engine (python/fdtd/sim_fdtd.py:587-620 with --energy; SURVEY.md
+ * App. F), evaluated on the device.  Enabling it (before the first step) allocates a third grid for the
+ * boundary-aware Laplacian of the previous state and makes every step also accumulate
+ *   H_tot[n] (stored energy at step n), E_lost[n+1] (cumulative boundary + absorbing-shell losses),
+ *   E_in[n+1] (cumulative energy injected by the sources),
+ * all in double, in a fixed summation order.  The invariant is H_tot[n] + E_lost[n] == E_in[n] to rounding.
+ * With slabs each rank holds the sums over its own planes; the host adds the ranks.  Energy steps use the
+ * unfused kernels (same receiver traces bit for bit).  Not available for folded FCC grids (fcc_flag 2), which
+ * the reference's Python engine cannot load either. */
+typedef struct pffdtd_energy_desc {
+   int32_t struct_size;   /* = sizeof(pffdtd_energy_desc) */
+   int32_t reserved;
+   double h, c, Ts;       /* grid spacing, speed of sound, time step (sim_consts.h5: h, c, Ts) */
+   const double *mat_DEF; /* [Nm*PFFDTD_MMB*3] raw (D, E, F) per (material, branch), zero padded (sim_mats.h5 mat_XX_DEF) */
+} pffdtd_energy_desc;
+int pffdtd_energy_enable(pffdtd_engine *e, const pffdtd_energy_desc *d);
+/* H_tot[Nt], E_lost[Nt+1], E_in[Nt+1]; entries of steps not run yet are 0 */
+int pffdtd_read_energy(pffdtd_engine *e, double *H_tot, double *E_lost, double *E_in);
 
 /* Device self-test: the fused absorbing-shell update divides by the constants 1 + l*Q with a
  * reciprocal + one exact-residual correction instead of a general division; this compares the two on

@@ -19,6 +19,7 @@
 #include "pffdtd_b200.h"
 #include "kernels.cuh"
 #include "air_tma.cuh"
+#include "energy.cuh"
 
 using pf::i64;
 
@@ -105,7 +106,7 @@ struct pffdtd_engine {
    i64 Nx = 0, Ny = 0, Nz = 0, Nzp = 0, mwpr = 0, Nb = 0, Nbl = 0, Nba = 0, Ns = 0, Nr = 0, Nt = 0;
    i64 ix0 = 0;
    int x_lo_edge = 1, x_hi_edge = 1;
-   double l = 0, a1 = 0, a2 = 0, sl2 = 0, lo2 = 0;
+   double l = 0, l2 = 0, a1 = 0, a2 = 0, sl2 = 0, lo2 = 0;
    size_t rs = 4;  // sizeof(Real)
    pf::Offsets off{};
    // device memory
@@ -154,6 +155,12 @@ struct pffdtd_engine {
    double air_ms = 0;
    i64 air_timed = 0;
    pf::AirTma tma;
+   // energy balance (energy.cuh): third grid Lu, copies of the pre-step branch / source-node values, partial sums
+   int energy_on = 0;
+   void *Lu = nullptr, *vold = nullptr, *u2in = nullptr;
+   double *en_def = nullptr, *en_part = nullptr, *en_H = nullptr, *en_lost = nullptr, *en_in = nullptr;
+   pf::EnergyCoef en_k{};
+   double en_Ts = 0;
    std::vector<void *> allocs;
 };
 
@@ -281,7 +288,7 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    e->mwpr = (e->Nzp / 32 + 3) / 4 * 4;  // mask words per row, a multiple of 16 bytes (TMA stride)
    e->Nb = d->Nb, e->Nbl = d->Nbl, e->Nba = d->Nba, e->Ns = d->Ns, e->Nr = d->Nr, e->Nt = d->Nt;
    e->ix0 = d->ix0, e->x_lo_edge = d->x_lo_edge, e->x_hi_edge = d->x_hi_edge;
-   e->l = d->l, e->a1 = d->a1, e->a2 = d->a2, e->sl2 = d->sl2, e->lo2 = d->lo2;
+   e->l = d->l, e->l2 = d->l2, e->a1 = d->a1, e->a2 = d->a2, e->sl2 = d->sl2, e->lo2 = d->lo2;
    for (i64 i = 0; i < d->Nbl; i++) {
       const int k = d->mat_bnl[i];
       if (k < 0 || k >= d->Nm) return fail(PFFDTD_EINVAL, "mat_bnl[%lld]=%d out of range", (long long)i, k);
@@ -568,7 +575,8 @@ extern "C" int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out) {
       *out = ms;
    } else if (k == "air_kernel") *out = e->air_kernel;
    else if (k == "Nzp") *out = (double)e->Nzp;
-   else if (k == "fused") *out = (e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok) ? 1 : 0;
+   else if (k == "fused") *out = (e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->energy_on) ? 1 : 0;
+   else if (k == "energy") *out = e->energy_on;
    else if (k == "mirror_pairs") *out = (double)e->np;
    else return fail(PFFDTD_EINVAL, "unknown stat %s", key);
    return PFFDTD_OK;
@@ -691,6 +699,101 @@ struct Step {
    }
 };
 
+// ------------------------------------------------------------------------------------------------
+// energy balance (energy.cuh; sim_fdtd.py:587-620)
+// ------------------------------------------------------------------------------------------------
+static inline int en_blocks(i64 n) { return (int)std::max<i64>(1, std::min<i64>(pf::EN_BLOCKS, (n + pf::EN_THREADS - 1) / pf::EN_THREADS)); }
+
+// before the step's updates: u1 = state n (halos mirrored), u0 = state n-1, Lu = Laplacian of state n-1
+template <typename Real>
+static int energy_pre(pffdtd_engine *e, Real *u1, Real *u0, i64 n, cudaStream_t s) {
+   double *P = e->en_part;
+   const int EB = pf::EN_BLOCKS, nB = en_blocks(e->Nba), nC = en_blocks(e->Nbl);
+   Real *Lu = (Real *)e->Lu;
+   pf::k_energy_int<Real><<<EB, pf::EN_THREADS, 0, s>>>(u1, u0, Lu, e->Nx, e->Ny, e->Nz, e->Nzp, e->l2, P);
+   pf::k_energy_abc_corr<Real><<<nB, pf::EN_THREADS, 0, s>>>(u1, u0, Lu, e->bna, e->Q, e->Nba, e->l2, P + EB);
+   pf::k_energy_branches<Real, PFFDTD_MMB><<<nC, pf::EN_THREADS, 0, s>>>((const Real *)e->ssaf, e->matmb, (const Real *)e->vh1, (const Real *)e->gh1,
+                                                                        e->Nbl, e->en_def, e->en_Ts, 0, P + 2 * EB);
+   pf::k_energy_finish_H<<<1, pf::EN_THREADS, 0, s>>>(P, P + EB, P + 2 * EB, EB, nB, nC, e->en_k, e->en_H, n);
+   e->launches += 4;
+   if (e->Ns) {
+      pf::k_gather<Real><<<nblk(e->Ns, 128), 128, 0, s>>>(u0, e->in, (Real *)e->u2in, e->Ns);
+      e->launches += 1;
+   }
+   if (e->Nbl) CU(cudaMemcpyAsync(e->vold, e->vh1, (size_t)e->Nbl * PFFDTD_MMB * e->rs, cudaMemcpyDeviceToDevice, s));
+   // Lu <- Laplacian of state n, for the next step's H_tot (the reference keeps Lu1 the same way, sim_fdtd.py:603-604)
+   const double lfac = e->fcc ? 0.25 : 1.0;
+   dim3 blk(64, 4, 1), grd(nblk(e->Nzp, 64), nblk(e->Ny, 4), (unsigned)(e->Nx - 2));
+   if (e->fcc) {
+      pf::k_lap_air<Real, 12><<<grd, blk, 0, s>>>(u1, Lu, e->mask, e->Ny, e->Nzp, e->mwpr, 1, lfac, e->off);
+      if (e->Nb) pf::k_lap_bn<Real, 12><<<nblk(e->Nb, 128), 128, 0, s>>>(u1, Lu, e->bn, e->adj, e->Nb, lfac, e->off);
+   } else {
+      pf::k_lap_air<Real, 6><<<grd, blk, 0, s>>>(u1, Lu, e->mask, e->Ny, e->Nzp, e->mwpr, 1, lfac, e->off);
+      if (e->Nb) pf::k_lap_bn<Real, 6><<<nblk(e->Nb, 128), 128, 0, s>>>(u1, Lu, e->bn, e->adj, e->Nb, lfac, e->off);
+   }
+   e->launches += e->Nb ? 2 : 1;
+   CU(cudaGetLastError());
+   return 0;
+}
+
+// after the step's updates: u0 = state n+1, vh1 = the reference's vh0, vold = its vh1
+template <typename Real>
+static int energy_post(pffdtd_engine *e, Real *u0, i64 n, cudaStream_t s) {
+   double *P = e->en_part;
+   const int EB = pf::EN_BLOCKS, nD = en_blocks(e->Nbl), nE = en_blocks(e->Nba);
+   pf::k_energy_branches<Real, PFFDTD_MMB><<<nD, pf::EN_THREADS, 0, s>>>((const Real *)e->ssaf, e->matmb, (const Real *)e->vh1, (const Real *)e->vold,
+                                                                        e->Nbl, e->en_def, e->en_Ts, 1, P + 3 * EB);
+   pf::k_energy_abc_loss<Real><<<nE, pf::EN_THREADS, 0, s>>>(u0, (const Real *)e->u2ba, e->bna, e->Q, e->Nba, P + 4 * EB);
+   pf::k_energy_in<Real><<<1, pf::EN_THREADS, 0, s>>>(u0, (const Real *)e->u2in, e->in, (const Real *)e->insig + n * e->Ns, e->Ns, P + 5 * EB);
+   pf::k_energy_finish_E<<<1, pf::EN_THREADS, 0, s>>>(P + 3 * EB, P + 4 * EB, P + 5 * EB, nD, nE, e->en_k, e->en_lost, e->en_in, n);
+   e->launches += 4;
+   CU(cudaGetLastError());
+   return 0;
+}
+
+extern "C" int pffdtd_energy_enable(pffdtd_engine *e, const pffdtd_energy_desc *d) {
+   if (!e || !d) return fail(PFFDTD_EINVAL, "NULL argument");
+   if (d->struct_size != (int32_t)sizeof(pffdtd_energy_desc)) return fail(PFFDTD_EINVAL, "pffdtd_energy_desc size mismatch");
+   if (e->energy_on) return fail(PFFDTD_ESTATE, "energy balance already enabled");
+   if (e->steps_done != 0) return fail(PFFDTD_ESTATE, "enable the energy balance before the first step");
+   if (e->fcc == 2) return fail(PFFDTD_ESTATE, "no energy balance on folded FCC grids (fcc_flag 2): use the fcc_flag 1 folder");
+   if (!(d->h > 0) || !(d->c > 0) || !(d->Ts > 0)) return fail(PFFDTD_EINVAL, "h, c, Ts must be positive");
+   if (e->Nbl > 0 && !d->mat_DEF) return fail(PFFDTD_EINVAL, "lossy nodes but no mat_DEF");
+   CU(cudaSetDevice(e->device));
+   CU(cudaStreamSynchronize(e->s_main));
+   const size_t npad = (size_t)(e->Nx * e->Ny * e->Nzp);
+   if (dalloc_bytes(e, &e->Lu, npad * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->vold, (size_t)e->Nbl * PFFDTD_MMB * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->u2in, (size_t)e->Ns * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc(e, &e->en_def, (size_t)std::max(e->Nm, 1) * PFFDTD_MMB * 3)) return PFFDTD_ECUDA;
+   if (e->Nm && d->mat_DEF) CU(cudaMemcpy(e->en_def, d->mat_DEF, (size_t)e->Nm * PFFDTD_MMB * 3 * 8, cudaMemcpyHostToDevice));
+   if (dalloc(e, &e->en_part, (size_t)6 * pf::EN_BLOCKS)) return PFFDTD_ECUDA;
+   if (dalloc(e, &e->en_H, (size_t)e->Nt + 1)) return PFFDTD_ECUDA;
+   if (dalloc(e, &e->en_lost, (size_t)e->Nt + 1)) return PFFDTD_ECUDA;
+   if (dalloc(e, &e->en_in, (size_t)e->Nt + 1)) return PFFDTD_ECUDA;
+   e->en_k = pf::EnergyCoef{e->fcc ? 2.0 : 1.0, d->h, d->c, e->l, e->l2};
+   e->en_Ts = d->Ts;
+   for (int c = 0; c < 2; c++)
+      if (e->graph[c]) {
+         cudaGraphExecDestroy(e->graph[c]);
+         e->graph[c] = nullptr;
+      }
+   e->halo_dirty = 1;
+   e->energy_on = 1;
+   return PFFDTD_OK;
+}
+
+extern "C" int pffdtd_read_energy(pffdtd_engine *e, double *H_tot, double *E_lost, double *E_in) {
+   if (!e || !H_tot || !E_lost || !E_in) return fail(PFFDTD_EINVAL, "NULL argument");
+   if (!e->energy_on) return fail(PFFDTD_ESTATE, "energy balance not enabled");
+   CU(cudaSetDevice(e->device));
+   CU(cudaStreamSynchronize(e->s_main));
+   if (e->Nt) CU(cudaMemcpy(H_tot, e->en_H, (size_t)e->Nt * 8, cudaMemcpyDeviceToHost));
+   CU(cudaMemcpy(E_lost, e->en_lost, (size_t)(e->Nt + 1) * 8, cudaMemcpyDeviceToHost));
+   CU(cudaMemcpy(E_in, e->en_in, (size_t)(e->Nt + 1) * 8, cudaMemcpyDeviceToHost));
+   return PFFDTD_OK;
+}
+
 // the reference's mirror pass on one grid (cpu_engine.h:135-172): seam row, then z, y, x faces in that order
 template <typename Real>
 static void mirror_pass(pffdtd_engine *e, Real *u, cudaStream_t s) {
@@ -731,7 +834,7 @@ static int exchange(pffdtd_engine *e, void *unew, cudaStream_t s) {
 template <typename Real>
 static int step_impl(pffdtd_engine *e, i64 n) {
    if (n < 0 || n >= e->Nt) return fail(PFFDTD_EINVAL, "step %lld outside [0,%lld)", (long long)n, (long long)e->Nt);
-   const bool fused = e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok;
+   const bool fused = e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->energy_on;
    Step<Real> st{e, (Real *)e->u[e->cur], (Real *)e->u[e->cur ^ 1], e->s_main, n, fused};
    Real *u1 = st.u1, *u0 = st.u0;
    cudaStream_t s = e->s_main;
@@ -760,6 +863,7 @@ static int step_impl(pffdtd_engine *e, i64 n) {
       mirror_pass<Real>(e, u1, s);
       e->halo_dirty = 0;
    }
+   if (e->energy_on && (rc = energy_pre<Real>(e, u1, u0, n, s))) return rc;
    const bool lo = e->comm && !e->x_lo_edge, hi = e->comm && !e->x_hi_edge;
    const bool split = (lo || hi) && e->overlap && e->sorted && Nx >= 5;
    if (split) {
@@ -786,6 +890,7 @@ static int step_impl(pffdtd_engine *e, i64 n) {
       CU(cudaGetLastError());
       if ((rc = exchange(e, u0, s))) return rc;
    }
+   if (e->energy_on && (rc = energy_post<Real>(e, u0, n, s))) return rc;
    // 10. advance the device step counter, swap (the boundary history rotates with the counter's parity)
    pf::k_tick<<<1, 1, 0, s>>>(e->d_n);
    e->launches += 1;
@@ -809,7 +914,7 @@ extern "C" int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps
    while (n < nend) {
       // two steps bring `cur` back: a captured pair replays as one CUDA graph (single GPU, fused or not,
       // once the halos are clean and the first plain steps have sized the launches)
-      const bool graph_ok = e->use_graph && !e->comm && !e->profile_air && !e->manual_halo && nend - n >= 2 && e->steps_plain >= 2 &&
+      const bool graph_ok = e->use_graph && !e->energy_on && !e->comm && !e->profile_air && !e->manual_halo && nend - n >= 2 && e->steps_plain >= 2 &&
                             !(e->halo_dirty && e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok);
       if (graph_ok) {
          const int c = e->cur;

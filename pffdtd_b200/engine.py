@@ -22,6 +22,12 @@ HEADER = HERE.parent / "include" / "pffdtd_b200.h"
 OK, EINVAL, ECUDA, ENCCL, ESTATE = 0, -1, -2, -3, -4
 
 
+class pffdtd_energy_desc(C.Structure):
+    """include/pffdtd_b200.h: pffdtd_energy_desc"""
+    _fields_ = [("struct_size", C.c_int32), ("reserved", C.c_int32), ("h", C.c_double), ("c", C.c_double), ("Ts", C.c_double),
+                ("mat_DEF", C.c_void_p)]
+
+
 class PffdtdError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"[{code}] {msg}")
@@ -68,6 +74,8 @@ def lib():
     L.pffdtd_write_grid.argtypes = [vp, C.c_int, vp]
     L.pffdtd_read_boundary_state.argtypes = [vp, vp, vp]
     L.pffdtd_run_sim.argtypes = [C.POINTER(pffdtd_desc), C.c_int, vp, dp]
+    L.pffdtd_energy_enable.argtypes = [vp, C.POINTER(pffdtd_energy_desc)]
+    L.pffdtd_read_energy.argtypes = [vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -149,6 +157,25 @@ class Engine:
 
     def reset_stats(self):
         _check(self.L.pffdtd_reset_stats(self.h))
+
+    def energy_enable(self):
+        """accumulate the reference Python engine's energy balance (sim_fdtd.py:587-620) during the following steps"""
+        sd = self.sd
+        if not (sd.h > 0 and sd.c > 0):
+            raise ValueError("the energy balance needs h and c (sim_consts.h5)")
+        d = pffdtd_energy_desc()
+        d.struct_size = C.sizeof(pffdtd_energy_desc)
+        d.h, d.c, d.Ts = sd.h, sd.c, sd.Ts
+        self._def = np.ascontiguousarray(sd.DEF if sd.DEF is not None else np.zeros((max(sd.Nm, 1), 12, 3)), np.float64)
+        d.mat_DEF = self._def.ctypes.data
+        _check(self.L.pffdtd_energy_enable(self.h, C.byref(d)))
+
+    def read_energy(self):
+        """(H_tot[Nt], E_lost[Nt+1], E_in[Nt+1]) summed over this engine's planes"""
+        Nt = self.sd.Nt
+        H, lost, ein = np.zeros(max(Nt, 1)), np.zeros(Nt + 1), np.zeros(Nt + 1)
+        _check(self.L.pffdtd_read_energy(self.h, H.ctypes.data, lost.ctypes.data, ein.ctypes.data))
+        return H[:Nt], lost, ein
 
     # -- stepping
     def run_steps(self, nstart: int, nsteps: int):

@@ -48,6 +48,19 @@ def gather_rows(u: np.ndarray) -> np.ndarray:
     return np.concatenate(parts, axis=0)
 
 
+def sum_arrays(a: np.ndarray) -> np.ndarray:
+    """element-wise sum over ranks (per-rank partial sums of the energy balance), identical on every rank"""
+    dist = init()
+    if dist is None:
+        return a
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, np.asarray(a, np.float64))
+    out = np.zeros_like(parts[0])
+    for p in parts:  # fixed rank order: the same bits on every rank
+        out = out + p
+    return out
+
+
 def exchange_planes(send_lo, send_hi, rank, world):
     """CPU stand-in of the halo exchange, used by the gloo tests with the oracle as the per-rank engine:
     send plane 1 down / plane Nx-2 up, receive the neighbours' into plane Nx-1 / 0.  Returns (from_lo, from_hi)."""

@@ -213,4 +213,4 @@ def sim_data_from_files(files: dict, precision: int, abc_x_range=None):
                                Ts=c["Ts"], bn_ixyz=v["bn_ixyz"], adj_bn=v["adj_bn"], mat_bn=v["mat_bn"], saf_bn=v["saf_bn"],
                                in_ixyz=m["in_ixyz"], out_ixyz=m["out_ixyz"], out_reorder=m["out_reorder"], in_sigs=m["in_sigs"],
                                Mb=t["Mb"], DEF=[t[f"mat_{i:02d}_DEF"] for i in range(nm)], diff=bool(m["diff"]),
-                               abc_x_range=abc_x_range)
+                               abc_x_range=abc_x_range, h=c.get("h", 0.0), c=c.get("c", 0.0))

@@ -133,6 +133,10 @@ class SimData:
     ix0: int = 0
     x_lo_edge: bool = True
     x_hi_edge: bool = True
+    # only the energy balance needs these (sim_fdtd.py:59-95, 257-259): grid spacing, speed of sound, raw (D,E,F) triplets
+    h: float = 0.0
+    c: float = 0.0
+    DEF: np.ndarray = None     # float64 [Nm, MMB, 3], zero padded
     _keep: list = field(default_factory=list, repr=False)
 
     # ---- derived
@@ -174,7 +178,7 @@ class SimData:
     # ---- construction
     @classmethod
     def from_arrays(cls, precision, *, fcc_flag, Nx, Ny, Nz, l, l2, Ts, bn_ixyz, adj_bn, mat_bn, saf_bn,
-                    in_ixyz, out_ixyz, out_reorder, in_sigs, Mb, DEF, diff=True, abc_x_range=None):
+                    in_ixyz, out_ixyz, out_reorder, in_sigs, Mb, DEF, diff=True, abc_x_range=None, h=0.0, c=0.0):
         """Everything load_sim_data derives, from the raw file contents.
         `abc_x_range=(x0,x1)` builds the absorbing-shell list for those planes only (a rank that will keep just
         its slab of a very large grid need not enumerate the whole shell)."""
@@ -238,11 +242,13 @@ class SimData:
             raise ValueError("too many materials")
         quads = np.zeros((Nm, MMB, 4), R)
         beta = np.zeros(Nm, R)
+        DEF_pad = np.zeros((Nm, MMB, 3), np.float64)
         for i in range(Nm):
             d = np.asarray(DEF[i], np.float64).reshape(-1, 3)
             if d.shape[0] != Mb[i] or Mb[i] > MMB:
                 raise ValueError("bad DEF shape")
             D, E, F = d[:, 0], d[:, 1], d[:, 2]
+            DEF_pad[i, :Mb[i]] = d
             Dh, Eh, Fh = D / Ts, E, F * Ts
             b = 1.0 / (2.0 * Dh + Eh + 0.5 * Fh)
             bd = b * (2.0 * Dh - Eh - 0.5 * Fh)
@@ -268,7 +274,7 @@ class SimData:
                    ssaf_bnl=np.ascontiguousarray(ssaf[lossy]), bnl_ixyz=np.ascontiguousarray(bn_ixyz[lossy]),
                    bna_ixyz=bna, Q_bna=Q, in_ixyz=in_ixyz, out_ixyz=np.ascontiguousarray(out_ixyz, np.int64),
                    out_reorder=np.ascontiguousarray(out_reorder, np.int64), in_sigs=in_sigs.reshape(in_ixyz.size, Nt),
-                   Mb=Mb, mat_quads=quads, mat_beta=beta, a1=a1, a2=a2, sl2=sl2, lo2=lo2)
+                   Mb=Mb, mat_quads=quads, mat_beta=beta, a1=a1, a2=a2, sl2=sl2, lo2=lo2, h=float(h), c=float(c), DEF=DEF_pad)
 
     @classmethod
     def load(cls, data_dir, precision: int) -> "SimData":
@@ -290,7 +296,8 @@ class SimData:
             l=c["l"][()], l2=c["l2"][()], Ts=c["Ts"][()], bn_ixyz=v["bn_ixyz"][...], adj_bn=v["adj_bn"][...],
             mat_bn=v["mat_bn"][...], saf_bn=v["saf_bn"][...], in_ixyz=m["in_ixyz"][...], out_ixyz=m["out_ixyz"][...],
             out_reorder=m["out_reorder"][...], in_sigs=m["in_sigs"][...], Mb=Mb[:Nmat],
-            DEF=[t[f"mat_{i:02d}_DEF"][...] for i in range(Nmat)], diff=bool(m["diff"][()]))
+            DEF=[t[f"mat_{i:02d}_DEF"][...] for i in range(Nmat)], diff=bool(m["diff"][()]),
+            h=c["h"][()] if "h" in c else 0.0, c=c["c"][()] if "c" in c else 0.0)
         if sd.Nb != Nb or sd.Ns != Ns or sd.Nr != Nr or sd.Nt != Nt:
             raise ValueError("dataset sizes disagree with the stored counts")
         return sd

@@ -32,8 +32,8 @@ from .sim_data import SimData
 class SimEngine:
     def __init__(self, data_dir, energy_on=False, nthreads=None, precision=2, device=None, scale=True, quiet=False):
         self.data_dir = Path(data_dir)
-        if energy_on:
-            raise NotImplementedError("the energy balance (sim_fdtd.py:587-620) is not part of the GPU step yet")
+        self.energy_on = bool(energy_on)
+        self.H_tot = self.E_lost = self.E_in = None
         self.precision = int(precision)
         self.rank, self.world, local = parallel.dist_env()
         self.device = local if device is None else int(device)
@@ -56,6 +56,8 @@ class SimEngine:
         sd = SimData.load(self.data_dir, self.precision)
         if self.scale:
             sd.scale_input()  # fdtd_data.h:879-909
+        if self.energy_on and sd.fcc_flag == 2:
+            raise ValueError("the energy balance needs the fcc_flag=1 folder (as the reference's Python engine does)")
         if self.world > 1 or sd.fcc_flag == 2:
             if not sd.is_sorted():
                 self.print("sorting node lists (the reference needs a sort_sim_data'd folder here)")
@@ -75,6 +77,8 @@ class SimEngine:
         self.eng = Engine(self.sd, self.device)
         if self.world > 1:
             self._comm_init()
+        if self.energy_on:
+            self.eng.energy_enable()
 
     def set_coeffs(self):
         pass  # derived in SimData.from_arrays exactly as load_sim_data does (fdtd_data.h:186-194, 424-460)
@@ -108,6 +112,15 @@ class SimEngine:
         if self.scale:
             u = self.sd_full.rescale_output(u)  # fdtd_data.h:912-925
         self.u_out = u
+        if self.energy_on:
+            # every rank summed its own planes; the three series add up across ranks
+            self.H_tot, self.E_lost, self.E_in = (parallel.sum_arrays(a) for a in self.eng.read_energy())
+
+    def print_last_energy(self, Np):
+        """sim_fdtd.py:662-669: rel_diff(H_tot+E_lost, E_in) of the last Np steps (common/myfuncs.py:164-165)"""
+        self.print("ENERGY")
+        for n in range(max(self.Nt - Np, 0), self.Nt):
+            self.print(f"normalised energy balance:{energy_balance(self.H_tot, self.E_lost, self.E_in)[n]:.16e}")
 
     def save_outputs(self):
         if self.rank == 0:
@@ -125,6 +138,16 @@ class SimEngine:
         if self.eng is not None:
             self.eng.close()
             self.eng = None
+
+
+def energy_balance(H_tot, E_lost, E_in):
+    """rel_diff(H_tot[n] + E_lost[n], E_in[n]) = (x0 - x1) / 2^floor(log2 x0)   (common/myfuncs.py:164-165); 0 where x0 <= 0"""
+    x0 = np.asarray(H_tot) + np.asarray(E_lost)[:len(H_tot)]
+    x1 = np.asarray(E_in)[:len(H_tot)]
+    out = np.zeros_like(x0)
+    ok = x0 > 0
+    out[ok] = (x0[ok] - x1[ok]) / 2.0 ** np.floor(np.log2(x0[ok]))
+    return out
 
 
 def run_folder(data_dir, precision=2, device=None, nsteps=1, quiet=True):
@@ -149,7 +172,7 @@ def main(argv=None):
     parser.add_argument("--nsteps", type=int, default=1, help="run in batches of steps")
     parser.add_argument("--nthreads", type=int, default=None, help="accepted for compatibility; unused")
     parser.add_argument("--precision", type=int, default=2, choices=(1, 2), help="1 single (fdtd_main_gpu_single.x), 2 double")
-    parser.add_argument("--energy", action="store_true", help="energy balance (not available on the GPU path yet)")
+    parser.add_argument("--energy", action="store_true", help="do energy calc (the reference's balance, evaluated on the device)")
     parser.add_argument("--device", type=int, default=None)
     args = parser.parse_args(argv)
     if args.data_dir is None:
@@ -163,6 +186,8 @@ def main(argv=None):
     eng.run_all(args.nsteps)
     eng.save_outputs()
     eng.print_last_samples(5)
+    if args.energy:
+        eng.print_last_energy(5)
     eng.close()
 
 
