@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--xc", type=int, default=0)
+    ap.add_argument("--overlap", type=int, default=1, choices=(0, 1), help="N>1: 0 = halo exchange after the whole step (diagnostic)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -235,6 +236,10 @@ def main():
         dist.broadcast_object_list(box, src=0)
         eng.comm_init(box[0], rank, world)
     eng.set_option("air_kernel", args.air_kernel)
+    if world > 1:
+        eng.set_option("overlap", args.overlap)
+        config["halo_exchange"] = "ncclSend/ncclRecv of one plane per neighbour per step, " + (
+            "overlapped with the interior update on a second stream" if args.overlap else "after the step (not overlapped)")
     if args.xc:
         eng.set_option("air_xc", args.xc)
     t_prep = time.perf_counter() - t_prep
