@@ -93,7 +93,8 @@ int pffdtd_comm_init(pffdtd_engine *e, const void *id128, int rank, int nranks);
  * "fuse" (1 = the tiled kernel also applies the absorbing shell and mirrors the halos on write [default]),
  * "overlap" (1 = edge planes first, halo exchange overlapped with the interior [default]),
  * "air_cfg" (tile configuration), "air_xc" (x-chunk length), "profile_air" (CUDA events around every air launch),
- * "manual_halo" (allow stepping a slab without a communicator; the caller moves the halo planes). */
+ * "manual_halo" (allow stepping a slab without a communicator; the caller moves the halo planes),
+ * "use_graph" (1 = replay captured steps as CUDA graphs [default]). */
 int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t value);
 /* Counters/timers: "launches", "steps", "air_ms" / "air_launches_timed" (CUDA-event time of the air launches
  * since reset, with profile_air), "timer_start" / "timer_stop_ms" (device stopwatch on the engine's stream),
@@ -107,7 +108,8 @@ int pffdtd_reset_stats(pffdtd_engine *e);
 int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps);
 /* One step with HOST buffers: in_samples[Ns] (this step's source samples, NULL = use uploaded
  * in_sigs) are copied to the device, the step runs, and the step's receiver samples
- * out_samples[Nr] are copied back; blocks until done (the per-step D2H of gpu_engine.h:1059-1075). */
+ * out_samples[Nr] are copied back; blocks until done (the per-step D2H of gpu_engine.h:1059-1075).
+ * On one GPU the two copies and the step's kernels replay as ONE captured CUDA graph (fixed staging buffers). */
 int pffdtd_step_host(pffdtd_engine *e, int64_t n, const double *in_samples, double *out_samples);
 /* Block until all queued work is complete. */
 int pffdtd_sync(pffdtd_engine *e);

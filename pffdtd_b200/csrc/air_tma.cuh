@@ -405,13 +405,43 @@ __global__ void __maxnreg__(MAXR)
 
       if constexpr (FCC) {
          // ---- 13-point FCC (cpu_engine.h:205-216; the same stencil on the checkerboard and on the folded grid):
-         // the taps of the planes x-1 and x+1 are (y+-1, z) and (y, z+-1), those of plane x are (y+-1, z+-1), so all
-         // three planes stay in shared memory and every tap is an LDS; the sum runs in the reference's order.
+         // the taps of the planes x-1 and x+1 are (y+-1, z) and (y, z+-1), those of plane x are (y+-1, z+-1).
+         // Rows y-1, y, y+1 of the three planes live in registers and rotate along the sweep (x+1 -> x -> x-1), so a
+         // plane costs three vector LDS per row; the z-1 / z+1 end taps come from the neighbouring lanes by shuffle,
+         // only lanes 0 and 31 read theirs from the stage (the first version read all nine rows and eight scalar taps
+         // from shared memory: 73 wavefronts per row-vector, the LSU data pipe 94 % busy -- the kernel's bound).
+         // Every lane runs the loads and shuffles (out-of-grid parts of a box are zero-filled); only the store is
+         // predicated.  The sum runs in the reference's order.
+         const bool edge_lane = lane == 0 || lane == 31;
+         const int eoff = lane == 0 ? -1 : VEC;  // where an edge lane finds its out-of-warp neighbour in a box row
+         auto zleft = [&](const Real(&v)[VEC], const Real e) {
+            const Real t = __shfl_up_sync(0xffffffffu, v[VEC - 1], 1);
+            return lane == 0 ? e : t;
+         };
+         auto zright = [&](const Real(&v)[VEC], const Real e) {
+            const Real t = __shfl_down_sync(0xffffffffu, v[0], 1);
+            return lane == 31 ? e : t;
+         };
          Ring gm = g0;  // plane x-1
          Ring gc = g0;  // plane x
          gc.next();
          wait_full(gc);
+         Real m0[RPT][VEC], m1[RPT][VEC], m2[RPT][VEC], c0[RPT][VEC], c1[RPT][VEC], c2[RPT][VEC];
+         {
+            const Real *sm = (const Real *)stage(gm) + soff;
+            const Real *sc = (const Real *)stage(gc) + soff;
+#pragma unroll
+            for (int r = 0; r < RPT; r++) {
+               ld_vec<Real, VEC>(sm + (r - 1) * BZ, m0[r]);
+               ld_vec<Real, VEC>(sm + r * BZ, m1[r]);
+               ld_vec<Real, VEC>(sm + (r + 1) * BZ, m2[r]);
+               ld_vec<Real, VEC>(sc + (r - 1) * BZ, c0[r]);
+               ld_vec<Real, VEC>(sc + r * BZ, c1[r]);
+               ld_vec<Real, VEC>(sc + (r + 1) * BZ, c2[r]);
+            }
+         }
          Real *u0p = u0g + ((i64)sg.xa * Ny + ybase) * Nzp + zv;
+         const bool row_warp = ybase <= Ny - 2;  // warp-uniform: the strip has at least one row inside the grid
          for (int j = 0; j < sg.cnt; j++) {
             Ring gu = gc;  // plane x+1
             gu.next();
@@ -422,41 +452,49 @@ __global__ void __maxnreg__(MAXR)
             const Real *su = (const Real *)stage(gu) + soff;
 #pragma unroll
             for (int r = 0; r < RPT; r++) {
-               if (r < nrow) {
-                  // rows y-1, y, y+1 of the three planes, with the z-1 / z+1 end taps where the stencil needs them
-                  Real m0[VEC], m1[VEC], m2[VEC], c0[VEC], c1[VEC], c2[VEC], p0[VEC], p1[VEC], p2[VEC], u0v[VEC];
-                  ld_vec<Real, VEC>(sm + (r - 1) * BZ, m0);
-                  ld_vec<Real, VEC>(sm + r * BZ, m1);
-                  ld_vec<Real, VEC>(sm + (r + 1) * BZ, m2);
-                  ld_vec<Real, VEC>(sc + (r - 1) * BZ, c0);
-                  ld_vec<Real, VEC>(sc + r * BZ, c1);
-                  ld_vec<Real, VEC>(sc + (r + 1) * BZ, c2);
-                  ld_vec<Real, VEC>(su + (r - 1) * BZ, p0);
-                  ld_vec<Real, VEC>(su + r * BZ, p1);
-                  ld_vec<Real, VEC>(su + (r + 1) * BZ, p2);
-                  const Real m1l = sm[r * BZ - 1], m1r = sm[r * BZ + VEC], p1l = su[r * BZ - 1], p1r = su[r * BZ + VEC];
-                  const Real c0l = sc[(r - 1) * BZ - 1], c0r = sc[(r - 1) * BZ + VEC], c2l = sc[(r + 1) * BZ - 1], c2r = sc[(r + 1) * BZ + VEC];
+               Real p0[VEC], p1[VEC], p2[VEC];
+               ld_vec<Real, VEC>(su + (r - 1) * BZ, p0);
+               ld_vec<Real, VEC>(su + r * BZ, p1);
+               ld_vec<Real, VEC>(su + (r + 1) * BZ, p2);
+               if (row_warp && ybase + r <= Ny - 2) {  // warp-uniform
+                  Real em1 = (Real)0, ec0 = (Real)0, ec2 = (Real)0, ep1 = (Real)0;
+                  if (edge_lane) {
+                     em1 = sm[r * BZ + eoff];
+                     ec0 = sc[(r - 1) * BZ + eoff];
+                     ec2 = sc[(r + 1) * BZ + eoff];
+                     ep1 = su[r * BZ + eoff];
+                  }
+                  const Real m1l = zleft(m1[r], em1), m1r = zright(m1[r], em1);
+                  const Real c0l = zleft(c0[r], ec0), c0r = zright(c0[r], ec0);
+                  const Real c2l = zleft(c2[r], ec2), c2r = zright(c2[r], ec2);
+                  const Real p1l = zleft(p1, ep1), p1r = zright(p1, ep1);
+                  Real u0v[VEC];
                   ld_vec<Real, VEC>((const Real *)(stc + u0off) + r * TZ, u0v);
                   const uint32_t m = (*(const uint32_t *)(stc + mkoff + r * C::MKW * 4) >> mshift) & VMASK;
                   Real o[VEC];
 #pragma unroll
                   for (int k = 0; k < VEC; k++) {
-                     Real p = O::sub(O::mul(a1, c1[k]), u0v[k]);
-                     p = O::add(p, O::mul(a2, p2[k]));                                  // +x +y
-                     p = O::add(p, O::mul(a2, m0[k]));                                  // -x -y
-                     p = O::add(p, O::mul(a2, (k < VEC - 1) ? c2[k + 1] : c2r));        // +y +z
-                     p = O::add(p, O::mul(a2, (k > 0) ? c0[k - 1] : c0l));              // -y -z
-                     p = O::add(p, O::mul(a2, (k < VEC - 1) ? p1[k + 1] : p1r));        // +x +z
-                     p = O::add(p, O::mul(a2, (k > 0) ? m1[k - 1] : m1l));              // -x -z
-                     p = O::add(p, O::mul(a2, p0[k]));                                  // +x -y
-                     p = O::add(p, O::mul(a2, m2[k]));                                  // -x +y
-                     p = O::add(p, O::mul(a2, (k > 0) ? c2[k - 1] : c2l));              // +y -z
-                     p = O::add(p, O::mul(a2, (k < VEC - 1) ? c0[k + 1] : c0r));        // -y +z
-                     p = O::add(p, O::mul(a2, (k > 0) ? p1[k - 1] : p1l));              // +x -z
-                     p = O::add(p, O::mul(a2, (k < VEC - 1) ? m1[k + 1] : m1r));        // -x +z
+                     Real p = O::sub(O::mul(a1, c1[r][k]), u0v[k]);
+                     p = O::add(p, O::mul(a2, p2[k]));                                     // +x +y
+                     p = O::add(p, O::mul(a2, m0[r][k]));                                  // -x -y
+                     p = O::add(p, O::mul(a2, (k < VEC - 1) ? c2[r][k + 1] : c2r));        // +y +z
+                     p = O::add(p, O::mul(a2, (k > 0) ? c0[r][k - 1] : c0l));              // -y -z
+                     p = O::add(p, O::mul(a2, (k < VEC - 1) ? p1[k + 1] : p1r));           // +x +z
+                     p = O::add(p, O::mul(a2, (k > 0) ? m1[r][k - 1] : m1l));              // -x -z
+                     p = O::add(p, O::mul(a2, p0[k]));                                     // +x -y
+                     p = O::add(p, O::mul(a2, m2[r][k]));                                  // -x +y
+                     p = O::add(p, O::mul(a2, (k > 0) ? c2[r][k - 1] : c2l));              // +y -z
+                     p = O::add(p, O::mul(a2, (k < VEC - 1) ? c0[r][k + 1] : c0r));        // -y +z
+                     p = O::add(p, O::mul(a2, (k > 0) ? p1[k - 1] : p1l));                 // +x -z
+                     p = O::add(p, O::mul(a2, (k < VEC - 1) ? m1[r][k + 1] : m1r));        // -x +z
                      o[k] = ((m >> k) & 1u) ? u0v[k] : p;
                   }
-                  if (m != VMASK) st_vec<Real, VEC>(u0p + (i64)r * Nzp, o);
+                  if (r < nrow && m != VMASK) st_vec<Real, VEC>(u0p + (i64)r * Nzp, o);
+               }
+#pragma unroll
+               for (int k = 0; k < VEC; k++) {
+                  m0[r][k] = c0[r][k], m1[r][k] = c1[r][k], m2[r][k] = c2[r][k];
+                  c0[r][k] = p0[k], c1[r][k] = p1[k], c2[r][k] = p2[k];
                }
             }
             release(gm);
@@ -653,7 +691,10 @@ static void air_cfg_shape(int cfg, int *rpt, int *nw) {
 }
 
 static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 Nz, i64 Nzp, i64 mwpr, void *u_a, void *u_b, void *mask,
-                         int cfg = 0) {
+                         int cfg = -1) {
+   // defaults (measured on B200, profiles/): 7-point: 15 consumer warps, 64 registers; 13-point FCC: its nine rotating
+   // row vectors need 80 registers to stay out of local memory -> 11 consumer warps (c3s: 264 us vs 294 us with cfg 0)
+   if (cfg < 0) cfg = fcc ? 5 : 0;
    t->ok = false;
    t->precision = precision, t->fcc = fcc, t->Nx = Nx, t->Ny = Ny, t->Nz = Nz, t->Nzp = Nzp, t->mwpr = mwpr;
    t->base[0] = u_a, t->base[1] = u_b, t->mask = mask;

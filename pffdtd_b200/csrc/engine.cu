@@ -125,6 +125,10 @@ struct pffdtd_engine {
    i64 *d_n = nullptr;   // device step counter read by k_io / k_fd
    i64 n_dev = -1;       // value the host knows it holds (-1 unknown)
    cudaGraphExec_t graph[2] = {nullptr, nullptr};  // two consecutive steps starting with cur = 0 / 1
+   cudaGraphExec_t hgraph[2] = {nullptr, nullptr};  // one host-driven step (H2D samples, step, D2H samples) with cur = 0 / 1
+   double hgraph_launches[2] = {0, 0};
+   void *in_stage = nullptr, *out_stage = nullptr;  // device staging of one step's source / receiver samples
+   int host_mode = 0;                               // the step being launched belongs to pffdtd_step_host
    double graph_launches[2] = {0, 0};
    int use_graph = 1;
    i64 steps_plain = 0;  // steps launched kernel by kernel so far
@@ -252,8 +256,10 @@ extern "C" int pffdtd_destroy(pffdtd_engine *e) {
       cudaEventDestroy(p.a);
       cudaEventDestroy(p.b);
    }
-   for (int c = 0; c < 2; c++)
+   for (int c = 0; c < 2; c++) {
       if (e->graph[c]) cudaGraphExecDestroy(e->graph[c]);
+      if (e->hgraph[c]) cudaGraphExecDestroy(e->hgraph[c]);
+   }
    if (e->ev_edge) cudaEventDestroy(e->ev_edge);
    if (e->ev_comm) cudaEventDestroy(e->ev_comm);
    if (e->ev_step) cudaEventDestroy(e->ev_step);
@@ -352,6 +358,8 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    if (dalloc_bytes(e, &e->zold, (size_t)(e->Nx * e->Ny * 2) * e->rs)) return PFFDTD_ECUDA;
    if (dalloc_bytes(e, &e->yold, (size_t)(e->Nx * 2 * e->Nzp) * e->rs)) return PFFDTD_ECUDA;
    if (dalloc_bytes(e, &e->xold, (size_t)(2 * e->Ny * e->Nzp) * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->in_stage, (size_t)e->Ns * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->out_stage, (size_t)e->Nr * e->rs)) return PFFDTD_ECUDA;
    CU(cudaMallocHost(&e->h_in, std::max<size_t>((size_t)e->Ns * 8, 64)));
    CU(cudaMallocHost(&e->h_out, std::max<size_t>((size_t)e->Nr * 8, 64)));
 
@@ -500,15 +508,19 @@ extern "C" int pffdtd_comm_init(pffdtd_engine *e, const void *id128, int rank, i
 // ------------------------------------------------------------------------------------------------
 // options / stats
 // ------------------------------------------------------------------------------------------------
+static void drop_graphs(pffdtd_engine *e) {
+   for (int c = 0; c < 2; c++) {
+      if (e->graph[c]) cudaGraphExecDestroy(e->graph[c]);
+      if (e->hgraph[c]) cudaGraphExecDestroy(e->hgraph[c]);
+      e->graph[c] = e->hgraph[c] = nullptr;
+   }
+}
+
 extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t value) {
    if (!e || !key) return fail(PFFDTD_EINVAL, "NULL argument");
    std::string k(key);
    // any option may change what a step launches: drop the captured graphs
-   for (int c = 0; c < 2; c++)
-      if (e->graph[c]) {
-         cudaGraphExecDestroy(e->graph[c]);
-         e->graph[c] = nullptr;
-      }
+   drop_graphs(e);
    e->steps_plain = 0;
    if (k == "use_graph") {
       e->use_graph = value != 0;
@@ -687,8 +699,10 @@ struct Step {
       }
       const i64 nr = p.recv ? e->Nr : 0;
       if (nr > 0 || p.ns > 0) {
-         pf::k_io<Real><<<nblk(std::max(nr, p.ns), 128), 128, 0, s>>>(u1, u0, e->out, (Real *)e->uout, nr, e->Nr, e->in,
-                                                                     (const Real *)e->insig, e->Ns, p.s0, p.ns, e->serial_src, e->d_n);
+         pf::k_io<Real><<<nblk(std::max(nr, p.ns), 128), 128, 0, s>>>(u1, u0, e->out, (Real *)e->uout, nr, e->Nr, e->in, (Real *)e->insig,
+                                                                     e->Ns, p.s0, p.ns, e->serial_src, e->d_n,
+                                                                     e->host_mode & 1 ? (const Real *)e->in_stage : nullptr,
+                                                                     e->host_mode & 2 ? (Real *)e->out_stage : nullptr);
          e->launches += 1;
       }
       if (fused && p.np > 0) {
@@ -773,11 +787,7 @@ extern "C" int pffdtd_energy_enable(pffdtd_engine *e, const pffdtd_energy_desc *
    if (dalloc(e, &e->en_in, (size_t)e->Nt + 1)) return PFFDTD_ECUDA;
    e->en_k = pf::EnergyCoef{e->fcc ? 2.0 : 1.0, d->h, d->c, e->l, e->l2};
    e->en_Ts = d->Ts;
-   for (int c = 0; c < 2; c++)
-      if (e->graph[c]) {
-         cudaGraphExecDestroy(e->graph[c]);
-         e->graph[c] = nullptr;
-      }
+   drop_graphs(e);
    e->halo_dirty = 1;
    e->energy_on = 1;
    return PFFDTD_OK;
@@ -902,6 +912,12 @@ static int step_impl(pffdtd_engine *e, i64 n) {
 
 static int step_any(pffdtd_engine *e, i64 n) { return e->precision == 1 ? step_impl<float>(e, n) : step_impl<double>(e, n); }
 
+// can a step starting now be replayed from a captured graph?
+static bool graphable(const pffdtd_engine *e) {
+   return e->use_graph && !e->energy_on && !e->comm && !e->profile_air && !e->manual_halo && e->steps_plain >= 2 &&
+          !(e->halo_dirty && e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok);
+}
+
 extern "C" int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps) {
    if (!e) return fail(PFFDTD_EINVAL, "NULL engine");
    if (nsteps < 0 || nstart < 0 || nstart + nsteps > e->Nt)
@@ -914,8 +930,7 @@ extern "C" int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps
    while (n < nend) {
       // two steps bring `cur` back: a captured pair replays as one CUDA graph (single GPU, fused or not,
       // once the halos are clean and the first plain steps have sized the launches)
-      const bool graph_ok = e->use_graph && !e->energy_on && !e->comm && !e->profile_air && !e->manual_halo && nend - n >= 2 && e->steps_plain >= 2 &&
-                            !(e->halo_dirty && e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok);
+      const bool graph_ok = nend - n >= 2 && graphable(e);
       if (graph_ok) {
          const int c = e->cur;
          if (e->n_dev != n) {
@@ -967,17 +982,57 @@ extern "C" int pffdtd_step_host(pffdtd_engine *e, int64_t n, const double *in_sa
    if ((!e->x_lo_edge || !e->x_hi_edge) && !e->comm && !e->manual_halo)
       return fail(PFFDTD_ESTATE, "slab engine without communicator: call pffdtd_comm_init");
    CU(cudaSetDevice(e->device));
-   if (in_samples && e->Ns) {
+   const bool has_in = in_samples && e->Ns, has_out = out_samples && e->Nr;
+   if (has_in) {
       if (e->precision == 1) for (i64 s = 0; s < e->Ns; s++) ((float *)e->h_in)[s] = (float)in_samples[s];
       else memcpy(e->h_in, in_samples, (size_t)e->Ns * 8);
-      CU(cudaMemcpyAsync((char *)e->insig + (size_t)(n * e->Ns) * e->rs, e->h_in, (size_t)e->Ns * e->rs, cudaMemcpyHostToDevice, e->s_main));
    }
-   int rc = step_any(e, n);
-   if (rc) return rc;
-   if (out_samples && e->Nr)
-      CU(cudaMemcpyAsync(e->h_out, (char *)e->uout + (size_t)(n * e->Nr) * e->rs, (size_t)e->Nr * e->rs, cudaMemcpyDeviceToHost, e->s_main));
+   int rc = PFFDTD_OK;
+   if (has_in && has_out && graphable(e)) {
+      // H2D of the source samples, the step, D2H of the receiver samples: one replayed graph per grid role
+      const int c = e->cur;
+      if (e->n_dev != n) {
+         pf::k_set_n<<<1, 1, 0, e->s_main>>>(e->d_n, n);
+         e->n_dev = n;
+      }
+      if (!e->hgraph[c]) {
+         cudaGraph_t g = nullptr;
+         const double l0 = e->launches;
+         const i64 nd = e->n_dev, sd = e->steps_done;
+         CU(cudaStreamBeginCapture(e->s_main, cudaStreamCaptureModeThreadLocal));
+         e->host_mode = 3;
+         cudaError_t ce = cudaMemcpyAsync(e->in_stage, e->h_in, (size_t)e->Ns * e->rs, cudaMemcpyHostToDevice, e->s_main);
+         rc = step_any(e, n);
+         if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->h_out, e->out_stage, (size_t)e->Nr * e->rs, cudaMemcpyDeviceToHost, e->s_main);
+         e->host_mode = 0;
+         cudaError_t ce2 = cudaStreamEndCapture(e->s_main, &g);
+         e->hgraph_launches[c] = e->launches - l0;
+         e->launches = l0, e->n_dev = nd, e->steps_done = sd, e->cur = c;  // nothing ran yet
+         if (rc) return rc;
+         if (ce != cudaSuccess || ce2 != cudaSuccess)
+            return fail(PFFDTD_ECUDA, "host-step graph capture: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ce2));
+         ce = cudaGraphInstantiate(&e->hgraph[c], g, 0);
+         cudaGraphDestroy(g);
+         if (ce != cudaSuccess) return fail(PFFDTD_ECUDA, "graph instantiate: %s", cudaGetErrorString(ce));
+      }
+      CU(cudaGraphLaunch(e->hgraph[c], e->s_main));
+      e->launches += e->hgraph_launches[c];
+      e->cur ^= 1;
+      e->n_dev = n + 1;
+      e->steps_done = n + 1;
+   } else {
+      e->host_mode = (has_in ? 1 : 0) | (has_out ? 2 : 0);
+      cudaError_t ce = cudaSuccess;
+      if (has_in) ce = cudaMemcpyAsync(e->in_stage, e->h_in, (size_t)e->Ns * e->rs, cudaMemcpyHostToDevice, e->s_main);
+      rc = step_any(e, n);
+      e->host_mode = 0;
+      if (rc) return rc;
+      if (ce != cudaSuccess) return fail(PFFDTD_ECUDA, "source sample upload: %s", cudaGetErrorString(ce));
+      e->steps_plain++;
+      if (has_out) CU(cudaMemcpyAsync(e->h_out, e->out_stage, (size_t)e->Nr * e->rs, cudaMemcpyDeviceToHost, e->s_main));
+   }
    CU(cudaStreamSynchronize(e->s_main));
-   if (out_samples) {
+   if (has_out) {
       if (e->precision == 1) for (i64 r = 0; r < e->Nr; r++) out_samples[r] = (double)((float *)e->h_out)[r];
       else memcpy(out_samples, e->h_out, (size_t)e->Nr * 8);
    }

@@ -284,21 +284,31 @@ __global__ void k_src(Real *__restrict__ u0, const i64 *__restrict__ in_ixyz, co
 
 // steps 8+9 in one launch: receivers (threads [0,Nr)) and sources (threads [0,ns)) touch different grids.
 // The time index comes from a device counter (so that a captured step can be replayed as a CUDA graph); `nr` = 0
-// for the parts of a step that do not read the receivers.
+// for the parts of a step that do not read the receivers.  Host-driven steps (pffdtd_step_host) pass fixed staging
+// buffers: `in_stage` holds this step's source samples (also filed into insig), `out_stage` receives a copy of the
+// receiver samples -- fixed addresses, so the host<->device copies can be nodes of the same replayed graph.
 template <typename Real>
 __global__ void k_io(const Real *__restrict__ u1, Real *__restrict__ u0, const i64 *__restrict__ out_ixyz, Real *__restrict__ uout,
-                     i64 Nr, i64 nr_all, const i64 *__restrict__ in_ixyz, const Real *__restrict__ insig, i64 Ns_all, i64 s0, i64 ns,
-                     int serial_src, const i64 *__restrict__ d_n) {
+                     i64 Nr, i64 nr_all, const i64 *__restrict__ in_ixyz, Real *__restrict__ insig, i64 Ns_all, i64 s0, i64 ns,
+                     int serial_src, const i64 *__restrict__ d_n, const Real *__restrict__ in_stage, Real *__restrict__ out_stage) {
    typedef Ops<Real> O;
    const i64 n = *d_n;
    Real *out_row = uout + n * nr_all;
-   const Real *in_row = insig + n * Ns_all;
+   Real *in_row = insig + n * Ns_all;
    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < Nr) out_row[i] = u1[out_ixyz[i]];
+   if (i < Nr) {
+      const Real v = u1[out_ixyz[i]];
+      out_row[i] = v;
+      if (out_stage) out_stage[i] = v;
+   }
    if (serial_src) {
       if (i == 0)
-         for (i64 s = s0; s < s0 + ns; s++) u0[in_ixyz[s]] = O::add(u0[in_ixyz[s]], in_row[s]);
+         for (i64 s = s0; s < s0 + ns; s++) {
+            if (in_stage) in_row[s] = in_stage[s];
+            u0[in_ixyz[s]] = O::add(u0[in_ixyz[s]], in_row[s]);
+         }
    } else if (i < ns) {
+      if (in_stage) in_row[s0 + i] = in_stage[s0 + i];
       u0[in_ixyz[s0 + i]] = O::add(u0[in_ixyz[s0 + i]], in_row[s0 + i]);
    }
 }

@@ -78,6 +78,27 @@ def test_step_host_matches_run_steps():
     assert np.array_equal(np.stack(cols, axis=1), ref)
 
 
+def test_step_host_mixes_with_run_steps_and_uploaded_signals():
+    """host-driven steps (plain launches, then the captured copy+step+copy graph) interleaved with device-driven
+    batches, with and without host source samples: one trace, bit for bit"""
+    sd = make_sim_data("cart_lossy_mb11", 2)
+    ref = Oracle(sd).run_all()
+    with Engine(sd) as e:
+        cols = []
+        n = 0
+        while n < sd.Nt:
+            if n % 10 < 6:
+                cols.append(e.step_host(n, sd.in_sigs[:, n] if n % 3 else None).copy())
+                n += 1
+            else:
+                k = min(4, sd.Nt - n)
+                e.run_steps(n, k)
+                cols.extend(e.read_outputs(n, n + k).T.copy())
+                n += k
+        whole = e.read_outputs()
+    assert np.array_equal(np.stack(cols, axis=1), ref) and np.array_equal(whole, ref)
+
+
 def test_run_sim_entry_point():
     sd = make_sim_data("cart_rigid", 2)
     out, t = run_sim(sd)
