@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--xc", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="engine option (pffdtd_set_option), repeatable (tuning / A-B runs)")
     ap.add_argument("--air-cfg", type=int, default=-1, help="tile configuration of the TMA air kernel (tuning)")
     ap.add_argument("--overlap", type=int, default=1, choices=(0, 1), help="N>1: 0 = halo exchange after the whole step (diagnostic)")
     args = ap.parse_args()
@@ -243,6 +244,10 @@ def main():
             "overlapped with the interior update on a second stream" if args.overlap else "after the step (not overlapped)")
     if args.xc:
         eng.set_option("air_xc", args.xc)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
+        config.setdefault("options", {})[k] = int(v)
     if args.air_cfg >= 0:
         eng.set_option("air_cfg", args.air_cfg)
         config["air_cfg"] = args.air_cfg

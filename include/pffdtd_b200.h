@@ -94,7 +94,9 @@ int pffdtd_comm_init(pffdtd_engine *e, const void *id128, int rank, int nranks);
  * "overlap" (1 = edge planes first, halo exchange overlapped with the interior [default]),
  * "air_cfg" (tile configuration), "air_xc" (x-chunk length), "profile_air" (CUDA events around every air launch),
  * "manual_halo" (allow stepping a slab without a communicator; the caller moves the halo planes),
- * "use_graph" (1 = replay captured steps as CUDA graphs [default]). */
+ * "use_graph" (1 = replay captured steps as CUDA graphs [default]), "fd_smem" (1 = the branch kernel keeps the material
+ * table in shared memory [default]), "abc_overlap" (1 = the absorbing-shell kernel runs beside the boundary kernels when no
+ * boundary / source node lies on the shell [default]). */
 int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t value);
 /* Counters/timers: "launches", "steps", "air_ms" / "air_launches_timed" (CUDA-event time of the air launches
  * since reset, with profile_air), "timer_start" / "timer_stop_ms" (device stopwatch on the engine's stream),

@@ -104,6 +104,7 @@ struct EvPair {
 struct pffdtd_engine {
    int device = 0, precision = 0, fcc = 0, Nm = 0, NN = 6;
    i64 Nx = 0, Ny = 0, Nz = 0, Nzp = 0, mwpr = 0, Nb = 0, Nbl = 0, Nba = 0, Ns = 0, Nr = 0, Nt = 0;
+   i64 Nblp = 0;  // pitch of the branch-major boundary state: Nbl rounded up to 32 elements
    i64 ix0 = 0;
    int x_lo_edge = 1, x_hi_edge = 1;
    double l = 0, l2 = 0, a1 = 0, a2 = 0, sl2 = 0, lo2 = 0;
@@ -151,6 +152,11 @@ struct pffdtd_engine {
    int rank = 0, nranks = 1, comm_pending = 0;
    // options
    int air_kernel = 1, overlap = 1, profile_air = 0, manual_halo = 0, fuse = 1;
+   int fd_smem = 1;      // k_fd reads the material table from shared memory
+   int abc_overlap = 1;  // the absorbing-shell kernel runs beside the boundary kernels when their node sets are disjoint
+   int abc_disjoint = 0, abc_pending = 0;
+   cudaStream_t s_abc = nullptr;
+   cudaEvent_t ev_abc0 = nullptr, ev_abc1 = nullptr;
    // stats
    i64 steps_done = 0;  // next time index expected by run_steps
    double launches = 0;
@@ -260,6 +266,9 @@ extern "C" int pffdtd_destroy(pffdtd_engine *e) {
       if (e->graph[c]) cudaGraphExecDestroy(e->graph[c]);
       if (e->hgraph[c]) cudaGraphExecDestroy(e->hgraph[c]);
    }
+   if (e->ev_abc0) cudaEventDestroy(e->ev_abc0);
+   if (e->ev_abc1) cudaEventDestroy(e->ev_abc1);
+   if (e->s_abc) cudaStreamDestroy(e->s_abc);
    if (e->ev_edge) cudaEventDestroy(e->ev_edge);
    if (e->ev_comm) cudaEventDestroy(e->ev_comm);
    if (e->ev_step) cudaEventDestroy(e->ev_step);
@@ -293,6 +302,7 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    e->Nzp = (d->Nz + 31) / 32 * 32;
    e->mwpr = (e->Nzp / 32 + 3) / 4 * 4;  // mask words per row, a multiple of 16 bytes (TMA stride)
    e->Nb = d->Nb, e->Nbl = d->Nbl, e->Nba = d->Nba, e->Ns = d->Ns, e->Nr = d->Nr, e->Nt = d->Nt;
+   e->Nblp = (d->Nbl + 31) / 32 * 32;
    e->ix0 = d->ix0, e->x_lo_edge = d->x_lo_edge, e->x_hi_edge = d->x_hi_edge;
    e->l = d->l, e->l2 = d->l2, e->a1 = d->a1, e->a2 = d->a2, e->sl2 = d->sl2, e->lo2 = d->lo2;
    for (i64 i = 0; i < d->Nbl; i++) {
@@ -313,6 +323,9 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
 
    CU(cudaStreamCreateWithFlags(&e->s_main, cudaStreamNonBlocking));
    CU(cudaStreamCreateWithFlags(&e->s_comm, cudaStreamNonBlocking));
+   CU(cudaStreamCreateWithFlags(&e->s_abc, cudaStreamNonBlocking));
+   CU(cudaEventCreateWithFlags(&e->ev_abc0, cudaEventDisableTiming));
+   CU(cudaEventCreateWithFlags(&e->ev_abc1, cudaEventDisableTiming));
    CU(cudaEventCreateWithFlags(&e->ev_edge, cudaEventDisableTiming));
    CU(cudaEventCreateWithFlags(&e->ev_comm, cudaEventDisableTiming));
    CU(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
@@ -350,8 +363,8 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    for (int k = 0; k < 2; k++)
       if (dalloc_bytes(e, &e->hist[k], (size_t)e->Nbl * e->rs)) return PFFDTD_ECUDA;
    if (dalloc_bytes(e, &e->u2ba, (size_t)e->Nba * e->rs)) return PFFDTD_ECUDA;
-   if (dalloc_bytes(e, &e->vh1, (size_t)e->Nbl * PFFDTD_MMB * e->rs)) return PFFDTD_ECUDA;
-   if (dalloc_bytes(e, &e->gh1, (size_t)e->Nbl * PFFDTD_MMB * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->vh1, (size_t)e->Nblp * PFFDTD_MMB * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->gh1, (size_t)e->Nblp * PFFDTD_MMB * e->rs)) return PFFDTD_ECUDA;
    if (dalloc_bytes(e, &e->lo2Kbg, (size_t)e->Nbl * e->rs)) return PFFDTD_ECUDA;
    if (dalloc_bytes(e, &e->facb, (size_t)e->Nbl * e->rs)) return PFFDTD_ECUDA;
    if (dalloc(e, &e->matmb, (size_t)e->Nbl)) return PFFDTD_ECUDA;
@@ -409,6 +422,16 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
          ok = Q > 0 && Q == d->Q_bna[i];
       }
       e->fuse_ok = ok;
+      // do boundary / source nodes stay clear of the shell (the usual case; the reference's Python engine assumes it,
+      // sim_fdtd.py:152)?  Then the shell kernel may run beside the boundary kernels.
+      auto on_shell = [&](i64 v) {
+         const i64 row = v / Nz, iz = v - row * Nz, ix = row / Ny, iy = row - ix * Ny;
+         return qx(ix) || iy == 1 || iy == Ny - 2 || iz == 1 || iz == Nz - 2;
+      };
+      bool clear = ok;
+      for (i64 i = 0; clear && i < e->Nb; i++) clear = !on_shell(d->bn_ixyz[i]);
+      for (i64 i = 0; clear && i < e->Ns; i++) clear = !on_shell(d->in_ixyz[i]);
+      e->abc_disjoint = clear;
    }
    // late halo mirrors: nodes written after the air kernel (boundary, source) whose value belongs in a halo
    if (e->fcc == 0) {
@@ -543,6 +566,10 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       CU(cudaStreamSynchronize(e->s_main));
       if (pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask, (int)value))
          return fail(PFFDTD_EINVAL, "air_cfg %lld: %s", (long long)value, e->tma.why.c_str());
+   } else if (k == "fd_smem") {
+      e->fd_smem = value != 0;
+   } else if (k == "abc_overlap") {
+      e->abc_overlap = value != 0;
    } else if (k == "manual_halo") {
       e->manual_halo = value != 0;
    } else {
@@ -590,6 +617,7 @@ extern "C" int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out) {
    else if (k == "fused") *out = (e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->energy_on) ? 1 : 0;
    else if (k == "energy") *out = e->energy_on;
    else if (k == "mirror_pairs") *out = (double)e->np;
+   else if (k == "abc_disjoint") *out = e->abc_disjoint;
    else return fail(PFFDTD_EINVAL, "unknown stat %s", key);
    return PFFDTD_OK;
 }
@@ -671,7 +699,16 @@ struct Step {
          fa.x_lo = e->x_lo_edge, fa.x_hi = e->x_hi_edge;
          fa.lQ1 = (Real)((Real)e->l * (Real)1), fa.lQ2 = (Real)((Real)e->l * (Real)2), fa.lQ3 = (Real)((Real)e->l * (Real)3);
          const i64 nt = (xe - xb) * e->Ny * 2 + (xe - xb) * 2 * e->Nz + 2 * e->Ny * e->Nz;
-         pf::k_abc_faces<Real><<<nblk(nt, 256), 256, 0, s>>>(fa);
+         if (e->abc_overlap && e->abc_disjoint) {
+            // no boundary or source node lies on the shell: the shell update commutes with the boundary kernels
+            CU(cudaEventRecord(e->ev_abc0, s));
+            CU(cudaStreamWaitEvent(e->s_abc, e->ev_abc0, 0));
+            pf::k_abc_faces<Real><<<nblk(nt, 256), 256, 0, e->s_abc>>>(fa);
+            CU(cudaEventRecord(e->ev_abc1, e->s_abc));
+            e->abc_pending = 1;
+         } else {
+            pf::k_abc_faces<Real><<<nblk(nt, 256), 256, 0, s>>>(fa);
+         }
          e->launches += 1;
       }
       return 0;
@@ -692,10 +729,20 @@ struct Step {
          e->launches += 1;
       }
       if (p.nbl > 0) {
-         pf::k_fd<Real, PFFDTD_MMB><<<nblk(p.nbl, 128), 128, 0, s>>>(u0, e->bnl, e->matmb, (const Real *)e->lo2Kbg, (const Real *)e->facb,
-                                                                    (Real *)e->hist[0], (Real *)e->hist[1], (Real *)e->vh1, (Real *)e->gh1,
-                                                                    p.l0, p.nbl, e->Nbl, (const Real *)e->quads, e->d_n);
+         const int nq = e->Nm * PFFDTD_MMB * 4;
+         if (e->fd_smem)
+            pf::k_fd<Real, PFFDTD_MMB, true><<<nblk(p.nbl, 128), 128, (size_t)nq * sizeof(Real), s>>>(
+                u0, e->bnl, e->matmb, (const Real *)e->lo2Kbg, (const Real *)e->facb, (Real *)e->hist[0], (Real *)e->hist[1], (Real *)e->vh1,
+                (Real *)e->gh1, p.l0, p.nbl, e->Nblp, (const Real *)e->quads, nq, e->d_n);
+         else
+            pf::k_fd<Real, PFFDTD_MMB, false><<<nblk(p.nbl, 128), 128, 0, s>>>(
+                u0, e->bnl, e->matmb, (const Real *)e->lo2Kbg, (const Real *)e->facb, (Real *)e->hist[0], (Real *)e->hist[1], (Real *)e->vh1,
+                (Real *)e->gh1, p.l0, p.nbl, e->Nblp, (const Real *)e->quads, nq, e->d_n);
          e->launches += 1;
+      }
+      if (e->abc_pending) {  // join the absorbing-shell kernel running beside the boundary kernels
+         CU(cudaStreamWaitEvent(s, e->ev_abc1, 0));
+         e->abc_pending = 0;
       }
       const i64 nr = p.recv ? e->Nr : 0;
       if (nr > 0 || p.ns > 0) {
@@ -727,14 +774,14 @@ static int energy_pre(pffdtd_engine *e, Real *u1, Real *u0, i64 n, cudaStream_t 
    pf::k_energy_int<Real><<<EB, pf::EN_THREADS, 0, s>>>(u1, u0, Lu, e->Nx, e->Ny, e->Nz, e->Nzp, e->l2, P);
    pf::k_energy_abc_corr<Real><<<nB, pf::EN_THREADS, 0, s>>>(u1, u0, Lu, e->bna, e->Q, e->Nba, e->l2, P + EB);
    pf::k_energy_branches<Real, PFFDTD_MMB><<<nC, pf::EN_THREADS, 0, s>>>((const Real *)e->ssaf, e->matmb, (const Real *)e->vh1, (const Real *)e->gh1,
-                                                                        e->Nbl, e->en_def, e->en_Ts, 0, P + 2 * EB);
+                                                                        e->Nbl, e->Nblp, e->en_def, e->en_Ts, 0, P + 2 * EB);
    pf::k_energy_finish_H<<<1, pf::EN_THREADS, 0, s>>>(P, P + EB, P + 2 * EB, EB, nB, nC, e->en_k, e->en_H, n);
    e->launches += 4;
    if (e->Ns) {
       pf::k_gather<Real><<<nblk(e->Ns, 128), 128, 0, s>>>(u0, e->in, (Real *)e->u2in, e->Ns);
       e->launches += 1;
    }
-   if (e->Nbl) CU(cudaMemcpyAsync(e->vold, e->vh1, (size_t)e->Nbl * PFFDTD_MMB * e->rs, cudaMemcpyDeviceToDevice, s));
+   if (e->Nbl) CU(cudaMemcpyAsync(e->vold, e->vh1, (size_t)e->Nblp * PFFDTD_MMB * e->rs, cudaMemcpyDeviceToDevice, s));
    // Lu <- Laplacian of state n, for the next step's H_tot (the reference keeps Lu1 the same way, sim_fdtd.py:603-604)
    const double lfac = e->fcc ? 0.25 : 1.0;
    dim3 blk(64, 4, 1), grd(nblk(e->Nzp, 64), nblk(e->Ny, 4), (unsigned)(e->Nx - 2));
@@ -756,7 +803,7 @@ static int energy_post(pffdtd_engine *e, Real *u0, i64 n, cudaStream_t s) {
    double *P = e->en_part;
    const int EB = pf::EN_BLOCKS, nD = en_blocks(e->Nbl), nE = en_blocks(e->Nba);
    pf::k_energy_branches<Real, PFFDTD_MMB><<<nD, pf::EN_THREADS, 0, s>>>((const Real *)e->ssaf, e->matmb, (const Real *)e->vh1, (const Real *)e->vold,
-                                                                        e->Nbl, e->en_def, e->en_Ts, 1, P + 3 * EB);
+                                                                        e->Nbl, e->Nblp, e->en_def, e->en_Ts, 1, P + 3 * EB);
    pf::k_energy_abc_loss<Real><<<nE, pf::EN_THREADS, 0, s>>>(u0, (const Real *)e->u2ba, e->bna, e->Q, e->Nba, P + 4 * EB);
    pf::k_energy_in<Real><<<1, pf::EN_THREADS, 0, s>>>(u0, (const Real *)e->u2in, e->in, (const Real *)e->insig + n * e->Ns, e->Ns, P + 5 * EB);
    pf::k_energy_finish_E<<<1, pf::EN_THREADS, 0, s>>>(P + 3 * EB, P + 4 * EB, P + 5 * EB, nD, nE, e->en_k, e->en_lost, e->en_in, n);
@@ -777,7 +824,7 @@ extern "C" int pffdtd_energy_enable(pffdtd_engine *e, const pffdtd_energy_desc *
    CU(cudaStreamSynchronize(e->s_main));
    const size_t npad = (size_t)(e->Nx * e->Ny * e->Nzp);
    if (dalloc_bytes(e, &e->Lu, npad * e->rs)) return PFFDTD_ECUDA;
-   if (dalloc_bytes(e, &e->vold, (size_t)e->Nbl * PFFDTD_MMB * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->vold, (size_t)e->Nblp * PFFDTD_MMB * e->rs)) return PFFDTD_ECUDA;
    if (dalloc_bytes(e, &e->u2in, (size_t)e->Ns * e->rs)) return PFFDTD_ECUDA;
    if (dalloc(e, &e->en_def, (size_t)std::max(e->Nm, 1) * PFFDTD_MMB * 3)) return PFFDTD_ECUDA;
    if (e->Nm && d->mat_DEF) CU(cudaMemcpy(e->en_def, d->mat_DEF, (size_t)e->Nm * PFFDTD_MMB * 3 * 8, cudaMemcpyHostToDevice));
@@ -1102,14 +1149,14 @@ extern "C" int pffdtd_read_boundary_state(pffdtd_engine *e, double *vh1, double 
    CU(cudaSetDevice(e->device));
    int rc = pffdtd_sync(e);
    if (rc) return rc;
-   const size_t n = (size_t)e->Nbl * PFFDTD_MMB;
-   if (n == 0) return PFFDTD_OK;
+   const size_t n = (size_t)e->Nblp * PFFDTD_MMB;
+   if (e->Nbl == 0) return PFFDTD_OK;
    std::vector<char> tv(n * e->rs), tg(n * e->rs);
    CU(cudaMemcpy(tv.data(), e->vh1, tv.size(), cudaMemcpyDeviceToHost));
    CU(cudaMemcpy(tg.data(), e->gh1, tg.size(), cudaMemcpyDeviceToHost));
    for (i64 i = 0; i < e->Nbl; i++)
       for (int m = 0; m < PFFDTD_MMB; m++) {
-         const size_t src = (size_t)m * e->Nbl + i, dst = (size_t)i * PFFDTD_MMB + m;
+         const size_t src = (size_t)m * e->Nblp + i, dst = (size_t)i * PFFDTD_MMB + m;
          vh1[dst] = e->precision == 1 ? (double)((float *)tv.data())[src] : ((double *)tv.data())[src];
          gh1[dst] = e->precision == 1 ? (double)((float *)tg.data())[src] : ((double *)tg.data())[src];
       }

@@ -214,20 +214,29 @@ __global__ void k_fd_prep(const int8_t *__restrict__ mat_bnl, const Real *__rest
    matmb[i] = (uint16_t)((unsigned)k | ((unsigned)mt.Mb[k] << 8));
 }
 
-template <typename Real, int MMB>
+// `Nbl` below is the PITCH of the branch-major state arrays (the node count rounded up to 32 elements, so that a warp's
+// 32 consecutive nodes are one aligned 128-byte line for every branch).  SQ: the material table is staged in shared
+// memory (4*Mb coefficient reads per node become LDS instead of L1 hits).
+template <typename Real, int MMB, bool SQ>
 __global__ void __launch_bounds__(128) k_fd(Real *__restrict__ u0, const i64 *__restrict__ bnl, const uint16_t *__restrict__ matmb,
                                             const Real *__restrict__ lo2Kbg_bnl, const Real *__restrict__ fac_bnl,
                                             Real *__restrict__ hist0, Real *__restrict__ hist1, Real *__restrict__ vh1,
-                                            Real *__restrict__ gh1, i64 i0, i64 n, i64 Nbl, const Real *__restrict__ quads,
+                                            Real *__restrict__ gh1, i64 i0, i64 n, i64 Nbl, const Real *__restrict__ quads, int nquads,
                                             const i64 *__restrict__ d_n) {
    typedef Ops<Real> O;
+   extern __shared__ __align__(16) unsigned char fd_smem[];
+   if (SQ) {
+      Real *qs = reinterpret_cast<Real *>(fd_smem);
+      for (int t = threadIdx.x; t < nquads; t += blockDim.x) qs[t] = quads[t];
+      __syncthreads();
+   }
    const i64 i = i0 + n - 1 - ((i64)blockIdx.x * blockDim.x + threadIdx.x);  // descending, see k_rigid
    if (i < i0) return;
    const Real one = (Real)1.0, two = (Real)2.0;
    Real *hist = (*d_n & 1) ? hist1 : hist0;  // the value two steps back lives in the buffer of the step's parity
    const unsigned mm = matmb[i];
    const int Mb = (int)(mm >> 8);
-   const Real *q = quads + (i64)(mm & 0xffu) * MMB * 4;
+   const Real *q = (SQ ? reinterpret_cast<const Real *>(fd_smem) : quads) + (i64)(mm & 0xffu) * MMB * 4;
    // everything this node needs from memory is requested up front; the dependent gather (index -> u0) first
    const i64 c = bnl[i];
    const Real u0c = u0[c];
