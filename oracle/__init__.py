@@ -123,22 +123,24 @@ class Reference:
         return p.exists() or REF_SRC.exists()
 
     @classmethod
-    def lib(cls, precision):
-        if precision not in cls._libs:
-            L = C.CDLL(_need(HERE / "_ref" / f"libpffdtd_ref_f{32 if precision == 1 else 64}.so"))
+    def lib(cls, precision, gpu=False):
+        """gpu=True: the reference's own CUDA engine (c_cuda/gpu_engine.h), a performance comparator (tools/ref_gpu_engine.py)"""
+        key = (precision, bool(gpu))
+        if key not in cls._libs:
+            L = C.CDLL(_need(HERE / "_ref" / f"libpffdtd_ref{'gpu' if gpu else ''}_f{32 if precision == 1 else 64}.so"))
             L.refdrv_put.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
             L.refdrv_load.argtypes = [C.c_char_p]
             L.refdrv_run_sim.restype = C.c_double
             L.refdrv_field.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int)]
             L.refdrv_get_dataset.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_uint64]
             assert L.refdrv_precision() == precision
-            cls._libs[precision] = L
-        return cls._libs[precision]
+            cls._libs[key] = L
+        return cls._libs[key]
 
-    def __init__(self, precision, files: dict, data_dir, threads=None):
+    def __init__(self, precision, files: dict, data_dir, threads=None, gpu=False):
         """files: {'sim_consts': {...}, ...} datasets; data_dir: folder holding the four .h5 files
         (the reference loader stat()s them)."""
-        self.L = self.lib(precision)
+        self.L = self.lib(precision, gpu)
         self.precision = precision
         self.real = np.float32 if precision == 1 else np.float64
         self.L.refdrv_clear()

@@ -15,7 +15,9 @@
  * host prep (pffdtd_b200/sim_data.py) field by field; (3) generate tests/golden/ fixtures;
  * (4) the CPU baseline arm of bench.py ("kind": "reference").
  */
+#ifndef _DEFAULT_SOURCE
 #define _DEFAULT_SOURCE
+#endif
 #include <stdio.h>
 #include <stdlib.h>
 #include <stdint.h>
@@ -33,7 +35,18 @@
 #include <helper_funcs.h>
 #include <fdtd_common.h>
 #include <fdtd_data.h>
+#if USING_CUDA
+#include <gpu_engine.h> /* the reference's own CUDA engine, a PERFORMANCE COMPARATOR only (tools/ref_gpu_engine.py); built by nvcc -x cu */
+#else
 #include <cpu_engine.h>
+#endif
+
+/* nvcc compiles this file as C++ (the reference's Makefile does the same to fdtd_main.c): keep the entry points unmangled */
+#ifdef __cplusplus
+#define REFDRV_API extern "C"
+#else
+#define REFDRV_API
+#endif
 
 /* ------------------------------------------------------------------------------------------
  * in-memory dataset registry
@@ -71,14 +84,14 @@ static struct dset_rec *find_dset(const char *file, const char *name) {
    return NULL;
 }
 
-void refdrv_clear(void) {
+REFDRV_API void refdrv_clear(void) {
    for (int i = 0; i < g_ndsets; i++) free(g_dsets[i].data);
    g_ndsets = 0;
    g_nfiles = 0;
    g_nspaces = 0;
 }
 
-int refdrv_put(const char *file, const char *name, int dtype, int ndims, const int64_t *dims, const void *data) {
+REFDRV_API int refdrv_put(const char *file, const char *name, int dtype, int ndims, const int64_t *dims, const void *data) {
    if (g_ndsets >= MAX_DSETS || ndims > 4) return -1;
    struct dset_rec *r = find_dset(file, name);
    if (r == NULL) r = &g_dsets[g_ndsets++];
@@ -198,14 +211,14 @@ static void quiet_end(int saved) {
    close(saved);
 }
 
-void refdrv_set_quiet(int q) { g_quiet = q; }
-void refdrv_set_threads(int n) { omp_set_num_threads(n); }
-int refdrv_max_threads(void) { return omp_get_max_threads(); }
-int refdrv_precision(void) { return PRECISION; }
+REFDRV_API void refdrv_set_quiet(int q) { g_quiet = q; }
+REFDRV_API void refdrv_set_threads(int n) { omp_set_num_threads(n); }
+REFDRV_API int refdrv_max_threads(void) { return omp_get_max_threads(); }
+REFDRV_API int refdrv_precision(void) { return PRECISION; }
 
 /* runs the reference load_sim_data(); `dir` must contain the four (real) .h5 files because the
  * loader stat()s them (fdtd_data.h:143) before "opening" them through the shim */
-int refdrv_load(const char *dir) {
+REFDRV_API int refdrv_load(const char *dir) {
    char cwd[4096];
    if (getcwd(cwd, sizeof cwd) == NULL) return -1;
    if (chdir(dir) != 0) return -2;
@@ -218,14 +231,14 @@ int refdrv_load(const char *dir) {
    if (chdir(cwd) != 0) return -3;
    return 0;
 }
-void refdrv_scale_input(void) { int s = quiet_begin(); scale_input(&g_sd); quiet_end(s); }
-double refdrv_run_sim(void) { int s = quiet_begin(); double t = run_sim(&g_sd); quiet_end(s); return t; }
-void refdrv_rescale_output(void) { int s = quiet_begin(); rescale_output(&g_sd); quiet_end(s); }
+REFDRV_API void refdrv_scale_input(void) { int s = quiet_begin(); scale_input(&g_sd); quiet_end(s); }
+REFDRV_API double refdrv_run_sim(void) { int s = quiet_begin(); double t = run_sim(&g_sd); quiet_end(s); return t; }
+REFDRV_API void refdrv_rescale_output(void) { int s = quiet_begin(); rescale_output(&g_sd); quiet_end(s); }
 /* reference write_outputs() -> lands in the registry as ("sim_outs.h5","u_out") */
-void refdrv_write_outputs(void) { int s = quiet_begin(); g_nfiles = 0; write_outputs(&g_sd); quiet_end(s); }
-void refdrv_free(void) { int s = quiet_begin(); if (g_loaded) free_sim_data(&g_sd); g_loaded = false; quiet_end(s); }
+REFDRV_API void refdrv_write_outputs(void) { int s = quiet_begin(); g_nfiles = 0; write_outputs(&g_sd); quiet_end(s); }
+REFDRV_API void refdrv_free(void) { int s = quiet_begin(); if (g_loaded) free_sim_data(&g_sd); g_loaded = false; quiet_end(s); }
 
-int refdrv_get_dataset(const char *file, const char *name, void *out, uint64_t nbytes) {
+REFDRV_API int refdrv_get_dataset(const char *file, const char *name, void *out, uint64_t nbytes) {
    struct dset_rec *r = find_dset(file, name);
    if (r == NULL || r->nbytes != nbytes) return -1;
    memcpy(out, r->data, nbytes);
@@ -233,7 +246,7 @@ int refdrv_get_dataset(const char *file, const char *name, void *out, uint64_t n
 }
 
 /* field access into the reference's struct SimData (fdtd_data.h:38-76) */
-int refdrv_field(const char *f, const void **ptr, int64_t *count, int *elsize) {
+REFDRV_API int refdrv_field(const char *f, const void **ptr, int64_t *count, int *elsize) {
    const struct SimData *sd = &g_sd;
    int64_t Nbm = (sd->Npts - 1) / 8 + 1;
 #define FIELD_ARR(nm, cnt) if (strcmp(f, #nm) == 0) { *ptr = sd->nm; *count = (cnt); *elsize = (int)sizeof(*sd->nm); return 0; }
