@@ -25,13 +25,23 @@ CASES = {
     "fcc2_wide": (dict(Nx=18, Ny=44, Nz=150, Nt=30, fcc=True, nmat=1, mb=2), "fcc2"),
     "fcc1_wide": (dict(Nx=16, Ny=38, Nz=140, Nt=30, fcc=True, nmat=1, mb=2), "fcc1"),
     "fcc2_rigid": (dict(Nx=26, Ny=24, Nz=40, Nt=40, fcc=True, rigid=True), "fcc2"),
+    # edge cases: the maximum branch count (MMb = 12, fdtd_data.h:33); a room without any boundary node (empty lists: only the
+    # absorbing shell acts); one plane more than the minimum the voxeliser can produce in x
+    "cart_mb12": (dict(Nx=22, Ny=20, Nz=26, Nt=50, nmat=2, mb=12), "cart"),
+    "cart_empty": (dict(Nx=18, Ny=17, Nz=35, Nt=70, nmat=1, mb=2, _empty=True), "cart"),
+    "fcc2_empty": (dict(Nx=20, Ny=18, Nz=34, Nt=50, fcc=True, nmat=1, mb=2, _empty=True), "fcc2"),
 }
 
 
 def make_files(name):
     kw, layout = CASES[name]
     kw = dict(kw)
+    empty = kw.pop("_empty", False)
     files = shoebox.make_shoebox(kw.pop("Nx"), kw.pop("Ny"), kw.pop("Nz"), kw.pop("Nt"), **kw)
+    if empty:  # no walls at all: Nb = Nbl = 0
+        nn = 12 if kw.get("fcc") else 6
+        files["vox_out"].update(Nb=np.int64(0), bn_ixyz=np.zeros(0, np.int64), adj_bn=np.zeros((0, nn), bool),
+                                mat_bn=np.zeros(0, np.int8), saf_bn=np.zeros(0))
     if layout == "fcc2":
         files = folder_prep.gpu_folder(files)
     return files

@@ -99,6 +99,31 @@ def test_step_host_mixes_with_run_steps_and_uploaded_signals():
     assert np.array_equal(np.stack(cols, axis=1), ref) and np.array_equal(whole, ref)
 
 
+@pytest.mark.parametrize("precision", (2, 1))
+def test_no_receivers_no_sources_no_steps(precision):
+    """empty receiver / source lists and a zero-step run are legal descriptions"""
+    from dataclasses import replace
+    sd = make_sim_data("cart_lossy", precision)
+    z = np.zeros(0, np.int64)
+    quiet = replace(sd, in_ixyz=z, in_sigs=np.zeros((0, sd.Nt)), _keep=[])
+    with Engine(quiet) as e:
+        e.run_steps(0, quiet.Nt)
+        assert np.array_equal(e.read_outputs(), np.zeros((sd.Nr, sd.Nt)))
+    deaf = replace(sd, out_ixyz=z, out_reorder=z, _keep=[])
+    g1, g0 = noise_grids(sd)
+    o = Oracle(deaf)
+    with Engine(deaf) as e:
+        for x in (o, e):
+            x.write_grid(1, g1)
+            x.write_grid(0, g0)
+            x.run_steps(0, 20)
+        assert e.read_outputs().shape == (0, sd.Nt)
+        assert np.array_equal(e.read_grid(1)[1:-1, 1:-1, 1:-1], o.read_grid(1)[1:-1, 1:-1, 1:-1])
+    with Engine(sd) as e:
+        e.run_steps(0, 0)
+        assert not e.read_outputs().any()
+
+
 def test_run_sim_entry_point():
     sd = make_sim_data("cart_rigid", 2)
     out, t = run_sim(sd)

@@ -32,6 +32,8 @@ for n in range(sd.Nt):
 u = parallel.gather_rows(o.u_out[:, :sd.Nt])
 payload = parallel.broadcast_bytes(b"id-from-rank-0" if rank == 0 else None)
 assert payload == b"id-from-rank-0"
+tot = parallel.sum_arrays(np.arange(5.0) * (rank + 1))   # what adds the per-slab energy sums
+assert np.array_equal(tot, np.arange(5.0) * (world * (world + 1) // 2))
 if rank == 0:
     np.save(out, full.reorder_output(full.rescale_output(u)))
 '''
