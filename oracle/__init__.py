@@ -124,7 +124,7 @@ class Reference:
 
     @classmethod
     def lib(cls, precision, gpu=False):
-        """gpu=True: the reference's own CUDA engine (c_cuda/gpu_engine.h), a performance comparator (tools/ref_gpu_engine.py)"""
+        """gpu=True: the reference's own CUDA engine (c_cuda/gpu_engine.h), a performance comparator (tests/diag/compare_reference_gpu_engine.py)"""
         key = (precision, bool(gpu))
         if key not in cls._libs:
             L = C.CDLL(_need(HERE / "_ref" / f"libpffdtd_ref{'gpu' if gpu else ''}_f{32 if precision == 1 else 64}.so"))

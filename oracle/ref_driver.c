@@ -36,7 +36,7 @@
 #include <fdtd_common.h>
 #include <fdtd_data.h>
 #if USING_CUDA
-#include <gpu_engine.h> /* the reference's own CUDA engine, a PERFORMANCE COMPARATOR only (tools/ref_gpu_engine.py); built by nvcc -x cu */
+#include <gpu_engine.h> /* the reference's own CUDA engine, a PERFORMANCE COMPARATOR only (tests/diag/compare_reference_gpu_engine.py); built by nvcc -x cu */
 #else
 #include <cpu_engine.h>
 #endif

@@ -1,8 +1,8 @@
-"""Performance comparator (not part of the product, not part of bench.py): the reference's OWN CUDA engine
+"""TEST INFRASTRUCTURE -- performance comparator (not part of the product, not part of bench.py): the reference's OWN CUDA engine
 (c_cuda/gpu_engine.h, unmodified, compiled for sm_100a by oracle/Makefile into oracle/_ref/libpffdtd_refgpu_*.so) on the
 same B200 and the same inputs as this repo's engine.  Prints one JSON line per workload:
 
-    python tools/ref_gpu_engine.py --workload c2 --steps 200
+    python tests/diag/compare_reference_gpu_engine.py --workload c2 --steps 200
 
 Both engines run `--steps` time steps of the bench workload from the same in-memory files; throughput is
 Npts*steps / loop seconds for both (the reference's own clock, gpu_engine.h:1253; ours the same wall clock around
@@ -20,7 +20,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 import bench  # noqa: E402
 

@@ -1,7 +1,7 @@
-"""where does the fused step differ from the oracle?  python tools/diag_noise.py case precision cfg steps"""
+"""where does the fused step differ from the oracle?  python tests/diag/diag_noise.py case precision cfg steps"""
 import sys
 from pathlib import Path
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import numpy as np
 from cases import make_sim_data, noise_grids

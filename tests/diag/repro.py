@@ -1,5 +1,8 @@
+"""does the CUDA path equal the oracle on one case?  python tests/diag/repro.py <case> <precision>   (diagnostic, uses the test oracle)"""
 import sys
-sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent.parent
+sys.path.insert(0, str(ROOT / "tests")); sys.path.insert(0, str(ROOT))
 import numpy as np
 from cases import make_sim_data
 from oracle import Oracle
