@@ -46,6 +46,11 @@ WORKLOADS = {
     "c5": dict(N=(2048, 2048, 1024), precision=1, fcc=False, nmat=1, mb=11, rigid=False,
                desc="BASELINE configs[4]: shoebox 2048x2048x1024, 7-pt Cartesian, fp32, lossy walls, x-slabs + NCCL halo exchange"),
     "small": dict(N=(128, 96, 64), precision=1, fcc=False, nmat=1, mb=11, rigid=False, desc="smoke-sized shoebox"),
+    # the real rooms at full size, voxelised by the reference tool chain (tools/make_large_models.py -> data_large/, not committed)
+    "ctk_real": dict(folder="data_large/ctk_cart_gpu", precision=1, fcc=False,
+                     desc="BASELINE configs[1] with the real model: CTK church, h = 0.041 m, 7-pt Cartesian, fp32, 8 materials x 11 branches"),
+    "mv_real": dict(folder="data_large/mv_fcc_gpu", precision=1, fcc=True,
+                    desc="BASELINE configs[2] with the real model: Musikverein, h = 0.06 m, 13-pt FCC folded, fp32, 5 materials x 11 branches"),
 }
 BYTES_PER_NODE = {1: 12.125, 2: 24.125}  # u1 read + u0 read + u0 write + 1 mask bit
 # CPU-arm sample grids for workloads whose full grid would take the CPU engine minutes per step
@@ -58,6 +63,17 @@ CPU_SAMPLE_GRID = {
 def build_problem(wl, Nt, x_range=None):
     from pffdtd_b200 import folder_prep, shoebox
     w = WORKLOADS[wl]
+    if "folder" in w:  # a sim_setup folder: keep everything, stretch / cut the source signals to Nt steps (zeros after the end)
+        d = ROOT / w["folder"]
+        if not (d / "vox_out.h5").exists():
+            raise SystemExit(f"{d} missing: python tools/make_large_models.py (needs the reference tool chain)")
+        files = folder_prep.load_folder(d)
+        cm = files["comms_out"]
+        sig = np.asarray(cm["in_sigs"], np.float64)
+        out = np.zeros((sig.shape[0], Nt))
+        out[:, :min(Nt, sig.shape[1])] = sig[:, :Nt]
+        cm["in_sigs"], cm["Nt"] = out, np.int64(Nt)
+        return files
     Nx, Ny, Nz = w["N"]
     files = shoebox.make_shoebox(Nx, Ny, Nz, Nt, fcc=w["fcc"], nmat=w["nmat"], mb=max(w["mb"], 1), rigid=w["rigid"], diff=True,
                                  x_range=x_range)
@@ -147,8 +163,12 @@ def run_reference_cpu(wl, steps, warmup, budget_s=120.0, threads=None):
         sample_note = CPU_SAMPLE_GRID[wl][1]
         wl = wl + "_cpu_sample"
         w = WORKLOADS[wl]
+    if "folder" in w and "N" not in w:
+        from pffdtd_b200 import h5lite
+        v = h5lite.File(ROOT / w["folder"] / "vox_out.h5")
+        w = WORKLOADS[wl] = dict(w, N=tuple(int(v[k][()]) for k in ("Nx", "Ny", "Nz")))
     Npts = int(np.prod(w["N"]))
-    if w["fcc"]:
+    if w["fcc"] and "folder" not in w:
         Npts = w["N"][0] * (w["N"][1] // 2 + 1) * w["N"][2]
     # bound the sample: size it for ~0.8 Gvox/s (the pool's 16-core hosts measure 1.2-3.2), then report what was actually run
     per_step = Npts / 0.8e9
@@ -200,8 +220,16 @@ def main():
     wl = args.workload or ("c2" if N == 1 else "c5")
     w = WORKLOADS[wl]
     K, W = args.steps, max(args.warmup, 3)
-    Nx, Ny, Nz = w["N"]
-    Ny_st = Ny // 2 + 1 if w["fcc"] else Ny
+    if "folder" in w:  # stored grid of the folder (already folded for FCC)
+        from pffdtd_b200 import h5lite
+        v = h5lite.File(ROOT / w["folder"] / "vox_out.h5")
+        Nx, Ny, Nz = (int(v[k][()]) for k in ("Nx", "Ny", "Nz"))
+        Ny_st = Ny
+        w = dict(w, N=(Nx, Ny, Nz))
+        WORKLOADS[wl] = w
+    else:
+        Nx, Ny, Nz = w["N"]
+        Ny_st = Ny // 2 + 1 if w["fcc"] else Ny
     Npts = Nx * Ny_st * Nz
     config = {"workload": wl, "description": w["desc"], "grid": [Nx, Ny_st, Nz], "stencil": "13pt_fcc_folded" if w["fcc"] else "7pt_cartesian",
               "l2": "state (2 grids, %.0f MB) is larger than the 126 MB L2" % (2 * Npts * (4 if w["precision"] == 1 else 8) / 1e6)}

@@ -416,6 +416,11 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
          expect += qx(ix) ? (Ny - 2) * (Nz - 2) : (Ny - 2) * (Nz - 2) - std::max<i64>(inner, 0);
       }
       bool ok = (Ny >= 4 && Nz >= 4) && expect == e->Nba && ascending(d->bna_ixyz, e->Nba);
+      // mirror-on-write finds the source z = Nz-3 of the halo z = Nz-1 in the SAME z tile (or the lane before); when the
+      // shell node z = Nz-2 opens a tile (tile width 32 vectors = 128 nodes fp32 / 64 fp64) the source sits in another CTA's
+      // tile: such grids (Nz = 2 mod tile width) take the unfused step (tests: cart_nz_e, cart_nz_f)
+      const i64 tile_z = 32 * (16 / (i64)e->rs);
+      if ((Nz - 2) % tile_z == 0) ok = false;
       for (i64 i = 0; ok && i < e->Nba; i++) {
          const i64 v = d->bna_ixyz[i], row = v / Nz, iz = v - row * Nz, ix = row / Ny, iy = row - ix * Ny;
          const int Q = qx(ix) + ((iy == 1 || iy == Ny - 2) ? 1 : 0) + ((iz == 1 || iz == Nz - 2) ? 1 : 0);

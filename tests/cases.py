@@ -20,6 +20,9 @@ CASES = {
     "cart_nz_b": (dict(Nx=16, Ny=19, Nz=134, Nt=40, nmat=1, mb=2), "cart"),
     "cart_nz_c": (dict(Nx=16, Ny=18, Nz=135, Nt=40, nmat=1, mb=2), "cart"),
     "cart_nz_d": (dict(Nx=16, Ny=20, Nz=68, Nt=40, nmat=1, mb=2), "cart"),
+    # the shell node z = Nz-2 opens a z tile (tile width 128 nodes in fp32, 64 in fp64): its mirror source z = Nz-3 lives in the tile before
+    "cart_nz_e": (dict(Nx=16, Ny=19, Nz=130, Nt=40, nmat=1, mb=2), "cart"),
+    "cart_nz_f": (dict(Nx=16, Ny=18, Nz=66, Nt=40, nmat=1, mb=2), "cart"),
     "fcc1_lossy": (dict(Nx=24, Ny=20, Nz=18, Nt=50, fcc=True, nmat=2, mb=3), "fcc1"),
     "fcc2_lossy": (dict(Nx=24, Ny=20, Nz=18, Nt=50, fcc=True, nmat=2, mb=3), "fcc2"),
     "fcc2_wide": (dict(Nx=18, Ny=44, Nz=150, Nt=30, fcc=True, nmat=1, mb=2), "fcc2"),

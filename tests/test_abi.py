@@ -39,6 +39,17 @@ def test_desc_layout_matches_the_header():
     assert pffdtd_desc.Nx.offset == o_nx and pffdtd_desc.ix0.offset == o_ix0 and pffdtd_desc.mat_quads.offset == o_quads
 
 
+def test_energy_desc_layout_matches_the_header():
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "pffdtd_b200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(pffdtd_energy_desc), ' \
+          'offsetof(pffdtd_energy_desc, h), offsetof(pffdtd_energy_desc, mat_DEF));return 0;}\n'
+    tmp = Path(subprocess.run(["mktemp", "-d"], capture_output=True, text=True).stdout.strip())
+    (tmp / "t.c").write_text(src)
+    subprocess.run(["/usr/bin/gcc", "-I", str(ROOT / "include"), str(tmp / "t.c"), "-o", str(tmp / "t")], check=True)
+    size, o_h, o_def = map(int, subprocess.run([str(tmp / "t")], capture_output=True, text=True).stdout.split())
+    d = engine.pffdtd_energy_desc
+    assert C.sizeof(d) == size and d.h.offset == o_h and d.mat_DEF.offset == o_def
+
+
 def test_kernels_are_sm_100a_tma_code():
     """the shipped library holds sm_100a SASS with TMA tensor loads (UTMALDG) for the air kernel"""
     out = subprocess.run(["cuobjdump", "-sass", str(engine.LIB_PATH)], capture_output=True, text=True).stdout

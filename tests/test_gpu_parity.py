@@ -24,7 +24,9 @@ def _engine(sd, ak, fuse):
     e.set_option("air_kernel", ak)
     e.set_option("fuse", fuse)
     if ak == 1 and fuse == 1:
-        assert e.stat("fused") == 1
+        # the fused step is refused (engine falls back to the unfused kernels) only when the shell node z = Nz-2 opens a z tile
+        tile_z = 128 if sd.precision == 1 else 64
+        assert e.stat("fused") == (0 if (sd.Nz - 2) % tile_z == 0 else 1)
     return e
 
 
@@ -43,6 +45,7 @@ def test_traces_bit_exact(name, precision):
 
 @pytest.mark.parametrize("precision", (2, 1))
 @pytest.mark.parametrize("name", ("cart_lossy", "cart_ragged", "cart_tight", "cart_tight0", "cart_nz_a", "cart_nz_b", "cart_nz_c", "cart_nz_d",
+                                  "cart_nz_e", "cart_nz_f",
                                   "fcc1_lossy", "fcc2_lossy", "fcc1_wide", "fcc2_wide"))
 def test_full_state_bit_exact_from_noise(name, precision):
     """whole grids + boundary ODE state after 25 steps from a random initial state: exercises every
