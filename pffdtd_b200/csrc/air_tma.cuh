@@ -42,6 +42,7 @@ struct AirTma {
    void *base[2] = {nullptr, nullptr};
    void *mask = nullptr;
    int cfg = 0;         // tile configuration, see PF_AIR_CONFIGS
+   int z_edge = 0;      // the shell node z = Nz-2 opens a z tile of this configuration: no fused step
    int xc = 0;          // planes per (long) x-chunk of the work order, 0 = default
    int sm_count = 148;
    int slots = 0;       // resident CTAs of the chosen configuration on this device
@@ -102,11 +103,14 @@ __device__ __forceinline__ void st_vec(Real *p, const Real (&d)[VEC]) {
    *reinterpret_cast<V *>(p) = v;
 }
 
-template <typename Real, int RPT, int NW, int S>
+// LZ = lanes of a warp along z (32, 16 or 8); the other 32/LZ = LR lane groups take further rows, so a warp covers
+// LZ vectors x LR*RPT rows.  Narrow tiles cut the padding a grid pays when Nz is not a multiple of 32 vectors.
+template <typename Real, int RPT, int NW, int S, int LZ = 32>
 struct AirCfg {
    static constexpr int VEC = 16 / (int)sizeof(Real);
-   static constexpr int TZ = 32 * VEC;
-   static constexpr int TY = NW * RPT;
+   static constexpr int LR = 32 / LZ;
+   static constexpr int TZ = LZ * VEC;
+   static constexpr int TY = NW * RPT * LR;
    static constexpr int BZ = TZ + 2 * VEC;  // u1 box starts one vector left of the tile: 16-byte aligned columns
    static constexpr int ROWS = TY + 2;
    static constexpr int MKW = 4;            // mask words per tile row in a stage (TZ/32 used, 16-byte TMA minimum)
@@ -279,12 +283,12 @@ __global__ void k_abc_faces(const FacesArgs<Real> a) {
 // full[s] flips when all bytes of a plane have landed in stage s, empty[s] when all NW consumer warps
 // are done with it.  Loads are numbered consecutively over all segments of the CTA; load i uses stage
 // i % S.  A segment of cnt planes loads planes xa-1 .. xa+cnt: the first and the last only as u1.
-template <typename Real, int RPT, int NW, int S, int MAXR, bool FCC>
+template <typename Real, int RPT, int NW, int S, int MAXR, bool FCC, int LZ>
 __global__ void __maxnreg__(MAXR)
     k_air_tma_cart(const __grid_constant__ CUtensorMap map_u1, const __grid_constant__ CUtensorMap map_u0,
                    const __grid_constant__ CUtensorMap map_mk, Real *__restrict__ u0g, const AirJob jb, const Real a1, const Real a2,
                    const AirEdge<Real> eg) {
-   typedef AirCfg<Real, RPT, NW, S> C;
+   typedef AirCfg<Real, RPT, NW, S, LZ> C;
    typedef Ops<Real> O;
    constexpr int VEC = C::VEC, BZ = C::BZ, TZ = C::TZ;
    constexpr uint32_t VMASK = (1u << VEC) - 1u;
@@ -298,6 +302,8 @@ __global__ void __maxnreg__(MAXR)
    int4 *hdr = (int4 *)(empty + S);  // per stage: the item (xa, cnt, z0, y0) whose first plane it holds; cnt < 0 = stop
 
    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+   const int lz = lane % LZ;                     // this thread's vector within its row
+   const int wr = w * C::LR + lane / LZ;         // this thread's row group within the tile ("virtual warp")
 
    if (tid == 0) {
       for (int s = 0; s < S; s++) {
@@ -367,9 +373,8 @@ __global__ void __maxnreg__(MAXR)
       if (lane == 0) mbar_arrive(&empty[g.s]);
    };
    auto stage = [&](const Ring &g) -> const unsigned char * { return smem + g.s * C::STAGE_PITCH; };
-   const int soff = (w * RPT + 1) * BZ + VEC + VEC * lane;  // strip row 0 inside the u1 box (box row 0 is y0-1)
-   const int u0off = C::U0_OFF + ((w * RPT) * TZ + VEC * lane) * (int)sizeof(Real);
-   const int mshift = (VEC * lane) & 31;
+   const int soff = (wr * RPT + 1) * BZ + VEC + VEC * lz;  // strip row 0 inside the u1 box (box row 0 is y0-1)
+   const int u0off = C::U0_OFF + ((wr * RPT) * TZ + VEC * lz) * (int)sizeof(Real);
    const int Ny = jb.Ny, Nz = jb.Nz, Nzp = jb.Nzp;
    const bool fuse = eg.fuse != 0;
 
@@ -379,10 +384,11 @@ __global__ void __maxnreg__(MAXR)
       const int4 h = hdr[g0.s];
       if (h.y < 0) break;  // stop marker
       const AirSeg sg = {h.x, h.y, h.z, h.w};
-      // this thread's strip: rows y0 + w*RPT + r, columns z0 + VEC*lane .. +VEC-1
-      const int zv = sg.z0 + VEC * lane;
-      const int ybase = sg.y0 + w * RPT;
-      const int mkoff = C::MK_OFF + ((w * RPT) * C::MKW + ((zv & 127) >> 5)) * 4;  // the stage holds the words of z0 & ~127 ..
+      // this thread's strip: rows y0 + wr*RPT + r, columns z0 + VEC*lz .. +VEC-1
+      const int zv = sg.z0 + VEC * lz;
+      const int ybase = sg.y0 + wr * RPT;
+      const int mkoff = C::MK_OFF + ((wr * RPT) * C::MKW + ((zv & 127) >> 5)) * 4;  // the stage holds the words of z0 & ~127 ..
+      const int mshift = zv & 31;
       int nrow = 0;  // active rows of the strip; vectors entirely in the far halo/padding are never touched
 #pragma unroll
       for (int r = 0; r < RPT; r++) nrow += (zv < Nz - 1 && (ybase + r) <= Ny - 2) ? 1 : 0;
@@ -412,15 +418,15 @@ __global__ void __maxnreg__(MAXR)
          // from shared memory: 73 wavefronts per row-vector, the LSU data pipe 94 % busy -- the kernel's bound).
          // Every lane runs the loads and shuffles (out-of-grid parts of a box are zero-filled); only the store is
          // predicated.  The sum runs in the reference's order.
-         const bool edge_lane = lane == 0 || lane == 31;
-         const int eoff = lane == 0 ? -1 : VEC;  // where an edge lane finds its out-of-warp neighbour in a box row
+         const bool edge_lane = lz == 0 || lz == LZ - 1;
+         const int eoff = lz == 0 ? -1 : VEC;  // where an edge lane finds its out-of-row neighbour in a box row
          auto zleft = [&](const Real(&v)[VEC], const Real e) {
             const Real t = __shfl_up_sync(0xffffffffu, v[VEC - 1], 1);
-            return lane == 0 ? e : t;
+            return lz == 0 ? e : t;
          };
          auto zright = [&](const Real(&v)[VEC], const Real e) {
             const Real t = __shfl_down_sync(0xffffffffu, v[0], 1);
-            return lane == 31 ? e : t;
+            return lz == LZ - 1 ? e : t;
          };
          Ring gm = g0;  // plane x-1
          Ring gc = g0;  // plane x
@@ -441,7 +447,6 @@ __global__ void __maxnreg__(MAXR)
             }
          }
          Real *u0p = u0g + ((i64)sg.xa * Ny + ybase) * Nzp + zv;
-         const bool row_warp = ybase <= Ny - 2;  // warp-uniform: the strip has at least one row inside the grid
          for (int j = 0; j < sg.cnt; j++) {
             Ring gu = gc;  // plane x+1
             gu.next();
@@ -456,7 +461,8 @@ __global__ void __maxnreg__(MAXR)
                ld_vec<Real, VEC>(su + (r - 1) * BZ, p0);
                ld_vec<Real, VEC>(su + r * BZ, p1);
                ld_vec<Real, VEC>(su + (r + 1) * BZ, p2);
-               if (row_warp && ybase + r <= Ny - 2) {  // warp-uniform
+               {
+                  // every lane of the warp takes part (shuffles); rows beyond the grid compute on zero-filled stages
                   Real em1 = (Real)0, ec0 = (Real)0, ec2 = (Real)0, ep1 = (Real)0;
                   if (edge_lane) {
                      em1 = sm[r * BZ + eoff];
@@ -551,6 +557,9 @@ __global__ void __maxnreg__(MAXR)
 #pragma unroll
          for (int r = 0; r < RPT; r++) {
             if (r < nrow) {
+               // the lanes of this warp whose vector holds interior nodes; taken before any row-dependent branch (with
+               // LZ < 32 the row groups of a warp can differ in their shell / mirror roles)
+               const unsigned am = __activemask();
                Real u0v[VEC];
                ld_vec<Real, VEC>((const Real *)(stc + u0off) + r * TZ, u0v);
                const uint32_t m = (*(const uint32_t *)(stc + mkoff + r * C::MKW * 4) >> mshift) & VMASK;
@@ -571,7 +580,7 @@ __global__ void __maxnreg__(MAXR)
                   o[k] = ((m >> k) & 1u) ? u0v[k] : p;
                }
                Real *dst = u0p + (i64)r * Nzp;
-               const unsigned rrole = ((yrole >> (3 * r)) & 7u) | xrole;  // warp-uniform
+               const unsigned rrole = ((yrole >> (3 * r)) & 7u) | xrole;  // uniform within a row group
                // Fused extras.  Everything lane-dependent below is written as selects / single predicated stores:
                // a divergent branch here would make the one lane at a z end run the rest of the step on its own.
                const bool shell = (rrole & 1u) != 0;
@@ -585,15 +594,15 @@ __global__ void __maxnreg__(MAXR)
                // Mirror targets that live in ANOTHER active lane's vector are delivered by a shuffle (that lane stores
                // its whole vector; a scalar store from here would race with it); only a target in a vector nobody
                // stores (the row's far padding) is written directly.
-               const unsigned am = __activemask();  // the lanes of this warp whose vector holds interior nodes
+               __syncwarp(am);  // the row groups may have diverged on `shell`
                if (zlo_tile) {  // warp-uniform: the tile starts at z = 0
                   // lane 0 holds z=1 (shell): stash its pre-update value; z=2 -> z=0 mirror
-                  if (lane == 0 && !shell) zop[2 * r] = u0v[1];
+                  if (lz == 0 && !shell) zop[2 * r] = u0v[1];
                   if constexpr (VEC >= 4) {
-                     o[0] = (lane == 0) ? o[2] : o[0];
+                     o[0] = (lz == 0) ? o[2] : o[0];
                   } else {
-                     const Real t = __shfl_down_sync(am, o[0], 1);  // fp64: z=2 is the first element of lane 1
-                     o[0] = (lane == 0) ? t : o[0];
+                     const Real t = __shfl_down_sync(am, o[0], 1);  // fp64: z=2 is the first element of the next lane
+                     o[0] = (lz == 0) ? t : o[0];
                   }
                }
                Real vm = o[0];  // value of z = Nz-3 if this thread holds it
@@ -608,6 +617,8 @@ __global__ void __maxnreg__(MAXR)
 #pragma unroll
                   for (int k = 0; k + 2 < VEC; k++) o[k + 2] = (k == khm) ? o[k] : o[k + 2];  // z=Nz-3 -> z=Nz-1 inside the vector
                   // a vector that starts at z=Nz-2 holds z=Nz-1 as element 1 and finds z=Nz-3 at the end of the previous lane's
+                  // (never the first vector of a tile: the engine refuses the fused step for such grids, AirTma::z_edge)
+                  __syncwarp(am);
                   const Real t = __shfl_up_sync(am, o[VEC - 1], 1);
                   o[1] = (khs == 0) ? t : o[1];
                }
@@ -654,47 +665,70 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// tile configurations (id, rows per thread, consumer warps, stages, register cap); cfg 0 is the default
+// tile configurations (id, rows per thread, consumer warps, stages, register cap, lanes along z); 0 / 5 are the defaults for
+// whole-tile grids (7-point / FCC), 8..11 their narrow-tile versions for ragged Nz (see air_pick_cfg)
 #define PF_AIR_CONFIGS(X) \
-   X(0, 1, 15, 6, 64)     \
-   X(1, 2, 8, 4, 72)      \
-   X(2, 2, 8, 6, 112)     \
-   X(3, 1, 15, 4, 64)     \
-   X(4, 4, 8, 3, 112)     \
-   X(5, 1, 11, 6, 80)     \
-   X(6, 2, 12, 4, 72)     \
-   X(7, 1, 8, 6, 80)
-#define PF_AIR_NCFG 8
+   X(0, 1, 15, 6, 64, 32)   \
+   X(1, 2, 8, 4, 72, 32)    \
+   X(2, 2, 8, 6, 112, 32)   \
+   X(3, 1, 15, 4, 64, 32)   \
+   X(4, 4, 8, 3, 112, 32)   \
+   X(5, 1, 11, 6, 80, 32)   \
+   X(6, 2, 12, 4, 72, 32)   \
+   X(7, 1, 8, 6, 80, 32)    \
+   X(8, 1, 15, 6, 64, 16)   \
+   X(9, 1, 15, 6, 64, 8)    \
+   X(10, 1, 11, 6, 80, 16)  \
+   X(11, 1, 11, 6, 80, 8)
+#define PF_AIR_NCFG 12
 
 template <typename Real>
 static int air_tma_attr(int cfg) {
    cudaError_t rc = cudaErrorInvalidValue;
-#define X(id, RPT, NW, S, MAXR)                                                                                     \
-   if (cfg == id) {                                                                                                        \
-      rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                AirCfg<Real, RPT, NW, S>::SMEM_BYTES);                                                       \
-      if (rc == cudaSuccess)                                                                                               \
-         rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                   AirCfg<Real, RPT, NW, S>::SMEM_BYTES);                                                    \
+#define X(id, RPT, NW, S, MAXR, LZ)                                                                                     \
+   if (cfg == id) {                                                                                                            \
+      rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, false, LZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                AirCfg<Real, RPT, NW, S, LZ>::SMEM_BYTES);                                                       \
+      if (rc == cudaSuccess)                                                                                                   \
+         rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   AirCfg<Real, RPT, NW, S, LZ>::SMEM_BYTES);                                                    \
    }
    PF_AIR_CONFIGS(X)
 #undef X
    return (int)rc;
 }
 
-static void air_cfg_shape(int cfg, int *rpt, int *nw) {
-   *rpt = 4, *nw = 8;
-#define X(id, RPT, NW, S, MAXR) \
-   if (cfg == id) *rpt = RPT, *nw = NW;
+static void air_cfg_shape(int cfg, int *rpt, int *nw, int *lz) {
+   *rpt = 4, *nw = 8, *lz = 32;
+#define X(id, RPT, NW, S, MAXR, LZ) \
+   if (cfg == id) *rpt = RPT, *nw = NW, *lz = LZ;
    PF_AIR_CONFIGS(X)
 #undef X
+}
+
+// default configuration for a grid: the widest tile (32, 16, 8 lanes along z) that wastes less than 12 % of its columns on the
+// padding behind Nz-1, else the one that wastes least.  Real rooms need this: the reference's gpu folders make z the SHORTEST
+// axis (CTK church Nz = 180: 70 % useful columns with 32 lanes, 93 % with 16; Musikverein Nz = 258: 67 % / 80 % / 89 %).
+static int air_pick_cfg(int fcc, int precision, i64 Nz) {
+   const int vec = precision == 1 ? 4 : 2;
+   const int ids[3] = {fcc ? 5 : 0, fcc ? 10 : 8, fcc ? 11 : 9};
+   const int lzs[3] = {32, 16, 8};
+   int best = 0;
+   double best_eff = 0;
+   for (int k = 0; k < 3; k++) {
+      const i64 tz = (i64)lzs[k] * vec, cols = (Nz - 1 + tz - 1) / tz * tz;
+      const double eff = (double)(Nz - 1) / (double)cols;
+      if (eff >= 0.88) return ids[k];
+      if (eff > best_eff + 1e-9) best_eff = eff, best = k;
+   }
+   return ids[best];
 }
 
 static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 Nz, i64 Nzp, i64 mwpr, void *u_a, void *u_b, void *mask,
                          int cfg = -1) {
    // defaults (measured on B200, profiles/): 7-point: 15 consumer warps, 64 registers; 13-point FCC: its nine rotating
    // row vectors need 80 registers to stay out of local memory -> 11 consumer warps (c3s: 264 us vs 294 us with cfg 0)
-   if (cfg < 0) cfg = fcc ? 5 : 0;
+   if (cfg < 0) cfg = air_pick_cfg(fcc, precision, Nz);
    t->ok = false;
    t->precision = precision, t->fcc = fcc, t->Nx = Nx, t->Ny = Ny, t->Nz = Nz, t->Nzp = Nzp, t->mwpr = mwpr;
    t->base[0] = u_a, t->base[1] = u_b, t->mask = mask;
@@ -719,13 +753,17 @@ static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 
    EncodeTiledFn encode = (EncodeTiledFn)fn;
    const size_t rs = precision == 1 ? 4 : 8;
    const int VEC = 16 / (int)rs;
-   int rpt, nw;
-   air_cfg_shape(cfg, &rpt, &nw);
+   int rpt, nw, lz;
+   air_cfg_shape(cfg, &rpt, &nw, &lz);
+   const int ty = nw * rpt * (32 / lz);
+   // mirror-on-write finds the source z = Nz-3 of the halo z = Nz-1 in the same z tile; when the shell node z = Nz-2 opens a tile
+   // the source sits in another CTA's tile and the fused step must not be used (tests cart_nz_e / cart_nz_f)
+   t->z_edge = ((Nz - 2) % ((i64)lz * VEC) == 0) ? 1 : 0;
    const CUtensorMapDataType dt = precision == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
    const cuuint64_t gdim[3] = {(cuuint64_t)Nzp, (cuuint64_t)Ny, (cuuint64_t)Nx};
    const cuuint64_t gstr[2] = {(cuuint64_t)Nzp * rs, (cuuint64_t)Ny * Nzp * rs};
-   const cuuint32_t box1[3] = {(cuuint32_t)(32 * VEC + 2 * VEC), (cuuint32_t)(nw * rpt + 2), 1};
-   const cuuint32_t box0[3] = {(cuuint32_t)(32 * VEC), (cuuint32_t)(nw * rpt), 1};
+   const cuuint32_t box1[3] = {(cuuint32_t)(lz * VEC + 2 * VEC), (cuuint32_t)(ty + 2), 1};
+   const cuuint32_t box0[3] = {(cuuint32_t)(lz * VEC), (cuuint32_t)ty, 1};
    const cuuint32_t estr[3] = {1, 1, 1};
    CUresult r = CUDA_SUCCESS;
    for (int k = 0; k < 2 && r == CUDA_SUCCESS; k++) {
@@ -738,7 +776,7 @@ static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 
    if (r == CUDA_SUCCESS) {
       const cuuint64_t mdim[3] = {(cuuint64_t)mwpr, (cuuint64_t)Ny, (cuuint64_t)Nx};
       const cuuint64_t mstr[2] = {(cuuint64_t)mwpr * 4, (cuuint64_t)Ny * mwpr * 4};
-      const cuuint32_t mbox[3] = {4, (cuuint32_t)(nw * rpt), 1};
+      const cuuint32_t mbox[3] = {4, (cuuint32_t)ty, 1};
       r = encode(&t->map_mk, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, mask, mdim, mstr, mbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
    }
@@ -760,10 +798,10 @@ static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 
    return 0;
 }
 
-template <typename Real, int RPT, int NW, int S, int MAXR>
+template <typename Real, int RPT, int NW, int S, int MAXR, int LZ>
 static int air_tma_launch_cfg(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real a1, Real a2, const AirEdge<Real> &eg, cudaStream_t s) {
-   typedef AirCfg<Real, RPT, NW, S> C;
-   auto kern = t->fcc ? k_air_tma_cart<Real, RPT, NW, S, MAXR, true> : k_air_tma_cart<Real, RPT, NW, S, MAXR, false>;
+   typedef AirCfg<Real, RPT, NW, S, LZ> C;
+   auto kern = t->fcc ? k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ> : k_air_tma_cart<Real, RPT, NW, S, MAXR, false, LZ>;
    if (t->slots <= 0) {
       int per_sm = 0;
       cudaError_t rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, C::SMEM_BYTES);
@@ -807,8 +845,8 @@ static int air_tma_launch_cfg(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real
 // planes [xb, xe) of the slab; `cur` = index of the grid that currently is u1 (u0 = the other one)
 template <typename Real>
 static int air_tma_launch(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real a1, Real a2, const AirEdge<Real> &eg, cudaStream_t s) {
-#define X(id, RPT, NW, S, MAXR) \
-   if (t->cfg == id) return air_tma_launch_cfg<Real, RPT, NW, S, MAXR>(t, cur, u0, xb, xe, a1, a2, eg, s);
+#define X(id, RPT, NW, S, MAXR, LZ) \
+   if (t->cfg == id) return air_tma_launch_cfg<Real, RPT, NW, S, MAXR, LZ>(t, cur, u0, xb, xe, a1, a2, eg, s);
    PF_AIR_CONFIGS(X)
 #undef X
    return (int)cudaErrorInvalidValue;

@@ -416,11 +416,6 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
          expect += qx(ix) ? (Ny - 2) * (Nz - 2) : (Ny - 2) * (Nz - 2) - std::max<i64>(inner, 0);
       }
       bool ok = (Ny >= 4 && Nz >= 4) && expect == e->Nba && ascending(d->bna_ixyz, e->Nba);
-      // mirror-on-write finds the source z = Nz-3 of the halo z = Nz-1 in the SAME z tile (or the lane before); when the
-      // shell node z = Nz-2 opens a tile (tile width 32 vectors = 128 nodes fp32 / 64 fp64) the source sits in another CTA's
-      // tile: such grids (Nz = 2 mod tile width) take the unfused step (tests: cart_nz_e, cart_nz_f)
-      const i64 tile_z = 32 * (16 / (i64)e->rs);
-      if ((Nz - 2) % tile_z == 0) ok = false;
       for (i64 i = 0; ok && i < e->Nba; i++) {
          const i64 v = d->bna_ixyz[i], row = v / Nz, iz = v - row * Nz, ix = row / Ny, iy = row - ix * Ny;
          const int Q = qx(ix) + ((iy == 1 || iy == Ny - 2) ? 1 : 0) + ((iz == 1 || iz == Nz - 2) ? 1 : 0);
@@ -619,7 +614,7 @@ extern "C" int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out) {
       *out = ms;
    } else if (k == "air_kernel") *out = e->air_kernel;
    else if (k == "Nzp") *out = (double)e->Nzp;
-   else if (k == "fused") *out = (e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->energy_on) ? 1 : 0;
+   else if (k == "fused") *out = (e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge && !e->energy_on) ? 1 : 0;
    else if (k == "energy") *out = e->energy_on;
    else if (k == "mirror_pairs") *out = (double)e->np;
    else if (k == "abc_disjoint") *out = e->abc_disjoint;
@@ -896,7 +891,7 @@ static int exchange(pffdtd_engine *e, void *unew, cudaStream_t s) {
 template <typename Real>
 static int step_impl(pffdtd_engine *e, i64 n) {
    if (n < 0 || n >= e->Nt) return fail(PFFDTD_EINVAL, "step %lld outside [0,%lld)", (long long)n, (long long)e->Nt);
-   const bool fused = e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->energy_on;
+   const bool fused = e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge && !e->energy_on;
    Step<Real> st{e, (Real *)e->u[e->cur], (Real *)e->u[e->cur ^ 1], e->s_main, n, fused};
    Real *u1 = st.u1, *u0 = st.u0;
    cudaStream_t s = e->s_main;
@@ -967,7 +962,7 @@ static int step_any(pffdtd_engine *e, i64 n) { return e->precision == 1 ? step_i
 // can a step starting now be replayed from a captured graph?
 static bool graphable(const pffdtd_engine *e) {
    return e->use_graph && !e->energy_on && !e->comm && !e->profile_air && !e->manual_halo && e->steps_plain >= 2 &&
-          !(e->halo_dirty && e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok);
+          !(e->halo_dirty && e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge);
 }
 
 extern "C" int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps) {

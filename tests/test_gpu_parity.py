@@ -19,15 +19,18 @@ def _kernels(sd):
     return ((0, 0), (1, 0), (1, 1)) if sd.fcc_flag == 0 else ((0, 0), (1, 0))  # FCC: generic and tiled 13-point kernels
 
 
-def _engine(sd, ak, fuse):
+def _engine(sd, ak, fuse, cfg=None):
     e = Engine(sd)
     e.set_option("air_kernel", ak)
     e.set_option("fuse", fuse)
-    if ak == 1 and fuse == 1:
-        # the fused step is refused (engine falls back to the unfused kernels) only when the shell node z = Nz-2 opens a z tile
-        tile_z = 128 if sd.precision == 1 else 64
-        assert e.stat("fused") == (0 if (sd.Nz - 2) % tile_z == 0 else 1)
+    if cfg is not None:
+        e.set_option("air_cfg", cfg)
     return e
+
+
+def _fused_expected(sd, lz):
+    """the fused step is refused only when the shell node z = Nz-2 opens a z tile (tile = lz vectors of 16 bytes)"""
+    return (sd.Nz - 2) % (lz * (4 if sd.precision == 1 else 2)) != 0
 
 
 @pytest.mark.parametrize("precision", (2, 1))
@@ -71,6 +74,39 @@ def test_full_state_bit_exact_from_noise(name, precision):
             v, g = e.read_boundary_state()
             vo, go = o.read_boundary_state()
             assert np.array_equal(v, vo) and np.array_equal(g, go)
+
+
+# tile configurations of the TMA kernel: (id, lanes along z); 0/8/9 = 7-point defaults, 5/10/11 = FCC defaults (air_tma.cuh)
+TILE_CFGS = {"cart": ((0, 32), (8, 16), (9, 8)), "fcc": ((5, 32), (10, 16), (11, 8))}
+
+
+@pytest.mark.parametrize("precision", (2, 1))
+@pytest.mark.parametrize("name", ("cart_lossy_mb11", "cart_ragged", "cart_wide", "cart_tight", "cart_tight0", "cart_nz_a", "cart_nz_b", "cart_nz_c",
+                                  "cart_nz_d", "cart_nz_e", "cart_nz_f", "fcc1_lossy", "fcc2_lossy", "fcc1_wide", "fcc2_wide"))
+def test_every_tile_width_gives_the_same_bits(name, precision):
+    """32, 16 and 8 lanes along z (the narrow tiles serve grids whose Nz is not a multiple of 32 vectors), fused and not:
+    whole grids + boundary state after 25 steps from noise, against the oracle"""
+    sd = make_sim_data(name, precision)
+    g1, g0 = noise_grids(sd)
+    o = Oracle(sd)
+    o.write_grid(1, g1)
+    o.write_grid(0, g0)
+    o.run_steps(0, 25)
+    want = [o.read_grid(1)[1:-1, 1:-1, 1:-1], o.read_grid(0)[1:-1, 1:-1, 1:-1]]
+    vo, go = o.read_boundary_state()
+    for cfg, lz in TILE_CFGS["cart" if sd.fcc_flag == 0 else "fcc"]:
+        for fuse in ((0, 1) if sd.fcc_flag == 0 else (0,)):
+            with _engine(sd, 1, fuse, cfg) as e:
+                if fuse:
+                    assert e.stat("fused") == (1 if _fused_expected(sd, lz) else 0)
+                e.write_grid(1, g1)
+                e.write_grid(0, g0)
+                e.run_steps(0, 25)
+                for which in (1, 0):
+                    a = e.read_grid(which)[1:-1, 1:-1, 1:-1]
+                    assert np.array_equal(a, want[1 - which]), f"{name} p{precision} cfg={cfg} fuse={fuse} grid{which}: {np.abs(a - want[1 - which]).max():.3e}"
+                v, g = e.read_boundary_state()
+                assert np.array_equal(v, vo) and np.array_equal(g, go)
 
 
 def test_step_host_matches_run_steps():
