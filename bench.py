@@ -291,6 +291,8 @@ def main():
         eng.set_option("air_cfg", args.air_cfg)
         config["air_cfg"] = args.air_cfg
     t_prep = time.perf_counter() - t_prep
+    if args.air_kernel == 1:
+        config["air_tile"] = {"cfg": int(eng.stat("air_cfg")), "lanes_z": int(eng.stat("air_lanes_z")), "fused_step": bool(eng.stat("fused"))}
 
     def barrier():
         eng.sync()

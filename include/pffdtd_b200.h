@@ -100,7 +100,8 @@ int pffdtd_comm_init(pffdtd_engine *e, const void *id128, int rank, int nranks);
 int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t value);
 /* Counters/timers: "launches", "steps", "air_ms" / "air_launches_timed" (CUDA-event time of the air launches
  * since reset, with profile_air), "timer_start" / "timer_stop_ms" (device stopwatch on the engine's stream),
- * "fused", "mirror_pairs", "air_kernel", "Nzp", "energy". */
+ * "fused", "mirror_pairs", "air_kernel", "air_cfg" / "air_lanes_z" (tile configuration in use: 32, 16 or 8 lanes of a warp along z),
+ * "abc_disjoint", "Nzp", "energy". */
 int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out);
 int pffdtd_reset_stats(pffdtd_engine *e);
 

@@ -994,8 +994,10 @@ extern "C" int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps
             cudaError_t ce = cudaStreamEndCapture(e->s_main, &g);
             e->graph_launches[c] = e->launches - l0;
             e->launches = l0, e->n_dev = nd, e->steps_done = sd;  // nothing ran yet
-            if (rc) return rc;
-            if (ce != cudaSuccess) return fail(PFFDTD_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
+            if (rc || ce != cudaSuccess) {
+               if (g) cudaGraphDestroy(g);
+               return rc ? rc : fail(PFFDTD_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
+            }
             ce = cudaGraphInstantiate(&e->graph[c], g, 0);
             cudaGraphDestroy(g);
             if (ce != cudaSuccess) return fail(PFFDTD_ECUDA, "graph instantiate: %s", cudaGetErrorString(ce));
@@ -1055,9 +1057,10 @@ extern "C" int pffdtd_step_host(pffdtd_engine *e, int64_t n, const double *in_sa
          cudaError_t ce2 = cudaStreamEndCapture(e->s_main, &g);
          e->hgraph_launches[c] = e->launches - l0;
          e->launches = l0, e->n_dev = nd, e->steps_done = sd, e->cur = c;  // nothing ran yet
-         if (rc) return rc;
-         if (ce != cudaSuccess || ce2 != cudaSuccess)
-            return fail(PFFDTD_ECUDA, "host-step graph capture: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ce2));
+         if (rc || ce != cudaSuccess || ce2 != cudaSuccess) {
+            if (g) cudaGraphDestroy(g);
+            return rc ? rc : fail(PFFDTD_ECUDA, "host-step graph capture: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ce2));
+         }
          ce = cudaGraphInstantiate(&e->hgraph[c], g, 0);
          cudaGraphDestroy(g);
          if (ce != cudaSuccess) return fail(PFFDTD_ECUDA, "graph instantiate: %s", cudaGetErrorString(ce));
