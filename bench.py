@@ -292,7 +292,10 @@ def main():
         config["air_cfg"] = args.air_cfg
     t_prep = time.perf_counter() - t_prep
     if args.air_kernel == 1:
-        config["air_tile"] = {"cfg": int(eng.stat("air_cfg")), "lanes_z": int(eng.stat("air_lanes_z")), "fused_step": bool(eng.stat("fused"))}
+        try:  # informational only: never let a missing counter cost the bench line
+            config["air_tile"] = {"cfg": int(eng.stat("air_cfg")), "lanes_z": int(eng.stat("air_lanes_z")), "fused_step": bool(eng.stat("fused"))}
+        except Exception as ex:  # noqa: BLE001
+            config["air_tile"] = {"error": repr(ex)}
 
     def barrier():
         eng.sync()

@@ -613,7 +613,12 @@ extern "C" int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out) {
       CU(cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1));
       *out = ms;
    } else if (k == "air_kernel") *out = e->air_kernel;
-   else if (k == "Nzp") *out = (double)e->Nzp;
+   else if (k == "air_cfg") *out = e->tma.ok ? e->tma.cfg : -1;
+   else if (k == "air_lanes_z") {
+      int rpt = 0, nw = 0, lz = 0;
+      pf::air_cfg_shape(e->tma.cfg, &rpt, &nw, &lz);
+      *out = e->tma.ok ? lz : 0;
+   } else if (k == "Nzp") *out = (double)e->Nzp;
    else if (k == "fused") *out = (e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge && !e->energy_on) ? 1 : 0;
    else if (k == "energy") *out = e->energy_on;
    else if (k == "mirror_pairs") *out = (double)e->np;
