@@ -122,6 +122,25 @@ class SimEngine:
         for n in range(max(self.Nt - Np, 0), self.Nt):
             self.print(f"normalised energy balance:{energy_balance(self.H_tot, self.E_lost, self.E_in)[n]:.16e}")
 
+    def gather_slice(self, ix=None, iy=None, iz=None):
+        """2-D cut through the current state (sim_fdtd.py:640-658), for plots between batches of steps; on the
+        checkerboard FCC grid the unused nodes are filled with the mean of their four in-plane neighbours.  One slab only."""
+        if self.world > 1:
+            raise NotImplementedError("gather_slice reads one engine's grid; run on one GPU for plots")
+        u1 = self.eng.read_grid(1)
+        if ix is not None:
+            uslice, i3 = u1[ix, :, :], ix
+        elif iy is not None:
+            uslice, i3 = u1[:, iy, :], iy
+        elif iz is not None:
+            uslice, i3 = u1[:, :, iz], iz
+        else:
+            raise ValueError("give ix, iy or iz")
+        uslice = np.array(uslice)
+        if self.sd_full.fcc_flag == 1:
+            fcc_fill_plot_holes(uslice, i3)
+        return uslice
+
     def save_outputs(self):
         if self.rank == 0:
             self.sd_full.write_outputs(self.data_dir, self.u_out)
@@ -138,6 +157,18 @@ class SimEngine:
         if self.eng is not None:
             self.eng.close()
             self.eng = None
+
+
+def fcc_fill_plot_holes(uslice, i3):
+    """nb_fcc_fill_plot_holes (sim_fdtd.py:888-894), in place: interior nodes of odd parity (i1 + i2 + i3) become the mean of their
+    four neighbours in the slice"""
+    N1, N2 = uslice.shape
+    i1, i2 = np.meshgrid(np.arange(1, N1 - 1), np.arange(1, N2 - 1), indexing="ij")
+    odd = ((i1 + i2 + i3) % 2) == 1
+    a, b = i1[odd], i2[odd]
+    # the four neighbours of an odd node are even nodes, which the fill never touches: order does not matter
+    uslice[a, b] = 0.25 * (uslice[a + 1, b] + uslice[a - 1, b] + uslice[a, b + 1] + uslice[a, b - 1])
+    return uslice
 
 
 def energy_balance(H_tot, E_lost, E_in):
@@ -174,7 +205,14 @@ def main(argv=None):
     parser.add_argument("--precision", type=int, default=2, choices=(1, 2), help="1 single (fdtd_main_gpu_single.x), 2 double")
     parser.add_argument("--energy", action="store_true", help="do energy calc (the reference's balance, evaluated on the device)")
     parser.add_argument("--device", type=int, default=None)
+    # accepted so that the reference's command lines keep working (sim_fdtd.py:899-906); plotting is not part of the simulation step
+    parser.add_argument("--plot", action="store_true", help="not available: use SimEngine.gather_slice between run_steps batches")
+    parser.add_argument("--draw_backend", type=str, default="matplotlib", help="ignored")
+    parser.add_argument("--json_model", type=str, default=None, help="ignored")
+    parser.add_argument("--abc", action="store_true", help="ignored (the absorbing shell is always applied, as in the reference)")
     args = parser.parse_args(argv)
+    if args.plot:
+        parser.error("--plot: live plots are outside the simulation step; SimEngine.gather_slice(ix|iy|iz) returns the cuts")
     if args.data_dir is None:
         args.data_dir = os.getcwd()  # the C binaries run in the data folder (fdtd_main.c:35)
     eng = SimEngine(args.data_dir, energy_on=args.energy, nthreads=args.nthreads, precision=args.precision, device=args.device)

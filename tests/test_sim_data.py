@@ -106,3 +106,21 @@ def test_inconsistent_inputs_are_rejected():
     m = dict(files["comms_out"], diff=np.int8(0))
     with pytest.raises(ValueError):
         shoebox.sim_data_from_files(dict(files, comms_out=m), 1)  # fp32 needs a differentiated source
+
+
+@pytest.mark.skipif(not __import__("refshim").available(), reason="/root/reference absent")
+def test_fcc_plot_hole_fill_equals_the_reference():
+    """gather_slice's checkerboard fill against the reference's nb_fcc_fill_plot_holes (sim_fdtd.py:888-894)"""
+    pytest.importorskip("numba")
+    import refshim
+    refshim.install()
+    from fdtd.sim_fdtd import nb_fcc_fill_plot_holes
+    from pffdtd_b200.sim_fdtd import fcc_fill_plot_holes
+    rng = np.random.default_rng(5)
+    for i3 in (4, 7):
+        a = rng.standard_normal((13, 18))
+        i1, i2 = np.meshgrid(np.arange(13), np.arange(18), indexing="ij")
+        a[((i1 + i2 + i3) % 2) == 1] = 0.0   # the unused nodes of a checkerboard slice hold zeros
+        want = a.copy()
+        nb_fcc_fill_plot_holes(want, i3)
+        assert np.array_equal(fcc_fill_plot_holes(a.copy(), i3), want)
