@@ -89,3 +89,15 @@ def test_reads_the_genuine_hdf5_files_shipped_with_the_reference(tmp_path):
         # our writer reproduces a file our reader (and theirs: same superblock/heap/B-tree/object-header layout) parses back
         h5lite.write_all(tmp_path / p.name, d)
         assert np.array_equal(h5lite.read_all(tmp_path / p.name)["DEF"], d["DEF"])
+
+
+def test_reads_a_genuine_libhdf5_file_with_a_user_block():
+    """scipy ships one real HDF5 file (a MATLAB v7.3 .mat written by libhdf5, with a 512-byte user block in front of the
+    superblock and a (9,1) float64 dataset): the only genuine file besides the reference's materials that travels with the image"""
+    import scipy.io
+    p = Path(scipy.io.__file__).parent / "matlab" / "tests" / "data" / "testhdf5_7.4_GLNX86.mat"
+    if not p.exists():
+        pytest.skip("scipy test data not installed")
+    d = h5lite.read_all(p)
+    assert list(d) == ["testdouble"]
+    assert d["testdouble"].shape == (9, 1) and np.allclose(d["testdouble"].ravel(), np.arange(9) * np.pi / 4, rtol=0, atol=1e-15)
