@@ -30,7 +30,7 @@ from .sim_data import SimData
 
 
 class SimEngine:
-    def __init__(self, data_dir, energy_on=False, nthreads=None, precision=2, device=None, scale=True, quiet=False):
+    def __init__(self, data_dir, energy_on=False, nthreads=None, precision=2, device=None, scale=True, quiet=False, timing=False):
         self.data_dir = Path(data_dir)
         self.energy_on = bool(energy_on)
         self.H_tot = self.E_lost = self.E_in = None
@@ -44,6 +44,8 @@ class SimEngine:
         self.sd = None
         self.u_out = None
         self.t_elapsed = 0.0
+        self.timing = bool(timing)  # CUDA events around every air launch -> the reference's air / boundary split lines
+        self.t_air = None
         del nthreads  # host threads play no role here; accepted for call compatibility
 
     def print(self, fstring):
@@ -100,12 +102,30 @@ class SimEngine:
         t0 = time.perf_counter()
         # batches only bound how far the host runs ahead of the device; there is no per-step sync
         batch = max(int(nsteps), 64)
+        if self.timing:
+            self.eng.set_option("profile_air", 1)
+            self.eng.reset_stats()
         for n in range(0, self.Nt, batch):
             self.run_steps(n, min(batch, self.Nt - n))
         self.eng.sync()
         self.t_elapsed = time.perf_counter() - t0
         self.print(f"Run-time loop: {self.t_elapsed:.6f}, {self.Nt * Npts / 1e6 / max(self.t_elapsed, 1e-12):.2f} MVox/s")
+        if self.timing:
+            self.t_air = self.eng.stat("air_ms") * 1e-3
+            self.eng.set_option("profile_air", 0)
         self._collect()
+        self.print_timing()
+
+    def print_timing(self):
+        """the three closing lines of the reference's C engines (cpu_engine.h:355-357, gpu_engine.h:1251-1253); "Combined
+        (total)" is the published MVPS metric (benchmarks/README.md:9).  The air / boundary split needs `timing=True`
+        (CUDA events around every air launch of this rank; everything that is not the air kernel counts as boundary loop)."""
+        Npts, Nt, t = self.Nx * self.Ny * self.Nz, self.Nt, max(self.t_elapsed, 1e-12)
+        if self.t_air is not None:
+            t_air, t_bn = max(self.t_air, 1e-12), max(t - self.t_air, 1e-12)
+            self.print(f"Air update: {t_air:.6f}s, {Npts * Nt / 1e6 / t_air:.2f} Mvox/s")
+            self.print(f"Boundary loop: {t_bn:.6f}s, {self.sd_full.Nb * Nt / 1e6 / t_bn:.2f} Mvox/s")
+        self.print(f"Combined (total): {t:.6f}s, {Npts * Nt / 1e6 / t:.2f} Mvox/s")
 
     def _collect(self):
         u = parallel.gather_rows(self.eng.read_outputs(0, self.Nt))  # rank order == sorted receiver order
@@ -205,6 +225,7 @@ def main(argv=None):
     parser.add_argument("--precision", type=int, default=2, choices=(1, 2), help="1 single (fdtd_main_gpu_single.x), 2 double")
     parser.add_argument("--energy", action="store_true", help="do energy calc (the reference's balance, evaluated on the device)")
     parser.add_argument("--device", type=int, default=None)
+    parser.add_argument("--timing", action="store_true", help="also print the reference's 'Air update' / 'Boundary loop' lines (CUDA events around every air launch)")
     # accepted so that the reference's command lines keep working (sim_fdtd.py:899-906); plotting is not part of the simulation step
     parser.add_argument("--plot", action="store_true", help="not available: use SimEngine.gather_slice between run_steps batches")
     parser.add_argument("--draw_backend", type=str, default="matplotlib", help="ignored")
@@ -215,7 +236,7 @@ def main(argv=None):
         parser.error("--plot: live plots are outside the simulation step; SimEngine.gather_slice(ix|iy|iz) returns the cuts")
     if args.data_dir is None:
         args.data_dir = os.getcwd()  # the C binaries run in the data folder (fdtd_main.c:35)
-    eng = SimEngine(args.data_dir, energy_on=args.energy, nthreads=args.nthreads, precision=args.precision, device=args.device)
+    eng = SimEngine(args.data_dir, energy_on=args.energy, nthreads=args.nthreads, precision=args.precision, device=args.device, timing=args.timing)
     eng.load_h5_data()
     eng.setup_mask()
     eng.allocate_mem()
