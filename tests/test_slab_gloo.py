@@ -63,3 +63,63 @@ def test_slabs_over_gloo_equal_the_single_domain(tmp_path, name, precision, worl
     logs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(logs)
     assert np.array_equal(np.load(out), gold)
+
+
+HOST_WORKER = r'''
+import sys, numpy as np
+sys.path.insert(0, "{root}"); sys.path.insert(0, "{root}/tests")
+from oracle import Oracle
+from pffdtd_b200 import parallel, sim_fdtd
+
+class SlabOracleEngine:
+    """what SimEngine asks of the CUDA engine, served by the CPU oracle; the halo planes travel over gloo"""
+    def __init__(self, sd, device=0):
+        self.sd, self.o = sd, Oracle(sd)
+    def comm_init(self, uid, rank, world):
+        assert uid == b"u" * 128
+        self.rank, self.world = rank, world
+    def set_option(self, k, v): pass
+    def run_steps(self, n0, k):
+        for n in range(n0, n0 + k):
+            self.o.run_steps(n, 1)
+            lo, hi = parallel.exchange_planes(self.o.read_plane(1), self.o.read_plane(self.sd.Nx - 2), self.rank, self.world)
+            if lo is not None: self.o.write_plane(0, lo)
+            if hi is not None: self.o.write_plane(self.sd.Nx - 1, hi)
+    def sync(self): pass
+    def read_outputs(self, n0=0, n1=None): return self.o.u_out[:, n0:n1].copy()
+    def close(self): pass
+
+sim_fdtd.Engine = SlabOracleEngine
+sim_fdtd.comm_unique_id = lambda: b"u" * 128
+parallel.init("gloo")
+u = sim_fdtd.run_folder(sys.argv[1], precision=int(sys.argv[2]), nsteps=9)
+if parallel.dist_env()[0] == 0:
+    np.save(sys.argv[3], u)
+'''
+
+
+@pytest.mark.parametrize("name,precision,world", (("cart_lossy_mb11", 1, 2), ("fcc2_lossy", 2, 3)))
+def test_host_loop_under_torchrun_env_with_slabs(tmp_path, name, precision, world):
+    """SimEngine with WORLD_SIZE > 1: every rank loads the folder, sorts, takes its slab, shares the communicator id, runs, and rank 0
+    gathers the receiver rows and writes sim_outs.h5 -- equal to the single-domain reference run"""
+    import sys as _sys
+    _sys.path.insert(0, str(ROOT / "tests"))
+    from cases import make_files
+    from pffdtd_b200 import h5lite, shoebox
+    gold = np.load(ROOT / "tests" / "golden" / "traces_ref_cpu_engine.npz")[f"{name}_p{precision}"]
+    data = tmp_path / "data"
+    shoebox.write_folder(make_files(name), data)
+    script = tmp_path / "worker.py"
+    script.write_text(HOST_WORKER.format(root=ROOT))
+    out = tmp_path / "u.npy"
+    port = _free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, str(script), str(data), str(precision), str(out)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    logs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    assert np.array_equal(np.load(out), gold)
+    assert np.array_equal(h5lite.File(data / "sim_outs.h5")["u_out"][...], gold)
