@@ -64,6 +64,30 @@ def _boundary_nodes(N, lo, hi, offs, fcc):
     return lin, ~cut, ins, c
 
 
+def _boundary_nodes_dense(N, lo, hi, offs, fcc, obstacles):
+    """like _boundary_nodes, for a room with solid blocks inside (small grids: dense occupancy array).  `obstacles` = inclusive
+    index boxes (x0, x1, y0, y1, z0, z1) of solid nodes.  A link is cut where it joins an air node and a solid / outside node;
+    both ends of a cut link are boundary nodes (as the voxeliser lists them, vox_scene.py:230-232)."""
+    Nx, Ny, Nz = N
+    air = np.zeros(N, bool)
+    air[lo[0]:hi[0] + 1, lo[1]:hi[1] + 1, lo[2]:hi[2] + 1] = True
+    for (x0, x1, y0, y1, z0, z1) in obstacles:
+        air[x0:x1 + 1, y0:y1 + 1, z0:z1 + 1] = False
+    g = np.meshgrid(np.arange(1, Nx - 1), np.arange(1, Ny - 1), np.arange(1, Nz - 1), indexing="ij")
+    c = np.stack([x.ravel() for x in g], axis=1).astype(np.int64)
+    if fcc:
+        c = c[(c.sum(axis=1) & 1) == 0]
+    ins = air[c[:, 0], c[:, 1], c[:, 2]]
+    cut = np.zeros((c.shape[0], offs.shape[0]), bool)
+    for j, o in enumerate(offs):
+        q = c + o
+        cut[:, j] = air[q[:, 0], q[:, 1], q[:, 2]] != ins
+    keep = cut.any(axis=1)
+    c, cut, ins = c[keep], cut[keep], ins[keep]
+    lin = (c[:, 0] * Ny + c[:, 1]) * Nz + c[:, 2]
+    return lin, ~cut, ins, c
+
+
 def _cart_boundary_fast(N, lo, hi, x_range=None):
     """same result as _boundary_nodes for the Cartesian scheme, built face by face (large grids);
     `x_range=(x0,x1)` keeps only the nodes of planes x0 <= ix < x1 (one rank's slab of a huge grid)"""
@@ -98,7 +122,7 @@ def _cart_boundary_fast(N, lo, hi, x_range=None):
 
 
 def make_shoebox(Nx, Ny, Nz, Nt, *, fcc=False, wall_offset=3, nmat=1, mb=11, rigid=False, diff=True,
-                 h=0.05, c=343.0, nrec=3, sig="impulse", fast=None, x_range=None):
+                 h=0.05, c=343.0, nrec=3, sig="impulse", fast=None, x_range=None, obstacles=None):
     """-> dict of the four files' datasets: {'sim_consts': {...}, 'vox_out': {...}, 'comms_out': {...}, 'sim_mats': {...}}"""
     N = (int(Nx), int(Ny), int(Nz))
     w = int(wall_offset)
@@ -116,7 +140,11 @@ def make_shoebox(Nx, Ny, Nz, Nt, *, fcc=False, wall_offset=3, nmat=1, mb=11, rig
         fast = not fcc
     if x_range is not None and (fcc or not fast):
         raise ValueError("x_range needs the fast Cartesian builder")
-    if fast and not fcc:
+    if obstacles:
+        if x_range is not None:
+            raise ValueError("obstacles need the dense builder (no x_range)")
+        bn, adj, ins, _ = _boundary_nodes_dense(N, lo, hi, offs, fcc, obstacles)
+    elif fast and not fcc:
         bn, adj, ins = _cart_boundary_fast(N, lo, hi, x_range)
     else:
         bn, adj, ins, _ = _boundary_nodes(N, lo, hi, offs, fcc)

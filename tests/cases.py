@@ -36,8 +36,18 @@ CASES = {
 }
 
 
+# rooms with solid blocks inside (a pillar, a one-node-thick plate, single isolated voxels (K = 0), an L-shaped block):
+# boundary nodes away from the walls, every adjacency pattern a staircase produces
+_BLOBS = [(6, 7, 14, 18, 6, 9), (20, 20, 6, 12, 8, 14), (10, 10, 16, 16, 18, 18), (22, 22, 8, 8, 20, 20), (12, 15, 5, 7, 18, 22), (12, 13, 8, 10, 18, 22)]
+OBSTACLE_CASES = {
+    "cart_blobs": (dict(Nx=30, Ny=24, Nz=28, Nt=70, nmat=3, mb=4, obstacles=_BLOBS), "cart"),
+    "fcc1_blobs": (dict(Nx=30, Ny=24, Nz=28, Nt=60, fcc=True, nmat=2, mb=3, obstacles=_BLOBS), "fcc1"),
+    "fcc2_blobs": (dict(Nx=30, Ny=24, Nz=28, Nt=60, fcc=True, nmat=2, mb=3, obstacles=_BLOBS), "fcc2"),
+}
+
+
 def make_files(name):
-    kw, layout = CASES[name]
+    kw, layout = CASES[name] if name in CASES else OBSTACLE_CASES[name]
     kw = dict(kw)
     empty = kw.pop("_empty", False)
     files = shoebox.make_shoebox(kw.pop("Nx"), kw.pop("Ny"), kw.pop("Nz"), kw.pop("Nt"), **kw)

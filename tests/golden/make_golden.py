@@ -15,7 +15,7 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE.parent))
 sys.path.insert(0, str(HERE.parent.parent))
-from cases import CASES, make_files  # noqa: E402
+from cases import CASES, OBSTACLE_CASES, make_files  # noqa: E402
 from oracle import Reference  # noqa: E402
 from pffdtd_b200 import shoebox  # noqa: E402
 
@@ -24,7 +24,7 @@ def main():
     out = {}
     devnull = os.open(os.devnull, os.O_WRONLY)
     saved = os.dup(1)
-    for name in sorted(CASES):
+    for name in sorted(CASES) + sorted(OBSTACLE_CASES):
         files = make_files(name)
         for prec in (1, 2):
             d = tempfile.mkdtemp(prefix="golden_")

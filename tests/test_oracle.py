@@ -10,7 +10,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from cases import CASES, make_files, make_sim_data
+from cases import CASES, OBSTACLE_CASES, make_files, make_sim_data
 from oracle import Oracle, Reference
 from pffdtd_b200 import shoebox
 from pffdtd_b200.sim_data import SimData
@@ -25,7 +25,7 @@ def _oracle_file_order(name, precision):
 
 
 @pytest.mark.parametrize("precision", (1, 2))
-@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("name", sorted(CASES) + sorted(OBSTACLE_CASES))
 def test_oracle_matches_golden_reference_traces(name, precision):
     got = _oracle_file_order(name, precision)
     ref = GOLD[f"{name}_p{precision}"]
