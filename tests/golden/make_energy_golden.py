@@ -21,7 +21,7 @@ import refshim  # noqa: E402
 from cases import make_files  # noqa: E402
 from pffdtd_b200 import shoebox  # noqa: E402
 
-ENERGY_CASES = ("cart_lossy", "cart_lossy_mb11", "cart_hann", "fcc1_lossy")  # walls clear of the absorbing shell, as the reference assumes (sim_fdtd.py:152)
+ENERGY_CASES = ("cart_lossy", "cart_lossy_mb11", "cart_hann", "fcc1_lossy", "cart_blobs", "fcc1_blobs")  # walls clear of the absorbing shell, as the reference assumes (sim_fdtd.py:152)
 ENERGY_FOLDERS = ("ctk_h030_cpu",)
 
 

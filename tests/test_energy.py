@@ -21,6 +21,7 @@ from pffdtd_b200.sim_fdtd import energy_balance
 GOLD_DIR = Path(__file__).parent / "golden"
 GOLD = np.load(GOLD_DIR / "energy_ref_python_engine.npz")
 CASES = ("cart_lossy", "cart_lossy_mb11", "cart_hann", "fcc1_lossy", "ctk_h030_cpu")
+CPU_CASES = CASES + ("cart_blobs", "fcc1_blobs")  # rooms with solid blocks inside: pinned on the CPU this round, on the GPU next
 TOL = 1e-11
 
 
@@ -37,13 +38,13 @@ def _close(a, b, tol=TOL):
     return np.abs(a - b).max() <= tol * np.abs(b).max()
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CPU_CASES)
 def test_reference_balance_holds_in_the_golden_vectors(name):
     b = energy_balance(GOLD[f"{name}/H_tot"], GOLD[f"{name}/E_lost"], GOLD[f"{name}/E_in"])
     assert np.abs(b[2:]).max() < 1e-13
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CPU_CASES)
 def test_restatement_reproduces_the_reference_python_engine(name):
     from oracle.energy import energy_trace
     H, lost, ein, u = energy_trace(_sd(name))
