@@ -704,7 +704,7 @@ struct Step {
          fa.x_lo = e->x_lo_edge, fa.x_hi = e->x_hi_edge;
          fa.lQ1 = (Real)((Real)e->l * (Real)1), fa.lQ2 = (Real)((Real)e->l * (Real)2), fa.lQ3 = (Real)((Real)e->l * (Real)3);
          const i64 nt = (xe - xb) * e->Ny * 2 + (xe - xb) * 2 * e->Nz + 2 * e->Ny * e->Nz;
-         if (e->abc_overlap && e->abc_disjoint) {
+         if (e->abc_overlap && e->abc_disjoint && !e->comm) {  // one GPU only: with slabs the edge parts order their work around the exchange
             // no boundary or source node lies on the shell: the shell update commutes with the boundary kernels
             CU(cudaEventRecord(e->ev_abc0, s));
             CU(cudaStreamWaitEvent(e->s_abc, e->ev_abc0, 0));

@@ -74,3 +74,37 @@ def test_unsorted_and_sorted_lists_give_the_same_file():
     ref = GOLD["cart_lossy_p2"]
     assert np.array_equal(u2, ref) and np.array_equal(u3, ref)
     del lossy_of
+
+
+def _random_room(seed, fcc):
+    """a shoebox with 2..6 random solid blocks (seeded), re-drawn until no source / receiver node touches a boundary node"""
+    rng = np.random.default_rng(seed)
+    N = (int(rng.integers(20, 34)) & ~1, int(rng.integers(18, 30)) & ~1, int(rng.integers(16, 40)) & ~1)
+    for _ in range(50):
+        blocks = []
+        for _ in range(int(rng.integers(2, 7))):
+            lo = [int(rng.integers(5, n - 8)) for n in N]
+            sz = [int(rng.integers(1, 5)) for _ in N]
+            blocks.append((lo[0], lo[0] + sz[0] - 1, lo[1], lo[1] + sz[1] - 1, lo[2], lo[2] + sz[2] - 1))
+        try:
+            return shoebox.make_shoebox(*N, 36, fcc=fcc, nmat=int(rng.integers(1, 4)), mb=int(rng.integers(1, 7)), obstacles=blocks,
+                                        wall_offset=int(rng.integers(1, 4)))
+        except AssertionError:
+            continue
+    raise RuntimeError("no admissible room drawn")
+
+
+@pytest.mark.skipif(not Reference.available(), reason="oracle/_ref not built and /root/reference absent")
+@pytest.mark.parametrize("seed", range(4))
+def test_oracle_matches_reference_engine_on_random_rooms(seed, capfd):
+    """seeded random geometry (blocks of 1..4 nodes per axis inside the room, random wall offset, 1-3 materials, 1-6 branches),
+    Cartesian for even seeds, checkerboard FCC for odd ones, both precisions: restatement == unmodified reference engine, bit for bit"""
+    files = _random_room(seed, fcc=bool(seed & 1))
+    d = tempfile.mkdtemp(prefix="ref_")
+    shoebox.write_folder(files, d)
+    for precision in (1, 2):
+        ref, _ = Reference(precision, files, d).run()
+        capfd.readouterr()
+        sd = shoebox.sim_data_from_files(files, precision).scale_input()
+        got = sd.reorder_output(sd.rescale_output(Oracle(sd).run_all()))
+        assert np.abs(ref).max() > 0 and np.array_equal(got, ref), f"seed {seed} p{precision}: {np.abs(got - ref).max():.3e}"
