@@ -30,7 +30,8 @@ from .sim_data import SimData
 
 
 class SimEngine:
-    def __init__(self, data_dir, energy_on=False, nthreads=None, precision=2, device=None, scale=True, quiet=False, timing=False):
+    def __init__(self, data_dir, energy_on=False, nthreads=None, precision=2, device=None, scale=True, quiet=False, timing=False,
+                 gpu_folder=False):
         self.data_dir = Path(data_dir)
         self.energy_on = bool(energy_on)
         self.H_tot = self.E_lost = self.E_in = None
@@ -44,6 +45,7 @@ class SimEngine:
         self.sd = None
         self.u_out = None
         self.t_elapsed = 0.0
+        self.gpu_folder = bool(gpu_folder)  # apply sim_setup's save_folder_gpu transforms (rotate, fold FCC, sort) in memory
         self.timing = bool(timing)  # CUDA events around every air launch -> the reference's air / boundary split lines
         self.t_air = None
         del nthreads  # host threads play no role here; accepted for call compatibility
@@ -55,7 +57,18 @@ class SimEngine:
     # ---- the reference's set-up sequence -------------------------------------------------------
     def load_h5_data(self):
         self.print("loading data..")
-        sd = SimData.load(self.data_dir, self.precision)
+        if self.gpu_folder:
+            # what sim_setup.py:119-125 + rotate_sim_data.py do to the files on disk, done to the datasets in memory: results equal
+            # the reference's run on the gpu folder (not bit for bit the run on the un-rotated folder: the sums change order)
+            from . import folder_prep, shoebox
+            for fn in ("sim_consts.h5", "vox_out.h5", "comms_out.h5", "sim_mats.h5"):
+                if not (self.data_dir / fn).exists():
+                    raise FileNotFoundError(f"{fn} doesn't exist in {self.data_dir}")
+            if self.energy_on:
+                raise ValueError("the energy balance runs on the folder as given (no --gpu_folder)")
+            sd = shoebox.sim_data_from_files(folder_prep.gpu_folder(folder_prep.load_folder(self.data_dir)), self.precision)
+        else:
+            sd = SimData.load(self.data_dir, self.precision)
         if self.scale:
             sd.scale_input()  # fdtd_data.h:879-909
         if self.energy_on and sd.fcc_flag == 2:
@@ -201,9 +214,9 @@ def energy_balance(H_tot, E_lost, E_in):
     return out
 
 
-def run_folder(data_dir, precision=2, device=None, nsteps=1, quiet=True):
+def run_folder(data_dir, precision=2, device=None, nsteps=1, quiet=True, gpu_folder=False):
     """load -> run -> write sim_outs.h5; returns u_out in file (original receiver) order"""
-    eng = SimEngine(data_dir, precision=precision, device=device, quiet=quiet)
+    eng = SimEngine(data_dir, precision=precision, device=device, quiet=quiet, gpu_folder=gpu_folder)
     eng.load_h5_data()
     eng.setup_mask()
     eng.allocate_mem()
@@ -225,6 +238,8 @@ def main(argv=None):
     parser.add_argument("--precision", type=int, default=2, choices=(1, 2), help="1 single (fdtd_main_gpu_single.x), 2 double")
     parser.add_argument("--energy", action="store_true", help="do energy calc (the reference's balance, evaluated on the device)")
     parser.add_argument("--device", type=int, default=None)
+    parser.add_argument("--gpu_folder", action="store_true", help="rotate / fold (FCC) / sort the folder's datasets in memory first, as sim_setup's "
+                        "save_folder_gpu does on disk: a plain folder then runs like its gpu folder (half the stored nodes for FCC)")
     parser.add_argument("--timing", action="store_true", help="also print the reference's 'Air update' / 'Boundary loop' lines (CUDA events around every air launch)")
     # accepted so that the reference's command lines keep working (sim_fdtd.py:899-906); plotting is not part of the simulation step
     parser.add_argument("--plot", action="store_true", help="not available: use SimEngine.gather_slice between run_steps batches")
@@ -236,7 +251,8 @@ def main(argv=None):
         parser.error("--plot: live plots are outside the simulation step; SimEngine.gather_slice(ix|iy|iz) returns the cuts")
     if args.data_dir is None:
         args.data_dir = os.getcwd()  # the C binaries run in the data folder (fdtd_main.c:35)
-    eng = SimEngine(args.data_dir, energy_on=args.energy, nthreads=args.nthreads, precision=args.precision, device=args.device, timing=args.timing)
+    eng = SimEngine(args.data_dir, energy_on=args.energy, nthreads=args.nthreads, precision=args.precision, device=args.device, timing=args.timing,
+                    gpu_folder=args.gpu_folder)
     eng.load_h5_data()
     eng.setup_mask()
     eng.allocate_mem()

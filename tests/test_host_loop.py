@@ -67,6 +67,22 @@ def test_folder_to_sim_outs_through_the_host_loop(tmp_path, stub, name, precisio
     assert np.array_equal(h5lite.File(tmp_path / "sim_outs.h5")["u_out"][...], gold)
 
 
+@pytest.mark.parametrize("precision", (1, 2))
+def test_plain_fcc_folder_run_as_its_gpu_folder(tmp_path, stub, precision):
+    """--gpu_folder: the checkerboard folder (fcc_flag 1) is rotated, folded and sorted in memory; the result is what the reference
+    computes from the gpu folder sim_setup would have written (golden fcc2_lossy), in the ORIGINAL receiver order"""
+    shoebox.write_folder(make_files("fcc1_lossy"), tmp_path)
+    u = sim_fdtd.run_folder(tmp_path, precision=precision, gpu_folder=True)
+    assert np.array_equal(u, GOLD[f"fcc2_lossy_p{precision}"])
+
+
+def test_plain_cartesian_room_run_as_its_gpu_folder(tmp_path, stub):
+    for f in (GOLD_DIR / "ctk_h030_cpu").glob("*.h5"):
+        shutil.copy(f, tmp_path / f.name)
+    u = sim_fdtd.run_folder(tmp_path, precision=1, gpu_folder=True)
+    assert np.array_equal(u, GOLD_MODELS["ctk_h030_gpu_p1"])
+
+
 def test_real_room_unsorted_folder_through_the_cli(tmp_path, stub, capsys):
     for f in (GOLD_DIR / "ctk_h030_cpu").glob("*.h5"):
         shutil.copy(f, tmp_path / f.name)
