@@ -40,3 +40,42 @@ def test_obstacle_rooms_bit_exact(name, precision):
                 assert np.array_equal(a, b), f"{name} p{precision} ak={ak} fuse={fuse} grid{which}: {np.abs(a - b).max():.3e}"
             v, g = e.read_boundary_state()
             assert np.array_equal(v, vo) and np.array_equal(g, go)
+
+
+def test_full_size_fp64_box_equals_the_reference_cpu_engine(tmp_path, capfd):
+    """BASELINE configs[3] at its full size: rigid shoebox 1024^3, 7-point Cartesian, fp64 -- receivers on a lattice of 100 nodes within 7 nodes
+    of the source, 12 steps, against the UNMODIFIED reference CPU engine on the box's cores (bit-exact).
+    Needs ~20 GB of device memory and ~20 GB of host memory; skipped on smaller machines."""
+    import os
+    import torch
+    from oracle import Reference
+    from pffdtd_b200 import shoebox
+    from pffdtd_b200.engine import Engine
+    if torch.cuda.get_device_properties(0).total_memory < 40e9:
+        pytest.skip("needs > 40 GB of device memory")
+    try:
+        with open("/proc/meminfo") as f:
+            avail_kb = int(next(l for l in f if l.startswith("MemAvailable")).split()[1])
+        if avail_kb < 48e6:
+            pytest.skip("needs > 48 GB of free host memory")
+    except (OSError, StopIteration):
+        pass
+    if not Reference.available(2):
+        pytest.skip("oracle/_ref not built")
+    N, Nt = 1024, 12
+    files = shoebox.make_shoebox(N, N, N, Nt, rigid=True, diff=False)
+    cm = files["comms_out"]
+    src = int(cm["in_ixyz"][0])
+    ring = sorted({src + dx * N * N + dy * N + dz for dx in (-5, -2, 0, 3, 7) for dy in (-4, 0, 2, 6) for dz in (-7, -3, 0, 2, 5)})
+    cm.update(out_ixyz=np.array(ring, np.int64), out_reorder=np.arange(len(ring), dtype=np.int64), Nr=np.int64(len(ring)),
+              out_alpha=np.full((1, len(ring)), 1.0 / len(ring)))
+    for fn in ("sim_consts.h5", "vox_out.h5", "comms_out.h5", "sim_mats.h5"):
+        (tmp_path / fn).touch()  # the reference loader stat()s the files; the datasets travel in memory
+    sd = shoebox.sim_data_from_files(files, 2).scale_input()
+    with Engine(sd) as e:
+        e.run_steps(0, Nt)
+        u = sd.reorder_output(sd.rescale_output(e.read_outputs()))
+    ref, _ = Reference(2, files, tmp_path, threads=os.cpu_count()).run()
+    capfd.readouterr()
+    assert np.count_nonzero(np.abs(ref).max(axis=1)) > 20  # the wave front has passed the nearer receivers
+    assert np.array_equal(u, ref), f"max|d| = {np.abs(u - ref).max():.3e} of peak {np.abs(ref).max():.3e}"
