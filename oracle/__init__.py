@@ -124,10 +124,13 @@ class Reference:
 
     @classmethod
     def lib(cls, precision, gpu=False):
-        """gpu=True: the reference's own CUDA engine (c_cuda/gpu_engine.h), a performance comparator (tests/diag/compare_reference_gpu_engine.py)"""
-        key = (precision, bool(gpu))
+        """gpu=True: the reference's own CUDA engine (c_cuda/gpu_engine.h), a performance comparator
+        (tests/diag/compare_reference_gpu_engine.py); gpu="b200": the reference's loader / scaling / output code around THIS repository's
+        engine (integration/b200_engine.h in the place of cpu_engine.h), the drop-in of INTEGRATION.md exercised by the GPU tests"""
+        key = (precision, gpu)
         if key not in cls._libs:
-            L = C.CDLL(_need(HERE / "_ref" / f"libpffdtd_ref{'gpu' if gpu else ''}_f{32 if precision == 1 else 64}.so"))
+            tag = "b200" if gpu == "b200" else ("gpu" if gpu else "")
+            L = C.CDLL(_need(HERE / "_ref" / f"libpffdtd_ref{tag}_f{32 if precision == 1 else 64}.so"))
             L.refdrv_put.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
             L.refdrv_load.argtypes = [C.c_char_p]
             L.refdrv_run_sim.restype = C.c_double

@@ -35,7 +35,9 @@
 #include <helper_funcs.h>
 #include <fdtd_common.h>
 #include <fdtd_data.h>
-#if USING_CUDA
+#if defined(USING_B200) && USING_B200
+#include <b200_engine.h> /* integration/b200_engine.h: the reference's main sequence with run_sim served by libpffdtd_b200.so (tests) */
+#elif USING_CUDA
 #include <gpu_engine.h> /* the reference's own CUDA engine, a PERFORMANCE COMPARATOR only (tests/diag/compare_reference_gpu_engine.py); built by nvcc -x cu */
 #else
 #include <cpu_engine.h>

@@ -84,3 +84,23 @@ def test_bad_descriptions_are_rejected_before_touching_the_device():
     d = sd.desc()
     d.precision = 3
     assert engine.lib().pffdtd_create(C.byref(d), 0, C.byref(h)) == engine.EINVAL
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU behaviour")
+def test_reference_side_binding_fails_loudly_without_a_gpu(tmp_path):
+    """integration/b200_engine.h inside the reference's main sequence (oracle/_ref/libpffdtd_refb200_*.so): without a CUDA device
+    run_sim must end the process with the engine's message -- the reference's error convention -- not compute anything on the CPU"""
+    import sys
+    lib = ROOT / "oracle" / "_ref" / "libpffdtd_refb200_f64.so"
+    if not lib.exists():
+        pytest.skip("oracle/_ref/libpffdtd_refb200_f64.so not built")
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from cases import make_files\n"
+        "from oracle import Reference\n"
+        "from pffdtd_b200 import shoebox\n"
+        "files = make_files('cart_rigid'); shoebox.write_folder(files, %r)\n"
+        "Reference(2, files, %r, gpu='b200').run()\n"
+        "print('COMPUTED WITHOUT A GPU')\n") % (str(ROOT), str(ROOT / "tests"), str(tmp_path), str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "b200 engine:" in r.stderr and "COMPUTED WITHOUT A GPU" not in r.stdout

@@ -79,3 +79,22 @@ def test_full_size_fp64_box_equals_the_reference_cpu_engine(tmp_path, capfd):
     capfd.readouterr()
     assert np.count_nonzero(np.abs(ref).max(axis=1)) > 20  # the wave front has passed the nearer receivers
     assert np.array_equal(u, ref), f"max|d| = {np.abs(u - ref).max():.3e} of peak {np.abs(ref).max():.3e}"
+
+
+@pytest.mark.parametrize("name,precision", (("cart_lossy_mb11", 1), ("cart_ragged", 2), ("fcc2_lossy", 1), ("cart_blobs", 2)))
+def test_reference_main_sequence_with_this_engine_as_run_sim(tmp_path, capfd, name, precision):
+    """INTEGRATION.md section 2 made real: the reference's own load_sim_data -> scale_input -> run_sim -> rescale_output ->
+    write_outputs (unmodified, oracle/ref_driver.c) with run_sim supplied by integration/b200_engine.h over the C ABI; the sim_outs
+    dataset it writes must equal the golden traces of the reference's CPU engine"""
+    from pathlib import Path
+    from cases import make_files
+    from oracle import Reference
+    from pffdtd_b200 import shoebox
+    if not (Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "libpffdtd_refb200_f32.so").exists():
+        pytest.skip("oracle/_ref/libpffdtd_refb200_*.so not built")
+    gold = np.load(Path(__file__).parent / "golden" / "traces_ref_cpu_engine.npz")[f"{name}_p{precision}"]
+    files = make_files(name)
+    shoebox.write_folder(files, tmp_path)
+    u, seconds = Reference(precision, files, tmp_path, gpu="b200").run()
+    capfd.readouterr()
+    assert seconds > 0 and np.array_equal(u, gold)
