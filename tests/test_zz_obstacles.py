@@ -82,19 +82,28 @@ def test_full_size_fp64_box_equals_the_reference_cpu_engine(tmp_path, capfd):
 
 
 @pytest.mark.parametrize("name,precision", (("cart_lossy_mb11", 1), ("cart_ragged", 2), ("fcc2_lossy", 1), ("cart_blobs", 2)))
-def test_reference_main_sequence_with_this_engine_as_run_sim(tmp_path, capfd, name, precision):
+def test_reference_main_sequence_with_this_engine_as_run_sim(tmp_path, name, precision):
     """INTEGRATION.md section 2 made real: the reference's own load_sim_data -> scale_input -> run_sim -> rescale_output ->
     write_outputs (unmodified, oracle/ref_driver.c) with run_sim supplied by integration/b200_engine.h over the C ABI; the sim_outs
-    dataset it writes must equal the golden traces of the reference's CPU engine"""
+    dataset it writes must equal the golden traces of the reference's CPU engine.  In a child process: the binding follows the
+    reference's error convention (message + exit), which must not take the test run with it."""
+    import subprocess
+    import sys
     from pathlib import Path
-    from cases import make_files
-    from oracle import Reference
-    from pffdtd_b200 import shoebox
-    if not (Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "libpffdtd_refb200_f32.so").exists():
+    root = Path(__file__).resolve().parent.parent
+    if not (root / "oracle" / "_ref" / "libpffdtd_refb200_f32.so").exists():
         pytest.skip("oracle/_ref/libpffdtd_refb200_*.so not built")
     gold = np.load(Path(__file__).parent / "golden" / "traces_ref_cpu_engine.npz")[f"{name}_p{precision}"]
-    files = make_files(name)
-    shoebox.write_folder(files, tmp_path)
-    u, seconds = Reference(precision, files, tmp_path, gpu="b200").run()
-    capfd.readouterr()
-    assert seconds > 0 and np.array_equal(u, gold)
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from cases import make_files\n"
+        "from oracle import Reference\n"
+        "from pffdtd_b200 import shoebox\n"
+        "files = make_files(%r); shoebox.write_folder(files, %r)\n"
+        "u, seconds = Reference(%d, files, %r, gpu='b200').run()\n"
+        "assert seconds > 0\n"
+        "np.save(%r, u)\n") % (str(root), str(root / "tests"), name, str(tmp_path), precision, str(tmp_path), str(tmp_path / "u.npy"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert np.array_equal(np.load(tmp_path / "u.npy"), gold)
