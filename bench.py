@@ -385,6 +385,15 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches), "host_prep_s": round(t_prep, 2)}
     if e2e:
         line["e2e"] = e2e
+    if N > 1:
+        # N = 1 of this script runs configs[1] (c2); the one-GPU number of THIS workload, for whoever computes a scaling efficiency,
+        # is the committed measurement of `bench.py --workload c5` (same grid on one B200)
+        try:
+            one = json.loads((ROOT / "profiles" / f"r01_bench_{wl}_1gpu.json").read_text())
+            line["same_workload_on_one_gpu"] = {"value": one["value"], "unit": one["unit"], "source": f"profiles/r01_bench_{wl}_1gpu.json",
+                                                "speedup": value / one["value"]}
+        except Exception:  # noqa: BLE001
+            pass
     eng.close()
 
     # ---- the reference's CPU engine on this box's cores (rank 0, N=1 only)
