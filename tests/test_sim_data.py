@@ -124,3 +124,36 @@ def test_fcc_plot_hole_fill_equals_the_reference():
         want = a.copy()
         nb_fcc_fill_plot_holes(want, i3)
         assert np.array_equal(fcc_fill_plot_holes(a.copy(), i3), want)
+
+
+def _run_slabs_in_process(full, nranks):
+    """the oracle on every slab of `full` in one process, halo planes copied by hand after every step"""
+    from oracle import Oracle
+    slabs = [full.slab(r, nranks) for r in range(nranks)]
+    orcs = [Oracle(s) for s in slabs]
+    for n in range(full.Nt):
+        for o in orcs:
+            o.run_steps(n, 1)
+        for r in range(nranks - 1):
+            lo, hi = orcs[r], orcs[r + 1]
+            up, down = lo.read_plane(slabs[r].Nx - 2), hi.read_plane(1)
+            hi.write_plane(0, up)
+            lo.write_plane(slabs[r].Nx - 1, down)
+    return np.concatenate([o.u_out[:, :full.Nt] for o in orcs], axis=0)
+
+
+@pytest.mark.parametrize("seed,nranks", ((3, 2), (4, 3), (5, 4), (6, 5)))
+def test_slab_split_of_random_rooms_changes_no_bit(seed, nranks):
+    """SimData.slab (gpu_engine.h:516-662 split_data): random rooms with solid blocks, Cartesian and folded FCC, 2..5 slabs, both
+    precisions -- receiver rows concatenated in rank order equal the single-domain run"""
+    from oracle import Oracle
+    from pffdtd_b200 import folder_prep
+    from test_oracle import _random_room
+    files = _random_room(seed, fcc=bool(seed & 1))
+    if seed & 1:
+        files = folder_prep.gpu_folder(files)
+    for precision in (1, 2):
+        full = shoebox.sim_data_from_files(files, precision).scale_input().sorted()
+        want = Oracle(full).run_all()
+        assert np.abs(want).max() > 0
+        assert np.array_equal(_run_slabs_in_process(full, nranks), want)
