@@ -153,6 +153,11 @@ int pffdtd_read_energy(pffdtd_engine *e, double *H_tot, double *E_lost, double *
  * `count` pseudo-random numerators per divisor and returns the number of differing results (must be 0). */
 int pffdtd_selftest(int device, double l, int precision, int64_t count, int64_t *mismatches);
 
+/* Diagnostic (no device needed): the x-chunk plan the tiled air kernel's work queue uses for a job of `n_planes` planes with
+ * chunk length `xc`: writes the nch+1 chunk bounds (bounds[0] = 0 ... bounds[nch] = n_planes) and returns nch, or a negative
+ * PFFDTD_E* code.  The plan is arithmetic (any number of planes) with a guided tail of halving chunk lengths. */
+int64_t pffdtd_air_chunk_plan(int64_t n_planes, int xc, int64_t *bounds, int64_t max_bounds);
+
 /* Whole-run convenience with the reference's run_sim() shape: create, run Nt steps, write
  * u_out[Nr*Nt], destroy; returns elapsed seconds of the loop through *elapsed_s. */
 int pffdtd_run_sim(const pffdtd_desc *desc, int device, double *u_out, double *elapsed_s);

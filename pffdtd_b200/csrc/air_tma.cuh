@@ -24,6 +24,7 @@
 // + 1 mask bit = 12.125 B fp32 / 24.125 B fp64.
 #pragma once
 #include <cstdint>
+#include <algorithm>
 #include <string>
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -130,14 +131,17 @@ struct AirCfg {
 // (chunk, tile): CTAs running at the same time work on neighbouring tiles of the same x-chunk, so tile halos
 // hit in L2.  Chunks get shorter towards the end of the job (guided self-scheduling), so that all CTAs finish
 // within a few planes of each other whatever the per-tile cost; every item costs two extra u1 plane loads.
-#define PF_AIR_MAXCH 96
+#define PF_AIR_MAXTAIL 24
 struct AirJob {
    int x_begin, n, tz, tiles;  // n planes, tiles = tz*ty
    int nch, n_items;           // chunks, items = nch*tiles
    int Ny, Nz, Nzp;
    i64 plane;                  // Ny*Nzp
    int *ctr;                   // {next item, CTAs done}; left at {0,0} by the last CTA
-   short bounds[PF_AIR_MAXCH + 1];  // chunk k covers planes [bounds[k], bounds[k+1]) of the job
+   // chunk k < n_main covers planes [k*xc, (k+1)*xc) of the job (the last one clipped to n); the guided tail that follows is
+   // chunk n_main + j = [tail[j], tail[j+1]).  Arithmetic bounds: the job may have any number of planes.
+   int xc, n_main;
+   int tail[PF_AIR_MAXTAIL + 1];
 };
 struct AirSeg {
    int xa, cnt, z0, y0;
@@ -146,11 +150,37 @@ template <int TZ, int TY>
 __device__ __forceinline__ AirSeg air_item(const AirJob &jb, int item) {
    const int k = item / jb.tiles, t = item - k * jb.tiles;
    AirSeg s;
-   s.xa = jb.x_begin + jb.bounds[k];
-   s.cnt = jb.bounds[k + 1] - jb.bounds[k];
+   int b0, b1;
+   if (k < jb.n_main) {
+      b0 = k * jb.xc;
+      b1 = min(b0 + jb.xc, jb.n);
+   } else {
+      b0 = jb.tail[k - jb.n_main];
+      b1 = jb.tail[k - jb.n_main + 1];
+   }
+   s.xa = jb.x_begin + b0;
+   s.cnt = b1 - b0;
    s.z0 = (t % jb.tz) * TZ;
    s.y0 = 1 + (t / jb.tz) * TY;
    return s;
+}
+
+// Chunk plan of a job of n planes: chunks of xc planes while more than a tail's worth of planes is left, then lengths that halve
+// down to 4, so that the items handed out last are small and all CTAs finish within a few planes of each other.
+static void air_plan_chunks(AirJob *jb, int n, int xc) {
+   xc = std::max(4, xc);
+   jb->n = n, jb->xc = xc;
+   const int tail_from = n - std::min(n / 4, 2 * xc);
+   jb->n_main = (tail_from + xc - 1) / xc;
+   int x = std::min(n, jb->n_main * xc), j = 0;
+   jb->tail[0] = x;
+   while (x < n) {
+      int len = std::max(4, std::min(xc, (n - x + 1) / 2));
+      if (j == PF_AIR_MAXTAIL - 1) len = n - x;
+      x = std::min(n, x + len);
+      jb->tail[++j] = x;
+   }
+   jb->nch = jb->n_main + j;
 }
 
 // Fused extras of the Cartesian step (all optional, `fuse` = 0 gives the plain masked air update):
@@ -817,22 +847,15 @@ static int air_tma_launch_cfg(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real
    jb.Ny = (int)t->Ny, jb.Nz = (int)t->Nz, jb.Nzp = (int)t->Nzp;
    jb.plane = t->Ny * t->Nzp;
    jb.ctr = t->ctr;
-   if (jb.n > 32767) return (int)cudaErrorInvalidValue;
-   // chunk lengths: chunks of xc planes (default 16) for most of the job, then halving down to 4, so that the
-   // items handed out last are small
+   // x-chunk length: 16 planes on grids that give a CTA few items (two extra u1 planes per item: 4 % more traffic), longer on
+   // large grids where 16-plane items would be handed out by the hundred (c5: 64 planes, 1 % extra)
    {
-      const int xc = std::max(4, t->xc > 0 ? t->xc : 16);
-      int k = 0, x = 0;
-      jb.bounds[0] = 0;
-      const int tail_from = jb.n - std::min(jb.n / 4, 2 * xc);
-      while (x < jb.n && k < PF_AIR_MAXCH - 1) {
-         int len = xc;
-         if (x >= tail_from) len = std::max(4, std::min(xc, (jb.n - x + 1) / 2));
-         if (k == PF_AIR_MAXCH - 2) len = jb.n - x;
-         x = std::min(jb.n, x + len);
-         jb.bounds[++k] = (short)x;
+      int xc = t->xc;
+      if (xc <= 0) {
+         const i64 per_cta = (i64)jb.n * jb.tiles / std::max(1, t->slots);
+         xc = (int)std::max<i64>(16, std::min<i64>(64, per_cta / 24 / 4 * 4));
       }
-      jb.nch = k;
+      air_plan_chunks(&jb, jb.n, xc);
    }
    const i64 items = (i64)jb.nch * jb.tiles;
    if (items > 0x7fffffff) return (int)cudaErrorInvalidValue;

@@ -240,9 +240,9 @@ static void edge_counts(const int64_t *a, i64 n, i64 limit, i64 from, i64 *lo, i
    *lo = std::lower_bound(a, a + n, limit) - a;
    *hi = (a + n) - std::lower_bound(a, a + n, from);
 }
-static bool ascending(const int64_t *a, i64 n) {
+static bool ascending(const int64_t *a, i64 n, bool strict = true) {
    for (i64 i = 1; i < n; i++)
-      if (a[i] <= a[i - 1]) return false;
+      if (strict ? a[i] <= a[i - 1] : a[i] < a[i - 1]) return false;
    return true;
 }
 
@@ -383,8 +383,10 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
       e->serial_src = std::adjacent_find(t.begin(), t.end()) != t.end();
    }
    // edge/interior split for the overlapped halo exchange needs ascending lists (gpu_engine.h:497-513)
+   // (duplicate source nodes are legal: non-decreasing is enough there, split_data only walks the list, and `serial_src`
+   // keeps their accumulation order)
    if (ascending(d->bn_ixyz, e->Nb) && ascending(d->bnl_ixyz, e->Nbl) && ascending(d->bna_ixyz, e->Nba) &&
-       ascending(d->in_ixyz, e->Ns)) {
+       ascending(d->in_ixyz, e->Ns, false)) {
       const i64 P = e->Ny * e->Nz;
       e->sorted = 1;
       edge_counts(d->bn_ixyz, e->Nb, 2 * P, (e->Nx - 2) * P, &e->nb_lo, &e->nb_hi);
@@ -450,6 +452,10 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
          if (iz == 2) oz[nz++] = 0;
          if (iz == e->Nz - 3) oz[nz++] = e->Nz - 1;
          const i64 src = (ix * e->Ny + iy) * e->Nzp + iz;
+         // a masked node at z = 1 / Nz-2 can make the whole 16-byte vector that holds the z halo masked (fp64: [halo, node]); the air
+         // kernel then never stores that vector and the halo misses its mirror-on-write: copy it from z = 2 / Nz-3 afterwards
+         if (iz == 1) pr.push_back({src + 1, src - 1});
+         if (iz == e->Nz - 2) pr.push_back({src - 1, src + 1});
          for (int a = 0; a < nx; a++)
             for (int b = 0; b < ny; b++)
                for (int c = 0; c < nz; c++)
@@ -861,14 +867,14 @@ template <typename Real>
 static void mirror_pass(pffdtd_engine *e, Real *u, cudaStream_t s) {
    const i64 Nx = e->Nx, Ny = e->Ny, Nz = e->Nz, Nzp = e->Nzp;
    if (e->fcc == 2) {
-      pf::k_fold_seam<Real><<<dim3(nblk(Nz, 128), (unsigned)Nx), 128, 0, s>>>(u, Nx, Ny, Nz, Nzp);
+      pf::k_fold_seam<Real><<<dim3(nblk(Nz, 128), (unsigned)std::min<i64>(Nx, 65535)), 128, 0, s>>>(u, Nx, Ny, Nz, Nzp);
       e->launches += 1;
    }
    pf::k_flip_z<Real><<<nblk(Nx * Ny, 128), 128, 0, s>>>(u, Nx * Ny, Nz, Nzp);
-   pf::k_flip_y<Real><<<dim3(nblk(Nz, 128), (unsigned)Nx), 128, 0, s>>>(u, Nx, Ny, Nz, Nzp, e->fcc != 2);
+   pf::k_flip_y<Real><<<dim3(nblk(Nz, 128), (unsigned)std::min<i64>(Nx, 65535)), 128, 0, s>>>(u, Nx, Ny, Nz, Nzp, e->fcc != 2);
    e->launches += 2;
    if (e->x_lo_edge || e->x_hi_edge) {
-      pf::k_flip_x<Real><<<dim3(nblk(Nz, 128), (unsigned)Ny), 128, 0, s>>>(u, Nx, Ny, Nz, Nzp, e->x_lo_edge, e->x_hi_edge);
+      pf::k_flip_x<Real><<<dim3(nblk(Nz, 128), (unsigned)std::min<i64>(Ny, 65535)), 128, 0, s>>>(u, Nx, Ny, Nz, Nzp, e->x_lo_edge, e->x_hi_edge);
       e->launches += 1;
    }
 }
@@ -966,8 +972,71 @@ static int step_any(pffdtd_engine *e, i64 n) { return e->precision == 1 ? step_i
 
 // can a step starting now be replayed from a captured graph?
 static bool graphable(const pffdtd_engine *e) {
-   return e->use_graph && !e->energy_on && !e->comm && !e->profile_air && !e->manual_halo && e->steps_plain >= 2 &&
+   return e->use_graph && !e->energy_on && !e->profile_air && !e->manual_halo && e->steps_plain >= 2 &&
           !(e->halo_dirty && e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge);
+}
+
+// Host-side bookkeeping a step changes; capturing a step must leave it as it was (nothing ran).
+struct HostState {
+   int cur, halo_dirty, comm_pending, abc_pending, host_mode;
+   i64 n_dev, steps_done;
+   double launches;
+};
+static HostState save_state(const pffdtd_engine *e) {
+   return HostState{e->cur, e->halo_dirty, e->comm_pending, e->abc_pending, e->host_mode, e->n_dev, e->steps_done, e->launches};
+}
+static void restore_state(pffdtd_engine *e, const HostState &h) {
+   e->cur = h.cur, e->halo_dirty = h.halo_dirty, e->comm_pending = h.comm_pending, e->abc_pending = h.abc_pending;
+   e->host_mode = h.host_mode, e->n_dev = h.n_dev, e->steps_done = h.steps_done, e->launches = h.launches;
+}
+
+// a halo exchange still in flight on the comm stream is joined for real (never from inside a capture)
+static int join_comm(pffdtd_engine *e) {
+   if (e->comm_pending) {
+      CU(cudaStreamWaitEvent(e->s_main, e->ev_comm, 0));
+      e->comm_pending = 0;
+   }
+   return 0;
+}
+
+// Capture `count` consecutive steps that start at time index n with grid role `c` (u[c] = current state) into an
+// executable graph; `host_io`: the sequence is one host-driven step with the H2D / D2H copies of its samples.
+// With slabs the NCCL send/recv of the halo planes and the second stream are part of the graph (the exchange is joined at
+// the end of the sequence).  Nothing runs and no host-side state changes, whatever the outcome.
+static int capture_steps(pffdtd_engine *e, int c, i64 n, int count, bool host_io, cudaGraphExec_t *out, double *launches) {
+   const HostState keep = save_state(e);
+   cudaGraph_t g = nullptr;
+   e->cur = c, e->n_dev = n, e->comm_pending = 0, e->abc_pending = 0;
+   cudaError_t ce = cudaStreamBeginCapture(e->s_main, cudaStreamCaptureModeThreadLocal);
+   if (ce != cudaSuccess) {
+      restore_state(e, keep);
+      return fail(PFFDTD_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
+   }
+   int rc = PFFDTD_OK;
+   cudaError_t cc = cudaSuccess;
+   if (host_io) {
+      e->host_mode = 3;
+      cc = cudaMemcpyAsync(e->in_stage, e->h_in, (size_t)e->Ns * e->rs, cudaMemcpyHostToDevice, e->s_main);
+   }
+   for (int k = 0; k < count && rc == PFFDTD_OK; k++) rc = step_any(e, n + k);
+   if (host_io && cc == cudaSuccess)
+      cc = cudaMemcpyAsync(e->h_out, e->out_stage, (size_t)e->Nr * e->rs, cudaMemcpyDeviceToHost, e->s_main);
+   if (e->comm_pending && cc == cudaSuccess) cc = cudaStreamWaitEvent(e->s_main, e->ev_comm, 0);  // re-join the comm stream
+   ce = cudaStreamEndCapture(e->s_main, &g);
+   *launches = e->launches - keep.launches;
+   restore_state(e, keep);
+   if (rc || cc != cudaSuccess || ce != cudaSuccess) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      return rc ? rc : fail(PFFDTD_ECUDA, "graph capture: %s", cudaGetErrorString(cc != cudaSuccess ? cc : ce));
+   }
+   ce = cudaGraphInstantiate(out, g, 0);
+   cudaGraphDestroy(g);
+   if (ce != cudaSuccess) {
+      *out = nullptr;
+      return fail(PFFDTD_ECUDA, "graph instantiate: %s", cudaGetErrorString(ce));
+   }
+   return PFFDTD_OK;
 }
 
 extern "C" int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps) {
@@ -980,32 +1049,21 @@ extern "C" int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps
    i64 n = nstart;
    const i64 nend = nstart + nsteps;
    while (n < nend) {
-      // two steps bring `cur` back: a captured pair replays as one CUDA graph (single GPU, fused or not,
-      // once the halos are clean and the first plain steps have sized the launches)
+      // two steps bring `cur` back: a captured pair replays as one CUDA graph (fused or not, one GPU or a slab with its
+      // halo exchange), once the halos are clean and the first plain steps have sized the launches and opened the
+      // NCCL connections.  Both grid roles are captured at the first use, so no later call pays for a capture.
       const bool graph_ok = nend - n >= 2 && graphable(e);
       if (graph_ok) {
          const int c = e->cur;
+         int rc = join_comm(e);
+         if (rc) return rc;
+         for (int k = 0; k < 2; k++) {
+            const int cc = c ^ k;
+            if (!e->graph[cc] && (rc = capture_steps(e, cc, n, 2, false, &e->graph[cc], &e->graph_launches[cc]))) return rc;
+         }
          if (e->n_dev != n) {
             pf::k_set_n<<<1, 1, 0, e->s_main>>>(e->d_n, n);
             e->n_dev = n;
-         }
-         if (!e->graph[c]) {
-            cudaGraph_t g = nullptr;
-            const double l0 = e->launches;
-            const i64 nd = e->n_dev, sd = e->steps_done;
-            CU(cudaStreamBeginCapture(e->s_main, cudaStreamCaptureModeThreadLocal));
-            int rc = step_any(e, n);
-            if (rc == PFFDTD_OK) rc = step_any(e, n + 1);
-            cudaError_t ce = cudaStreamEndCapture(e->s_main, &g);
-            e->graph_launches[c] = e->launches - l0;
-            e->launches = l0, e->n_dev = nd, e->steps_done = sd;  // nothing ran yet
-            if (rc || ce != cudaSuccess) {
-               if (g) cudaGraphDestroy(g);
-               return rc ? rc : fail(PFFDTD_ECUDA, "graph capture: %s", cudaGetErrorString(ce));
-            }
-            ce = cudaGraphInstantiate(&e->graph[c], g, 0);
-            cudaGraphDestroy(g);
-            if (ce != cudaSuccess) return fail(PFFDTD_ECUDA, "graph instantiate: %s", cudaGetErrorString(ce));
          }
          CU(cudaGraphLaunch(e->graph[c], e->s_main));
          e->launches += e->graph_launches[c];
@@ -1045,30 +1103,14 @@ extern "C" int pffdtd_step_host(pffdtd_engine *e, int64_t n, const double *in_sa
    if (has_in && has_out && graphable(e)) {
       // H2D of the source samples, the step, D2H of the receiver samples: one replayed graph per grid role
       const int c = e->cur;
+      if ((rc = join_comm(e))) return rc;
+      for (int k = 0; k < 2; k++) {
+         const int cc = c ^ k;
+         if (!e->hgraph[cc] && (rc = capture_steps(e, cc, n, 1, true, &e->hgraph[cc], &e->hgraph_launches[cc]))) return rc;
+      }
       if (e->n_dev != n) {
          pf::k_set_n<<<1, 1, 0, e->s_main>>>(e->d_n, n);
          e->n_dev = n;
-      }
-      if (!e->hgraph[c]) {
-         cudaGraph_t g = nullptr;
-         const double l0 = e->launches;
-         const i64 nd = e->n_dev, sd = e->steps_done;
-         CU(cudaStreamBeginCapture(e->s_main, cudaStreamCaptureModeThreadLocal));
-         e->host_mode = 3;
-         cudaError_t ce = cudaMemcpyAsync(e->in_stage, e->h_in, (size_t)e->Ns * e->rs, cudaMemcpyHostToDevice, e->s_main);
-         rc = step_any(e, n);
-         if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->h_out, e->out_stage, (size_t)e->Nr * e->rs, cudaMemcpyDeviceToHost, e->s_main);
-         e->host_mode = 0;
-         cudaError_t ce2 = cudaStreamEndCapture(e->s_main, &g);
-         e->hgraph_launches[c] = e->launches - l0;
-         e->launches = l0, e->n_dev = nd, e->steps_done = sd, e->cur = c;  // nothing ran yet
-         if (rc || ce != cudaSuccess || ce2 != cudaSuccess) {
-            if (g) cudaGraphDestroy(g);
-            return rc ? rc : fail(PFFDTD_ECUDA, "host-step graph capture: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ce2));
-         }
-         ce = cudaGraphInstantiate(&e->hgraph[c], g, 0);
-         cudaGraphDestroy(g);
-         if (ce != cudaSuccess) return fail(PFFDTD_ECUDA, "graph instantiate: %s", cudaGetErrorString(ce));
       }
       CU(cudaGraphLaunch(e->hgraph[c], e->s_main));
       e->launches += e->hgraph_launches[c];
@@ -1191,6 +1233,16 @@ extern "C" int pffdtd_selftest(int device, double l, int precision, int64_t coun
    cudaFree(bad);
    *mismatches = (int64_t)h;
    return PFFDTD_OK;
+}
+
+extern "C" int64_t pffdtd_air_chunk_plan(int64_t n_planes, int xc, int64_t *bounds, int64_t max_bounds) {
+   if (n_planes < 0 || n_planes > 0x7fffffff || !bounds) return fail(PFFDTD_EINVAL, "bad chunk plan arguments");
+   pf::AirJob jb;
+   pf::air_plan_chunks(&jb, (int)n_planes, xc);
+   if ((i64)jb.nch + 1 > max_bounds) return fail(PFFDTD_EINVAL, "chunk plan needs %d bounds", jb.nch + 1);
+   for (int k = 0; k <= jb.nch; k++)
+      bounds[k] = k < jb.n_main ? (i64)k * jb.xc : (i64)jb.tail[k - jb.n_main];
+   return jb.nch;
 }
 
 extern "C" int pffdtd_run_sim(const pffdtd_desc *desc, int device, double *u_out, double *elapsed_s) {

@@ -85,10 +85,11 @@ __global__ void k_gather(const Real *__restrict__ u, const i64 *__restrict__ idx
 template <typename Real>
 __global__ void k_fold_seam(Real *u1, i64 Nx, i64 Ny, i64 Nz, i64 Nzp) {
    const i64 iz = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-   const i64 ix = blockIdx.y;
    if (iz >= Nz) return;
-   Real *pl = u1 + ix * Ny * Nzp;
-   pl[(Ny - 1) * Nzp + iz] = pl[(Ny - 2) * Nzp + iz];
+   for (i64 ix = blockIdx.y; ix < Nx; ix += gridDim.y) {  // gridDim.y is capped at 65535
+      Real *pl = u1 + ix * Ny * Nzp;
+      pl[(Ny - 1) * Nzp + iz] = pl[(Ny - 2) * Nzp + iz];
+   }
 }
 
 template <typename Real>
@@ -103,21 +104,24 @@ __global__ void k_flip_z(Real *u1, i64 nrows, i64 Nz, i64 Nzp) {
 template <typename Real>
 __global__ void k_flip_y(Real *u1, i64 Nx, i64 Ny, i64 Nz, i64 Nzp, int do_yend) {
    const i64 iz = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-   const i64 ix = blockIdx.y;
    if (iz >= Nz) return;
-   Real *pl = u1 + ix * Ny * Nzp;
-   pl[iz] = pl[2 * Nzp + iz];
-   if (do_yend) pl[(Ny - 1) * Nzp + iz] = pl[(Ny - 3) * Nzp + iz];
+   for (i64 ix = blockIdx.y; ix < Nx; ix += gridDim.y) {
+      Real *pl = u1 + ix * Ny * Nzp;
+      pl[iz] = pl[2 * Nzp + iz];
+      if (do_yend) pl[(Ny - 1) * Nzp + iz] = pl[(Ny - 3) * Nzp + iz];
+   }
 }
 
 template <typename Real>
 __global__ void k_flip_x(Real *u1, i64 Nx, i64 Ny, i64 Nz, i64 Nzp, int lo, int hi) {
    const i64 iz = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-   const i64 iy = blockIdx.y;
    if (iz >= Nz) return;
-   const i64 P = Ny * Nzp, r = iy * Nzp + iz;
-   if (lo) u1[r] = u1[2 * P + r];
-   if (hi) u1[(Nx - 1) * P + r] = u1[(Nx - 3) * P + r];
+   const i64 P = Ny * Nzp;
+   for (i64 iy = blockIdx.y; iy < Ny; iy += gridDim.y) {
+      const i64 r = iy * Nzp + iz;
+      if (lo) u1[r] = u1[2 * P + r];
+      if (hi) u1[(Nx - 1) * P + r] = u1[(Nx - 3) * P + r];
+   }
 }
 
 // ------------------------------------------------------------------------------------------------

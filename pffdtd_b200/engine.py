@@ -76,6 +76,8 @@ def lib():
     L.pffdtd_run_sim.argtypes = [C.POINTER(pffdtd_desc), C.c_int, vp, dp]
     L.pffdtd_energy_enable.argtypes = [vp, C.POINTER(pffdtd_energy_desc)]
     L.pffdtd_read_energy.argtypes = [vp, vp, vp, vp]
+    L.pffdtd_air_chunk_plan.argtypes = [i64, C.c_int, C.POINTER(i64), i64]
+    L.pffdtd_air_chunk_plan.restype = i64
     _lib = L
     return L
 

@@ -121,6 +121,28 @@ def _cart_boundary_fast(N, lo, hi, x_range=None):
     return idx, adj, ins
 
 
+def plane_costs(Nx, Ny, Nz, wall_offset=3, rigid=False, mb=11):
+    """per x-plane cost of a Cartesian shoebox for SimData.slab_planes(cost=...), without building the node lists of the whole
+    grid: counts the boundary / lossy / shell nodes of the five kinds of planes (outside the room, the two wall planes of either side,
+    a plane across the room) with the same builder make_shoebox uses"""
+    from .sim_data import SimData
+    N, w = (int(Nx), int(Ny), int(Nz)), int(wall_offset)
+    lo, hi = [w + 1] * 3, [n - 2 - w for n in N]
+    P = float(Ny * Nz)
+
+    def counts(x):
+        _, _, ins = _cart_boundary_fast(N, lo, hi, (x, x + 1))
+        return float(ins.size), (0.0 if rigid else float(ins.sum()))
+    kinds = {x: counts(x) for x in {lo[0] - 1, lo[0], lo[0] + 1, hi[0], hi[0] + 1}}
+    cost = np.zeros(Nx)
+    lossy = SimData.COST_BNL_BASE + SimData.COST_BNL_BRANCH * mb
+    for x in range(1, Nx - 1):
+        nb, nbl = kinds[x] if x in kinds else (kinds[lo[0] + 1] if lo[0] < x < hi[0] else (0.0, 0.0))
+        nba = (Ny - 2) * (Nz - 2) if x in (1, Nx - 2) else 2 * (Ny - 2) + 2 * (Nz - 2) - 4
+        cost[x] = P + SimData.COST_BN * nb + lossy * nbl + SimData.COST_BNA * nba
+    return cost
+
+
 def make_shoebox(Nx, Ny, Nz, Nt, *, fcc=False, wall_offset=3, nmat=1, mb=11, rigid=False, diff=True,
                  h=0.05, c=343.0, nrec=3, sig="impulse", fast=None, x_range=None, obstacles=None):
     """-> dict of the four files' datasets: {'sim_consts': {...}, 'vox_out': {...}, 'comms_out': {...}, 'sim_mats': {...}}"""

@@ -2,7 +2,7 @@
 
 Restates, in numpy, the host prep of the reference C engines so the device receives exactly the
 numbers the reference would compute (validated field by field against the unmodified
-``load_sim_data`` in tests/test_sim_data_vs_ref.py):
+``load_sim_data`` in tests/test_sim_data.py):
 
 * ``SimData.load``           <- load_sim_data        c_cuda/fdtd_data.h:99-718
 * ``SimData.scale_input``    <- scale_input          c_cuda/fdtd_data.h:879-909
@@ -332,8 +332,9 @@ class SimData:
     # ---- ordering and partitioning
     def is_sorted(self):
         s = lambda a, strict: a.size < 2 or bool(np.all(np.diff(a) > 0) if strict else np.all(np.diff(a) >= 0))
+        # duplicates are legal among sources and receivers (split_data only walks the lists, gpu_engine.h:562-661)
         return (s(self.bn_ixyz, True) and s(self.bnl_ixyz, True) and s(self.bna_ixyz, True)
-                and s(self.in_ixyz, True) and s(self.out_ixyz, False))
+                and s(self.in_ixyz, False) and s(self.out_ixyz, False))
 
     def sorted(self) -> "SimData":
         """Ascending node lists, what sort_sim_data does to the files (rotate_sim_data.py:157-170);
@@ -353,24 +354,64 @@ class SimData:
                        out_ixyz=self.out_ixyz[ko], out_reorder=inv[self.out_reorder], _keep=[])
 
     @staticmethod
-    def slab_planes(Nx, nranks):
-        """owned planes per rank: Nx//n each, +1 for the first Nx%n ranks (gpu_engine.h:532-543)"""
-        base, rem = divmod(Nx, nranks)
-        sizes = [base + (1 if r < rem else 0) for r in range(nranks)]
+    def slab_planes(Nx, nranks, cost=None):
+        """owned planes per rank.  `cost=None`: the reference's split, Nx//n each, +1 for the first Nx%n ranks
+        (gpu_engine.h:532-543).  `cost` = per-plane cost [Nx] (see `plane_costs`): contiguous slabs of about equal total cost,
+        so that ranks holding walls perpendicular to x get fewer planes.  Every slab keeps at least 2 planes; the arithmetic of
+        a node does not depend on where the cuts are, so any split gives the same bits."""
+        if cost is None:
+            base, rem = divmod(Nx, nranks)
+            sizes = [base + (1 if r < rem else 0) for r in range(nranks)]
+        else:
+            cost = np.asarray(cost, np.float64)
+            if cost.shape != (Nx,) or np.any(cost < 0):
+                raise ValueError("cost must be a non-negative array of Nx entries")
+            if Nx < 2 * nranks:
+                raise ValueError("too many ranks for this grid")
+            cum = np.concatenate([[0.0], np.cumsum(cost)])
+            cuts = [0]
+            for r in range(1, nranks):
+                x = int(np.searchsorted(cum, cum[-1] * r / nranks, "left"))
+                # the nearer of the two planes around the target; leave >= 2 planes to this slab and to every later one
+                if x > 0 and abs(cum[x - 1] - cum[-1] * r / nranks) <= abs(cum[x] - cum[-1] * r / nranks):
+                    x -= 1
+                x = min(max(x, cuts[-1] + 2), Nx - 2 * (nranks - r))
+                cuts.append(x)
+            cuts.append(Nx)
+            sizes = [cuts[r + 1] - cuts[r] for r in range(nranks)]
         starts = [sum(sizes[:r]) for r in range(nranks)]
         return starts, sizes
 
-    def slab(self, rank: int, nranks: int) -> "SimData":
+    # cost of one node of each kind in units of one air node (12.125 B of HBM traffic, fp32), from the measured kernel
+    # times on B200 (profiles/): boundary node (rigid update + its share of the adjacency list), lossy node (11 branches of
+    # state read and written), absorbing-shell node
+    COST_BN, COST_BNL_BASE, COST_BNL_BRANCH, COST_BNA = 3.0, 4.0, 1.5, 2.0
+
+    def plane_costs(self):
+        """per x-plane cost [Nx] for `slab_planes(cost=...)`: air nodes + weighted node-list entries of the plane"""
+        P = self.Ny * self.Nz
+        cnt = lambda a: np.bincount(np.asarray(a, np.int64) // P, minlength=self.Nx).astype(np.float64)
+        mb = float(np.max(self.Mb)) if np.size(self.Mb) else 0.0
+        air = np.full(self.Nx, float(P))
+        if self.x_lo_edge:
+            air[0] = 0.0  # the global halo planes are never updated
+        if self.x_hi_edge:
+            air[-1] = 0.0
+        return (air + self.COST_BN * cnt(self.bn_ixyz) + (self.COST_BNL_BASE + self.COST_BNL_BRANCH * mb) * cnt(self.bnl_ixyz)
+                + self.COST_BNA * cnt(self.bna_ixyz))
+
+    def slab(self, rank: int, nranks: int, planes=None) -> "SimData":
         """The part of the problem rank `rank` of `nranks` owns, re-based to slab-local indices, with
         one halo plane towards each neighbour (gpu_engine.h:755-823).  Receiver rows of all ranks
-        concatenated in rank order give the internal (sorted) receiver order."""
+        concatenated in rank order give the internal (sorted) receiver order.  `planes` = (starts, sizes) of a
+        split other than the reference's equal one (`slab_planes(cost=...)`)."""
         if nranks == 1:
             return self
         if not self.is_sorted():
             raise ValueError("slab split needs sorted node lists; call .sorted() first")
-        if nranks > self.Nx - 2 or min(self.slab_planes(self.Nx, nranks)[1]) < 2:
+        starts, sizes = planes if planes is not None else self.slab_planes(self.Nx, nranks)
+        if nranks > self.Nx - 2 or min(sizes) < 2 or sum(sizes) != self.Nx or len(sizes) != nranks:
             raise ValueError("too many ranks for this grid")
-        starts, sizes = self.slab_planes(self.Nx, nranks)
         P = self.Ny * self.Nz
         lo, hi = starts[rank] * P, (starts[rank] + sizes[rank]) * P
         first = starts[rank] - (1 if rank > 0 else 0)           # global index of local plane 0

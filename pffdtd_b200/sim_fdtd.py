@@ -31,8 +31,9 @@ from .sim_data import SimData
 
 class SimEngine:
     def __init__(self, data_dir, energy_on=False, nthreads=None, precision=2, device=None, scale=True, quiet=False, timing=False,
-                 gpu_folder=False):
+                 gpu_folder=False, balance=True):
         self.data_dir = Path(data_dir)
+        self.balance = bool(balance)  # cost-weighted slab split (False: the reference's equal-plane split, gpu_engine.h:532-543)
         self.energy_on = bool(energy_on)
         self.H_tot = self.E_lost = self.E_in = None
         self.precision = int(precision)
@@ -88,7 +89,13 @@ class SimEngine:
         pass  # the node mask is built on the device at allocate_mem()
 
     def allocate_mem(self):
-        self.sd = self.sd_full.slab(self.rank, self.world)
+        # slabs of about equal cost (air nodes + weighted boundary / lossy / shell nodes per plane) unless the reference's
+        # equal-plane split is asked for; the receiver traces are the same bits either way
+        self.planes = None
+        if self.world > 1 and self.balance:
+            self.planes = SimData.slab_planes(self.sd_full.Nx, self.world, cost=self.sd_full.plane_costs())
+            self.print(f"slab planes per rank: {self.planes[1]}")
+        self.sd = self.sd_full.slab(self.rank, self.world, planes=self.planes)
         self.eng = Engine(self.sd, self.device)
         if self.world > 1:
             self._comm_init()
@@ -147,7 +154,10 @@ class SimEngine:
         self.u_out = u
         if self.energy_on:
             # every rank summed its own planes; the three series add up across ranks
-            self.H_tot, self.E_lost, self.E_in = (parallel.sum_arrays(a) for a in self.eng.read_energy())
+            # (the engine ran on scale_input()'d sources: energies are quadratic in the field, so undoing the scaling takes infac^2
+            # -- the reference's Python engine never scales, sim_fdtd.py:587-620)
+            k = self.sd_full.infac ** 2 if self.scale else 1.0
+            self.H_tot, self.E_lost, self.E_in = (parallel.sum_arrays(a) * k for a in self.eng.read_energy())
 
     def print_last_energy(self, Np):
         """sim_fdtd.py:662-669: rel_diff(H_tot+E_lost, E_in) of the last Np steps (common/myfuncs.py:164-165)"""
@@ -169,7 +179,7 @@ class SimEngine:
             uslice, i3 = u1[:, :, iz], iz
         else:
             raise ValueError("give ix, iy or iz")
-        uslice = np.array(uslice)
+        uslice = np.array(uslice) * (self.sd_full.infac if self.scale else 1.0)  # the field of the unscaled problem, as the reference plots it
         if self.sd_full.fcc_flag == 1:
             fcc_fill_plot_holes(uslice, i3)
         return uslice
@@ -240,6 +250,7 @@ def main(argv=None):
     parser.add_argument("--device", type=int, default=None)
     parser.add_argument("--gpu_folder", action="store_true", help="rotate / fold (FCC) / sort the folder's datasets in memory first, as sim_setup's "
                         "save_folder_gpu does on disk: a plain folder then runs like its gpu folder (half the stored nodes for FCC)")
+    parser.add_argument("--equal_slabs", action="store_true", help="multi-GPU: the reference's equal-plane split instead of the cost-weighted one")
     parser.add_argument("--timing", action="store_true", help="also print the reference's 'Air update' / 'Boundary loop' lines (CUDA events around every air launch)")
     # accepted so that the reference's command lines keep working (sim_fdtd.py:899-906); plotting is not part of the simulation step
     parser.add_argument("--plot", action="store_true", help="not available: use SimEngine.gather_slice between run_steps batches")
@@ -252,7 +263,7 @@ def main(argv=None):
     if args.data_dir is None:
         args.data_dir = os.getcwd()  # the C binaries run in the data folder (fdtd_main.c:35)
     eng = SimEngine(args.data_dir, energy_on=args.energy, nthreads=args.nthreads, precision=args.precision, device=args.device, timing=args.timing,
-                    gpu_folder=args.gpu_folder)
+                    gpu_folder=args.gpu_folder, balance=not args.equal_slabs)
     eng.load_h5_data()
     eng.setup_mask()
     eng.allocate_mem()

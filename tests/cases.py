@@ -46,11 +46,41 @@ OBSTACLE_CASES = {
 }
 
 
+def _open_halo_links(files):
+    """interior nodes of the walls at z = 1 / z = Nz-2 (wall_offset 0: their only cut link points at the halo): every third one gets that
+    link OPEN and its +x link cut instead -- a masked node on the z shell that reads the z halo, next to a plain air node at z = 2 / Nz-3
+    (the adjacency is not symmetric any more; the engines do not care)"""
+    v = files["vox_out"]
+    Nx, Ny, Nz = int(v["Nx"]), int(v["Ny"]), int(v["Nz"])
+    bn, adj = v["bn_ixyz"], v["adj_bn"].copy()
+    iz, iy, ix = bn % Nz, (bn // Nz) % Ny, bn // (Ny * Nz)
+    inner = (ix >= 3) & (ix <= Nx - 4) & (iy >= 3) & (iy <= Ny - 4) & ((ix + iy) % 3 == 0)
+    lo, hi = inner & (iz == 1), inner & (iz == Nz - 2)
+    assert lo.sum() > 10 and hi.sum() > 10 and not adj[lo, 5].any() and not adj[hi, 4].any()
+    adj[lo, 5], adj[hi, 4] = True, True
+    adj[lo | hi, 0] = False
+    v["adj_bn"] = adj
+    v["saf_bn"] = (~adj).sum(axis=1).astype(np.float64)
+    return files
+
+
+# cases without golden traces of the reference engine (checked against the oracle only)
+EXTRA_CASES = {
+    # more planes than round 1's 96-chunk work plan covered in 16-plane chunks (1536): every x-chunk of the arithmetic plan, the guided tail
+    "cart_long": (dict(Nx=1700, Ny=16, Nz=24, Nt=20, nmat=1, mb=2), "cart"),
+    # masked nodes ON the z shell with an open link to the z halo (the vector holding the halo is fully masked in fp64)
+    "cart_open_halo": (dict(Nx=20, Ny=19, Nz=22, Nt=40, nmat=1, mb=2, wall_offset=0, _hook=_open_halo_links), "cart"),
+}
+
+
 def make_files(name):
-    kw, layout = CASES[name] if name in CASES else OBSTACLE_CASES[name]
+    kw, layout = CASES[name] if name in CASES else (OBSTACLE_CASES[name] if name in OBSTACLE_CASES else EXTRA_CASES[name])
     kw = dict(kw)
     empty = kw.pop("_empty", False)
+    hook = kw.pop("_hook", None)
     files = shoebox.make_shoebox(kw.pop("Nx"), kw.pop("Ny"), kw.pop("Nz"), kw.pop("Nt"), **kw)
+    if hook:
+        files = hook(files)
     if empty:  # no walls at all: Nb = Nbl = 0
         nn = 12 if kw.get("fcc") else 6
         files["vox_out"].update(Nb=np.int64(0), bn_ixyz=np.zeros(0, np.int64), adj_bn=np.zeros((0, nn), bool),

@@ -16,7 +16,7 @@ HEADER = (ROOT / "include" / "pffdtd_b200.h").read_text()
 
 
 def declared_functions():
-    names = re.findall(r"^\s*(?:const\s+)?(?:int|char|void)\s*\*?\s*(pffdtd_\w+)\s*\(", HEADER, flags=re.M)
+    names = re.findall(r"^\s*(?:const\s+)?(?:int64_t|int|char|void)\s*\*?\s*(pffdtd_\w+)\s*\(", HEADER, flags=re.M)
     assert len(names) >= 15
     return sorted(set(names))
 
@@ -26,6 +26,24 @@ def test_library_exports_every_declared_symbol():
     for fn in declared_functions():
         assert hasattr(L, fn), f"{fn} declared in the header but not exported"
     assert b"sm_100a" in L.pffdtd_version()
+
+
+@pytest.mark.parametrize("xc", (4, 16, 64))
+def test_air_chunk_plan_covers_any_number_of_planes(xc):
+    """the work queue's x-chunks tile [0, n) exactly for every job length (round 1 capped the plan at 96 chunks, which left one
+    chunk of hundreds of planes on grids with Nx > 1536), main chunks are xc planes long and the tail shrinks to short chunks"""
+    import numpy as np
+    L = engine.lib()
+    buf = (C.c_int64 * 40000)()
+    for n in list(range(0, 200)) + [510, 1022, 1536, 1537, 2046, 2852, 4097, 32768, 100000]:
+        nch = L.pffdtd_air_chunk_plan(n, xc, buf, len(buf))
+        assert nch >= 0
+        b = np.array(buf[:nch + 1])
+        assert b[0] == 0 and b[-1] == n and np.all(np.diff(b) > 0) if n else nch == 0
+        if n >= 16 * xc:
+            d = np.diff(b)
+            assert d.max() == xc and d[-1] <= max(4, xc // 2) and d[-1] <= 8 or xc == 4
+            assert np.all(d[:-24] == xc)
 
 
 def test_desc_layout_matches_the_header():

@@ -34,11 +34,44 @@ class StubEngine:
         assert samples is None or len(samples) == self.sd.Ns
         return np.zeros(self.sd.Nr)
 
+    def read_outputs(self, n0=0, n1=None):
+        return np.zeros((self.sd.Nr, (self.sd.Nt if n1 is None else n1) - n0))
+
     def sync(self):
         pass
 
     def close(self):
         pass
+
+
+def test_default_workload_is_the_grid_the_metric_is_quoted_on():
+    """every N runs BASELINE configs[4] (it fits one B200), so that the 1/2/4/8 values are one strong-scaling curve"""
+    import bench
+    assert bench.WORKLOADS["c5"]["N"] == (2048, 2048, 1024) and bench.WORKLOADS["c5"]["probes"]
+    src = (ROOT / "bench.py").read_text()
+    assert 'wl = args.workload or "c5"' in src and '"scaling": "strong"' in src and '"scaling": "weak"' not in src
+
+
+def test_parity_object_and_probes(monkeypatch, capsys):
+    """the probes workload: a source on every interface of the 8-way split, receivers across them; the line carries the trace hash and
+    the reduced-grid check against the CPU engine (the stub engine returns silence, so the check must report a mismatch, not pass)"""
+    import torch
+    import bench
+    import pffdtd_b200.engine as eng_mod
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(eng_mod, "Engine", StubEngine)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "small_probes", "--steps", "6", "--warmup", "3", "--no-cpu"])
+    bench.main()
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    p = line["parity"]
+    assert p["steps"] == bench.PARITY_STEPS and p["receivers"] == 7 * 2 * (128 // 16) and len(p["traces_sha256"]) == 64
+    assert p["equal_to_one_gpu_run"] is None  # no committed hash for this workload
+    r = p["reduced_grid_vs_cpu_engine"]
+    assert r["bit_exact"] is False and r["peak"] > 0 and "checker" in r and r["steps"] == 48
+    assert line["e2e"]["h2d_bytes_per_step"] == 7 * 4 and line["scaling"] == "strong"
+    assert line["warmup"] == 4  # rounded up to even
 
 
 @pytest.mark.parametrize("workload", ("small",))
@@ -65,7 +98,7 @@ def test_bench_line_has_the_contract_keys(monkeypatch, capsys, workload):
     assert e["unit"] == "Gvox/s" and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     c = line["cpu_baseline"]
     assert c["kind"] == "reference" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
-    assert line["gpu_launches"] == 36
+    assert line["gpu_launches"] == 36 and "also" not in line and "parity" not in line
     # value = nodes * steps / device time: 128*96*64 nodes, 6 steps, 2 ms (the stub's stopwatch)
     assert abs(line["value"] - 128 * 96 * 64 * 6 / 2e-3 / 1e9) < 1e-9
 

@@ -48,7 +48,7 @@ def test_traces_bit_exact(name, precision):
 
 @pytest.mark.parametrize("precision", (2, 1))
 @pytest.mark.parametrize("name", ("cart_lossy", "cart_ragged", "cart_tight", "cart_tight0", "cart_nz_a", "cart_nz_b", "cart_nz_c", "cart_nz_d",
-                                  "cart_nz_e", "cart_nz_f",
+                                  "cart_nz_e", "cart_nz_f", "cart_long", "cart_open_halo",
                                   "fcc1_lossy", "fcc2_lossy", "fcc1_wide", "fcc2_wide"))
 def test_full_state_bit_exact_from_noise(name, precision):
     """whole grids + boundary ODE state after 25 steps from a random initial state: exercises every

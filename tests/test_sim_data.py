@@ -126,10 +126,10 @@ def test_fcc_plot_hole_fill_equals_the_reference():
         assert np.array_equal(fcc_fill_plot_holes(a.copy(), i3), want)
 
 
-def _run_slabs_in_process(full, nranks):
+def _run_slabs_in_process(full, nranks, planes=None):
     """the oracle on every slab of `full` in one process, halo planes copied by hand after every step"""
     from oracle import Oracle
-    slabs = [full.slab(r, nranks) for r in range(nranks)]
+    slabs = [full.slab(r, nranks, planes=planes) for r in range(nranks)]
     orcs = [Oracle(s) for s in slabs]
     for n in range(full.Nt):
         for o in orcs:
@@ -157,3 +157,43 @@ def test_slab_split_of_random_rooms_changes_no_bit(seed, nranks):
         want = Oracle(full).run_all()
         assert np.abs(want).max() > 0
         assert np.array_equal(_run_slabs_in_process(full, nranks), want)
+
+
+@pytest.mark.parametrize("nranks", (2, 3, 4))
+def test_cost_weighted_slabs_balance_the_walls_and_change_no_bit(nranks):
+    """slab_planes(cost=plane_costs()): ranks that hold the walls perpendicular to x get fewer planes, every slab keeps >= 2 planes,
+    the costs are closer to equal than with the reference's equal-plane split, and the traces are the same bits"""
+    from oracle import Oracle
+    sd = make_sim_data("cart_lossy_mb11", 2).sorted()
+    cost = sd.plane_costs()
+    assert cost.shape == (sd.Nx,) and cost[1:-1].min() >= sd.Ny * sd.Nz
+    starts, sizes = SimData.slab_planes(sd.Nx, nranks, cost=cost)
+    assert sum(sizes) == sd.Nx and starts[0] == 0 and min(sizes) >= 2 and starts == [sum(sizes[:r]) for r in range(nranks)]
+    e_starts, e_sizes = SimData.slab_planes(sd.Nx, nranks)
+    per = lambda st, sz: [cost[a:a + n].sum() for a, n in zip(st, sz)]
+    assert max(per(starts, sizes)) <= max(per(e_starts, e_sizes))
+    # heavy end planes (x walls + x shell of a large room): the end slabs get fewer planes
+    heavy = np.ones(64)
+    heavy[[1, 3, 4, 59, 60, 62]] = 12.0
+    hs = SimData.slab_planes(64, 4, cost=heavy)[1]
+    assert hs[0] < hs[1] and hs[3] < hs[2] and sum(hs) == 64
+    want = Oracle(sd).run_all()
+    assert np.array_equal(_run_slabs_in_process(sd, nranks, planes=(starts, sizes)), want)
+    with pytest.raises(ValueError):
+        SimData.slab_planes(sd.Nx, nranks, cost=cost[:-1])
+    with pytest.raises(ValueError):
+        SimData.slab_planes(5, 3, cost=np.ones(5))
+
+
+def test_duplicate_source_nodes_are_sorted_and_split():
+    """two source entries on one grid node (legal: the reference accumulates them in list order, cpu_engine.h:310-313) still count
+    as a sorted list and split into slabs (gpu_engine.h:562-661 only walks the list); the traces equal the single-domain run"""
+    from dataclasses import replace
+    from oracle import Oracle
+    sd = make_sim_data("cart_lossy", 2).sorted()
+    dup = replace(sd, in_ixyz=np.concatenate([sd.in_ixyz, sd.in_ixyz[:2]]), in_sigs=np.concatenate([sd.in_sigs, 0.5 * sd.in_sigs[:2]]), _keep=[])
+    dup = dup.sorted()
+    assert dup.is_sorted() and dup.Ns == sd.Ns + 2 and np.any(np.diff(dup.in_ixyz) == 0)
+    want = Oracle(dup).run_all()
+    assert not np.array_equal(want, Oracle(sd).run_all())
+    assert np.array_equal(_run_slabs_in_process(dup, 2), want)
