@@ -66,6 +66,8 @@ class Oracle:
         self.u_out = np.zeros((sd.Nr, max(sd.Nt, 1)), np.float64)
 
     def run_steps(self, nstart, nsteps):
+        if nstart < 0 or nsteps < 0 or nstart + nsteps > self.sd.Nt:  # the C side writes u_out[:, n] unchecked
+            raise ValueError(f"steps [{nstart},{nstart + nsteps}) outside [0,{self.sd.Nt})")
         self.lib().oracle_run_steps(self.h, nstart, nsteps, self.u_out.ctypes.data, self.u_out.shape[1])
 
     def run_all(self):

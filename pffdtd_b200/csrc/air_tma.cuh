@@ -32,6 +32,22 @@
 
 namespace pf {
 
+// In-kernel boundary work ("service warp", kernels built with SVC): a list of the SPARSE special nodes of every tile-plane --
+// rigid-boundary nodes (cpu_engine.h:234-287) of tile-planes that hold few of them, and the z faces of the absorbing shell
+// (cpu_engine.h:225-229) -- is processed by one extra warp from the shared-memory stages, where the node's seven (thirteen) u1
+// values and its old u0 already are: the warp writes the finished value into the stage's u0 tile (and sets the node's bit in the
+// stage's mask words) BEFORE the consumers read that tile, so the consumers carry it to HBM inside their ordinary full-vector
+// stores (and into the halo mirrors).  List-driven kernels pay a 32-byte DRAM sector per tap for exactly these nodes (z walls:
+// one or two nodes per row): round 1's k_rigid moved 86 B and k_abc_faces 76 B per node for them.  Dense runs of boundary nodes
+// (walls perpendicular to x or y, contiguous along z) stay with the list kernel, where they coalesce.
+// Entry: bits 0-6 column in the tile, 7-12 row in the tile, 13-15 kind (0 rigid, 1 shell face Q=1, 7 none), 16-27 adjacency.
+struct AirSvc {
+   const uint32_t *list;  // entries grouped by (tile, plane)
+   const uint32_t *off;   // [tiles][pitch]: entries of plane x of a tile = [off[x], off[x+1])
+   int pitch;             // Nx + 1
+};
+#define PF_SVC_NONE 0xE000u
+
 struct AirTma {
    bool ok = false;
    std::string why = "not set up";
@@ -48,6 +64,9 @@ struct AirTma {
    int sm_count = 148;
    int slots = 0;       // resident CTAs of the chosen configuration on this device
    int *ctr = nullptr;  // device: {next item, CTAs done}, zero between launches
+   int svc = 0;         // the configuration has the service warp
+   int ty = 0, tzn = 0; // tile shape in nodes (rows, columns)
+   AirSvc sv{nullptr, nullptr, 0};  // the service warp's lists for this tile shape (engine-built), null = none
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -106,7 +125,7 @@ __device__ __forceinline__ void st_vec(Real *p, const Real (&d)[VEC]) {
 
 // LZ = lanes of a warp along z (32, 16 or 8); the other 32/LZ = LR lane groups take further rows, so a warp covers
 // LZ vectors x LR*RPT rows.  Narrow tiles cut the padding a grid pays when Nz is not a multiple of 32 vectors.
-template <typename Real, int RPT, int NW, int S, int LZ = 32>
+template <typename Real, int RPT, int NW, int S, int LZ = 32, bool SVC = false>
 struct AirCfg {
    static constexpr int VEC = 16 / (int)sizeof(Real);
    static constexpr int LR = 32 / LZ;
@@ -121,8 +140,8 @@ struct AirCfg {
    static constexpr int U0_OFF = (U1_BYTES + 127) / 128 * 128;
    static constexpr int MK_OFF = U0_OFF + U0_BYTES;
    static constexpr int STAGE_PITCH = (MK_OFF + MK_BYTES + 127) / 128 * 128;
-   static constexpr int SMEM_BYTES = S * STAGE_PITCH + 2 * S * 8 + S * 16 + 128;  // stages, full/empty barriers, item headers
-   static constexpr int THREADS = (NW + 1) * 32;  // NW consumer warps + 1 TMA producer warp
+   static constexpr int SMEM_BYTES = S * STAGE_PITCH + 3 * S * 8 + S * 16 + 128;  // stages, full/empty/patched barriers, item headers
+   static constexpr int THREADS = (NW + 1 + (SVC ? 1 : 0)) * 32;  // NW consumer warps + 1 TMA producer warp (+ 1 service warp)
 };
 
 // ---------------------------------------------------------------- work decomposition
@@ -196,6 +215,8 @@ static void air_plan_chunks(AirJob *jb, int n, int xc) {
 template <typename Real>
 struct AirEdge {
    int fuse, x_lo, x_hi, Nx;
+   int zstash;  // the consumers stash the pre-update values of the shell's z faces for k_abc_faces (0 when the service warp does them)
+   Real sl2;    // rigid update: b1 = 2 - sl2*K
    // pre-update values of the shell nodes, for k_abc_faces:
    Real *zold;  // [Nx][Ny][2]    z=1 / z=Nz-2 of every row
    Real *yold;  // [Nx][2][Nzp]   rows y=1 / y=Ny-2
@@ -256,13 +277,14 @@ struct FacesArgs {
    Real *u0;
    const Real *zold, *yold, *xold;
    int Nx, Ny, Nz, Nzp, xb, xe, x_lo, x_hi;
+   int do_z;  // 0: the z faces were finished inside the air kernel (service warp)
    Real lQ1, lQ2, lQ3;
 };
 template <typename Real>
 __global__ void k_abc_faces(const FacesArgs<Real> a) {
    typedef Ops<Real> O;
    const int nx = a.xe - a.xb;
-   const i64 nZ = (i64)nx * a.Ny * 2, nY = (i64)nx * 2 * a.Nz, nX = (i64)2 * a.Ny * a.Nz;
+   const i64 nZ = a.do_z ? (i64)nx * a.Ny * 2 : 0, nY = (i64)nx * 2 * a.Nz, nX = (i64)2 * a.Ny * a.Nz;
    // descending x within each class: the planes the air kernel wrote last are still in L2
    i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
    if (t < nZ) t = nZ - 1 - t;
@@ -313,12 +335,12 @@ __global__ void k_abc_faces(const FacesArgs<Real> a) {
 // full[s] flips when all bytes of a plane have landed in stage s, empty[s] when all NW consumer warps
 // are done with it.  Loads are numbered consecutively over all segments of the CTA; load i uses stage
 // i % S.  A segment of cnt planes loads planes xa-1 .. xa+cnt: the first and the last only as u1.
-template <typename Real, int RPT, int NW, int S, int MAXR, bool FCC, int LZ>
+template <typename Real, int RPT, int NW, int S, int MAXR, bool FCC, int LZ, bool SVC>
 __global__ void __maxnreg__(MAXR)
     k_air_tma_cart(const __grid_constant__ CUtensorMap map_u1, const __grid_constant__ CUtensorMap map_u0,
                    const __grid_constant__ CUtensorMap map_mk, Real *__restrict__ u0g, const AirJob jb, const Real a1, const Real a2,
-                   const AirEdge<Real> eg) {
-   typedef AirCfg<Real, RPT, NW, S, LZ> C;
+                   const AirEdge<Real> eg, const AirSvc sv) {
+   typedef AirCfg<Real, RPT, NW, S, LZ, SVC> C;
    typedef Ops<Real> O;
    constexpr int VEC = C::VEC, BZ = C::BZ, TZ = C::TZ;
    constexpr uint32_t VMASK = (1u << VEC) - 1u;
@@ -328,8 +350,9 @@ __global__ void __maxnreg__(MAXR)
    extern __shared__ __align__(1024) unsigned char smem[];
    uint64_t *full = (uint64_t *)(smem + S * C::STAGE_PITCH);
    uint64_t *empty = full + S;
+   uint64_t *patched = empty + S;  // (SVC) flips when the service warp is done with the load in stage s
 
-   int4 *hdr = (int4 *)(empty + S);  // per stage: the item (xa, cnt, z0, y0) whose first plane it holds; cnt < 0 = stop
+   int4 *hdr = (int4 *)(patched + S);  // per stage: the item (xa, cnt, z0, y0) whose first plane it holds; cnt < 0 = stop
 
    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
    const int lz = lane % LZ;                     // this thread's vector within its row
@@ -338,7 +361,8 @@ __global__ void __maxnreg__(MAXR)
    if (tid == 0) {
       for (int s = 0; s < S; s++) {
          mbar_init(&full[s], 1);
-         mbar_init(&empty[s], NW);
+         mbar_init(&empty[s], NW + (SVC ? 1 : 0));
+         mbar_init(&patched[s], 1);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -388,6 +412,110 @@ __global__ void __maxnreg__(MAXR)
       return;
    }
 
+   // ---------------- service warp: the sparse special nodes of every centre plane, from the stages (see AirSvc)
+   // It walks the same sequence of loads as the consumers.  For the centre plane x in stage s it needs the u1 boxes of x-1, x, x+1
+   // (stages s-1, s, s+1), patches the u0 tile and the mask words of stage s and arrives on patched[s]; patched[] flips once per
+   // load (also for the planes that are only read as x-1 / x+1), so its parity follows the ring like full[] / empty[].  It counts as
+   // one more consumer on empty[]: a stage is refilled only after this warp has read its last tap from it.
+   if constexpr (SVC) {
+      if (w == NW + 1) {
+         constexpr int NN = FCC ? 12 : 6;
+         struct R2 {
+            int s;
+            uint32_t ph;
+            __device__ __forceinline__ void next() {
+               if (++s == S) s = 0, ph ^= 1u;
+            }
+         };
+         auto done = [&](uint64_t *bar) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
+         };
+         const Real lQ1 = eg.lQ1;
+         const double den1 = eg.den1, rden1 = eg.rden1;
+         R2 g0{0, 0u};
+         for (;;) {
+            mbar_wait(&full[g0.s], g0.ph);
+            const int4 h = hdr[g0.s];
+            if (h.y < 0) break;
+            const int cnt = h.y;
+            const int tile = ((h.w - 1) / C::TY) * jb.tz + h.z / C::TZ;
+            const uint32_t *ob = sv.off + (size_t)tile * sv.pitch + h.x;  // ob[j], ob[j+1]: entries of plane xa + j
+            const bool have = sv.list != nullptr;  // no list (unfused step, energy mode): the warp only keeps the barriers moving
+            const uint32_t o0 = have && lane <= cnt ? ob[lane] : 0u, o1 = have && lane + 32 <= cnt ? ob[lane + 32] : 0u;
+            auto off_at = [&](int j) {
+               const uint32_t a = __shfl_sync(0xffffffffu, o0, j & 31), b = __shfl_sync(0xffffffffu, o1, j & 31);
+               return j < 32 ? a : b;
+            };
+            // the first two passes of a plane are fetched one plane ahead (a dependent global load per plane would make this warp the
+            // pacemaker of the CTA)
+            uint32_t b0 = off_at(0), e0 = off_at(1);
+            uint32_t n0 = b0 + lane < e0 ? sv.list[b0 + lane] : PF_SVC_NONE, n1 = b0 + 32 + lane < e0 ? sv.list[b0 + 32 + lane] : PF_SVC_NONE;
+            done(&patched[g0.s]);
+            R2 gm = g0, gc = g0;
+            gc.next();
+            mbar_wait(&full[gc.s], gc.ph);
+            for (int j = 0; j < cnt; j++) {
+               R2 gu = gc;
+               gu.next();
+               mbar_wait(&full[gu.s], gu.ph);
+               const uint32_t b = b0, e = e0;
+               const uint32_t c0 = n0, c1 = n1;
+               if (j + 1 < cnt) {
+                  b0 = e0, e0 = off_at(j + 2);
+                  n0 = b0 + lane < e0 ? sv.list[b0 + lane] : PF_SVC_NONE;
+                  n1 = b0 + 32 + lane < e0 ? sv.list[b0 + 32 + lane] : PF_SVC_NONE;
+               }
+               unsigned char *stc = smem + gc.s * C::STAGE_PITCH;
+               const Real *sc = (const Real *)stc, *sm = (const Real *)(smem + gm.s * C::STAGE_PITCH),
+                          *su = (const Real *)(smem + gu.s * C::STAGE_PITCH);
+               Real *u0s = (Real *)(stc + C::U0_OFF);
+               uint32_t *mks = (uint32_t *)(stc + C::MK_OFF);
+               for (uint32_t i = b; i < e; i += 32) {
+                  const uint32_t ent = i == b ? c0 : (i == b + 32 ? c1 : (i + lane < e ? sv.list[i + lane] : PF_SVC_NONE));
+                  const unsigned kind = (ent >> 13) & 7u;
+                  if (kind < 2u) {
+                     const int c = (int)(ent & 127u), r = (int)((ent >> 7) & 63u);
+                     const unsigned adj = kind == 1u ? 0xfffu : (ent >> 16) & 0xfffu;
+                     const int idx = (r + 1) * BZ + VEC + c;
+                     const Real uc = sc[idx], uo = u0s[r * TZ + c];
+                     Real b1 = a1;
+                     if (kind == 0u) b1 = O::sub((Real)2.0, O::mul(eg.sl2, (Real)__popc(adj)));
+                     Real p = O::sub(O::mul(b1, uc), uo);
+                     Real t[NN];
+                     if constexpr (!FCC) {  // +x -x +y -y +z -z (cpu_engine.h:249-254)
+                        t[0] = su[idx], t[1] = sm[idx], t[2] = sc[idx + BZ], t[3] = sc[idx - BZ], t[4] = sc[idx + 1], t[5] = sc[idx - 1];
+                     } else {  // cpu_engine.h:273-284
+                        t[0] = su[idx + BZ], t[1] = sm[idx - BZ], t[2] = sc[idx + BZ + 1], t[3] = sc[idx - BZ - 1];
+                        t[4] = su[idx + 1], t[5] = sm[idx - 1], t[6] = su[idx - BZ], t[7] = sm[idx + BZ];
+                        t[8] = sc[idx + BZ - 1], t[9] = sc[idx - BZ + 1], t[10] = su[idx - 1], t[11] = sm[idx + 1];
+                     }
+#pragma unroll
+                     for (int q = 0; q < NN; q++) p = O::add(p, O::mul(((adj >> q) & 1u) ? a2 : (Real)0.0, t[q]));
+                     if (kind == 1u) {
+                        p = abc_apply<Real>(p, uo, lQ1, den1, rden1);
+                        const int zc = (h.z & 127) + c;
+                        atomicOr(&mks[r * C::MKW + (zc >> 5)], 1u << (zc & 31));
+                     }
+                     u0s[r * TZ + c] = p;
+                  }
+               }
+               done(&patched[gc.s]);
+               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+               done(&empty[gm.s]);
+               gm = gc;
+               gc = gu;
+            }
+            done(&patched[gc.s]);  // the last plane was only ever an "x+1" plane
+            done(&empty[gm.s]);
+            done(&empty[gc.s]);
+            g0 = gc;
+            g0.next();
+         }
+         return;
+      }
+   }
+
    // ---------------- consumers
    // ring position of a load: stage index and phase parity, advanced incrementally (no div/mod in the loop)
    struct Ring {
@@ -398,6 +526,9 @@ __global__ void __maxnreg__(MAXR)
       }
    };
    auto wait_full = [&](const Ring &g) { mbar_wait(&full[g.s], g.ph); };
+   auto wait_patched = [&](const Ring &g) {  // the centre plane's u0 tile and mask words are final
+      if constexpr (SVC) mbar_wait(&patched[g.s], g.ph);
+   };
    auto release = [&](const Ring &g) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[g.s]);
@@ -481,6 +612,7 @@ __global__ void __maxnreg__(MAXR)
             Ring gu = gc;  // plane x+1
             gu.next();
             wait_full(gu);
+            wait_patched(gc);
             const unsigned char *stc = stage(gc);
             const Real *sm = (const Real *)stage(gm) + soff;
             const Real *sc = (const Real *)stc + soff;
@@ -525,7 +657,8 @@ __global__ void __maxnreg__(MAXR)
                      p = O::add(p, O::mul(a2, (k < VEC - 1) ? m1[r][k + 1] : m1r));        // -x +z
                      o[k] = ((m >> k) & 1u) ? u0v[k] : p;
                   }
-                  if (r < nrow && m != VMASK) st_vec<Real, VEC>(u0p + (i64)r * Nzp, o);
+                  // (also a fully masked vector is stored: the service warp may have finished one of its nodes in the stage)
+                  if (r < nrow && (SVC || m != VMASK)) st_vec<Real, VEC>(u0p + (i64)r * Nzp, o);
                }
 #pragma unroll
                for (int k = 0; k < VEC; k++) {
@@ -571,6 +704,7 @@ __global__ void __maxnreg__(MAXR)
          Ring gu = gc;
          gu.next();
          wait_full(gu);
+         wait_patched(gc);
          const unsigned char *stc = stage(gc);
          const Real *sc = (const Real *)stc + soff;
          const Real *su = (const Real *)stage(gu) + soff;
@@ -627,7 +761,7 @@ __global__ void __maxnreg__(MAXR)
                __syncwarp(am);  // the row groups may have diverged on `shell`
                if (zlo_tile) {  // warp-uniform: the tile starts at z = 0
                   // lane 0 holds z=1 (shell): stash its pre-update value; z=2 -> z=0 mirror
-                  if (lz == 0 && !shell) zop[2 * r] = u0v[1];
+                  if (eg.zstash && lz == 0 && !shell) zop[2 * r] = u0v[1];
                   if constexpr (VEC >= 4) {
                      o[0] = (lz == 0) ? o[2] : o[0];
                   } else {
@@ -643,7 +777,7 @@ __global__ void __maxnreg__(MAXR)
                      vs = (k == khs) ? u0v[k] : vs;
                      vm = (k == khm) ? o[k] : vm;
                   }
-                  if (khs >= 0 && !shell) zop[2 * r + 1] = vs;  // z = Nz-2 (shell)
+                  if (eg.zstash && khs >= 0 && !shell) zop[2 * r + 1] = vs;  // z = Nz-2 (shell)
 #pragma unroll
                   for (int k = 0; k + 2 < VEC; k++) o[k + 2] = (k == khm) ? o[k] : o[k + 2];  // z=Nz-3 -> z=Nz-1 inside the vector
                   // a vector that starts at z=Nz-2 holds z=Nz-1 as element 1 and finds z=Nz-3 at the end of the previous lane's
@@ -652,10 +786,11 @@ __global__ void __maxnreg__(MAXR)
                   const Real t = __shfl_up_sync(am, o[VEC - 1], 1);
                   o[1] = (khs == 0) ? t : o[1];
                }
-               if (m != VMASK) {
-                  st_vec<Real, VEC>(dst, o);
-                  if (zhi_tile && khm + 2 == VEC) dst[VEC] = vm;  // z=Nz-1 opens the next vector, which nobody stores
-               }
+               // Every vector of an active row is stored, fully masked ones too: it may hold the z halo (mirror-on-write: a masked
+               // node at z = 1 / Nz-2 must not keep the halo next to it from being refreshed) or a node the service warp finished
+               // in the stage.  Masked elements carry their stage value.
+               st_vec<Real, VEC>(dst, o);
+               if (zhi_tile && khm + 2 == VEC) dst[VEC] = vm;  // z=Nz-1 opens the next vector, which nobody stores
                if (rrole & 6u) {
                   // mirror source of a y / x halo: the same row goes there as well (warp-uniform, a few rows / planes)
                   const int y = ybase + r;
@@ -695,53 +830,63 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// tile configurations (id, rows per thread, consumer warps, stages, register cap, lanes along z); 0 / 5 are the defaults for
-// whole-tile grids (7-point / FCC), 8..11 their narrow-tile versions for ragged Nz (see air_pick_cfg)
-#define PF_AIR_CONFIGS(X) \
-   X(0, 1, 15, 6, 64, 32)   \
-   X(1, 2, 8, 4, 72, 32)    \
-   X(2, 2, 8, 6, 112, 32)   \
-   X(3, 1, 15, 4, 64, 32)   \
-   X(4, 4, 8, 3, 112, 32)   \
-   X(5, 1, 11, 6, 80, 32)   \
-   X(6, 2, 12, 4, 72, 32)   \
-   X(7, 1, 8, 6, 80, 32)    \
-   X(8, 1, 15, 6, 64, 16)   \
-   X(9, 1, 15, 6, 64, 8)    \
-   X(10, 1, 11, 6, 80, 16)  \
-   X(11, 1, 11, 6, 80, 8)
-#define PF_AIR_NCFG 12
+// tile configurations (id, rows per thread, consumer warps, stages, register cap, lanes along z, service warp); 0 / 5 are the
+// defaults for whole-tile grids without in-kernel boundary work (7-point / FCC), 8..11 their narrow-tile versions for ragged Nz
+// (see air_pick_cfg); 12..17 the same three widths with the service warp (one consumer warp fewer: 16 / 12 warps per CTA keep two
+// CTAs per SM inside the register file)
+#define PF_AIR_CONFIGS(X)        \
+   X(0, 1, 15, 6, 64, 32, false)  \
+   X(1, 2, 8, 4, 72, 32, false)   \
+   X(2, 2, 8, 6, 112, 32, false)  \
+   X(3, 1, 15, 4, 64, 32, false)  \
+   X(4, 4, 8, 3, 112, 32, false)  \
+   X(5, 1, 11, 6, 80, 32, false)  \
+   X(6, 2, 12, 4, 72, 32, false)  \
+   X(7, 1, 8, 6, 80, 32, false)   \
+   X(8, 1, 15, 6, 64, 16, false)  \
+   X(9, 1, 15, 6, 64, 8, false)   \
+   X(10, 1, 11, 6, 80, 16, false) \
+   X(11, 1, 11, 6, 80, 8, false)  \
+   X(12, 1, 14, 6, 64, 32, true)  \
+   X(13, 1, 14, 6, 64, 16, true)  \
+   X(14, 1, 14, 6, 64, 8, true)   \
+   X(15, 1, 10, 6, 80, 32, true)  \
+   X(16, 1, 10, 6, 80, 16, true)  \
+   X(17, 1, 10, 6, 80, 8, true)
+#define PF_AIR_NCFG 18
 
 template <typename Real>
 static int air_tma_attr(int cfg) {
    cudaError_t rc = cudaErrorInvalidValue;
-#define X(id, RPT, NW, S, MAXR, LZ)                                                                                     \
-   if (cfg == id) {                                                                                                            \
-      rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, false, LZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                AirCfg<Real, RPT, NW, S, LZ>::SMEM_BYTES);                                                       \
-      if (rc == cudaSuccess)                                                                                                   \
-         rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                   AirCfg<Real, RPT, NW, S, LZ>::SMEM_BYTES);                                                    \
+#define X(id, RPT, NW, S, MAXR, LZ, SVC)                                                                                          \
+   if (cfg == id) {                                                                                                                   \
+      rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, false, LZ, SVC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                AirCfg<Real, RPT, NW, S, LZ, SVC>::SMEM_BYTES);                                                       \
+      if (rc == cudaSuccess)                                                                                                          \
+         rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ, SVC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   AirCfg<Real, RPT, NW, S, LZ, SVC>::SMEM_BYTES);                                                    \
    }
    PF_AIR_CONFIGS(X)
 #undef X
    return (int)rc;
 }
 
-static void air_cfg_shape(int cfg, int *rpt, int *nw, int *lz) {
+static void air_cfg_shape(int cfg, int *rpt, int *nw, int *lz, int *svc = nullptr) {
    *rpt = 4, *nw = 8, *lz = 32;
-#define X(id, RPT, NW, S, MAXR, LZ) \
-   if (cfg == id) *rpt = RPT, *nw = NW, *lz = LZ;
+   int sv = 0;
+#define X(id, RPT, NW, S, MAXR, LZ, SVC) \
+   if (cfg == id) *rpt = RPT, *nw = NW, *lz = LZ, sv = SVC ? 1 : 0;
    PF_AIR_CONFIGS(X)
 #undef X
+   if (svc) *svc = sv;
 }
 
 // default configuration for a grid: the widest tile (32, 16, 8 lanes along z) that wastes less than 12 % of its columns on the
 // padding behind Nz-1, else the one that wastes least.  Real rooms need this: the reference's gpu folders make z the SHORTEST
 // axis (CTK church Nz = 180: 70 % useful columns with 32 lanes, 93 % with 16; Musikverein Nz = 258: 67 % / 80 % / 89 %).
-static int air_pick_cfg(int fcc, int precision, i64 Nz) {
+static int air_pick_cfg(int fcc, int precision, i64 Nz, int svc = 0) {
    const int vec = precision == 1 ? 4 : 2;
-   const int ids[3] = {fcc ? 5 : 0, fcc ? 10 : 8, fcc ? 11 : 9};
+   const int ids[3] = {svc ? (fcc ? 15 : 12) : (fcc ? 5 : 0), svc ? (fcc ? 16 : 13) : (fcc ? 10 : 8), svc ? (fcc ? 17 : 14) : (fcc ? 11 : 9)};
    const int lzs[3] = {32, 16, 8};
    int best = 0;
    double best_eff = 0;
@@ -755,11 +900,12 @@ static int air_pick_cfg(int fcc, int precision, i64 Nz) {
 }
 
 static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 Nz, i64 Nzp, i64 mwpr, void *u_a, void *u_b, void *mask,
-                         int cfg = -1) {
+                         int cfg = -1, int svc = 0) {
    // defaults (measured on B200, profiles/): 7-point: 15 consumer warps, 64 registers; 13-point FCC: its nine rotating
    // row vectors need 80 registers to stay out of local memory -> 11 consumer warps (c3s: 264 us vs 294 us with cfg 0)
-   if (cfg < 0) cfg = air_pick_cfg(fcc, precision, Nz);
+   if (cfg < 0) cfg = air_pick_cfg(fcc, precision, Nz, svc);
    t->ok = false;
+   t->sv = AirSvc{nullptr, nullptr, 0};  // lists belong to a tile shape: the engine rebuilds them after every set-up
    t->precision = precision, t->fcc = fcc, t->Nx = Nx, t->Ny = Ny, t->Nz = Nz, t->Nzp = Nzp, t->mwpr = mwpr;
    t->base[0] = u_a, t->base[1] = u_b, t->mask = mask;
    if (cfg < 0 || cfg >= PF_AIR_NCFG) {
@@ -784,8 +930,9 @@ static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 
    const size_t rs = precision == 1 ? 4 : 8;
    const int VEC = 16 / (int)rs;
    int rpt, nw, lz;
-   air_cfg_shape(cfg, &rpt, &nw, &lz);
+   air_cfg_shape(cfg, &rpt, &nw, &lz, &t->svc);
    const int ty = nw * rpt * (32 / lz);
+   t->ty = ty, t->tzn = lz * VEC;
    // mirror-on-write finds the source z = Nz-3 of the halo z = Nz-1 in the same z tile; when the shell node z = Nz-2 opens a tile
    // the source sits in another CTA's tile and the fused step must not be used (tests cart_nz_e / cart_nz_f)
    t->z_edge = ((Nz - 2) % ((i64)lz * VEC) == 0) ? 1 : 0;
@@ -828,10 +975,11 @@ static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 
    return 0;
 }
 
-template <typename Real, int RPT, int NW, int S, int MAXR, int LZ>
-static int air_tma_launch_cfg(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real a1, Real a2, const AirEdge<Real> &eg, cudaStream_t s) {
-   typedef AirCfg<Real, RPT, NW, S, LZ> C;
-   auto kern = t->fcc ? k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ> : k_air_tma_cart<Real, RPT, NW, S, MAXR, false, LZ>;
+template <typename Real, int RPT, int NW, int S, int MAXR, int LZ, bool SVC>
+static int air_tma_launch_cfg(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real a1, Real a2, const AirEdge<Real> &eg, bool use_lists,
+                              cudaStream_t s) {
+   typedef AirCfg<Real, RPT, NW, S, LZ, SVC> C;
+   auto kern = t->fcc ? k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ, SVC> : k_air_tma_cart<Real, RPT, NW, S, MAXR, false, LZ, SVC>;
    if (t->slots <= 0) {
       int per_sm = 0;
       cudaError_t rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, C::SMEM_BYTES);
@@ -853,23 +1001,26 @@ static int air_tma_launch_cfg(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real
       int xc = t->xc;
       if (xc <= 0) {
          const i64 per_cta = (i64)jb.n * jb.tiles / std::max(1, t->slots);
-         xc = (int)std::max<i64>(16, std::min<i64>(64, per_cta / 24 / 4 * 4));
+         xc = (int)std::max<i64>(16, std::min<i64>(60, per_cta / 24 / 4 * 4));
       }
+      if (SVC) xc = std::min(xc, 60);  // the service warp keeps an item's cnt+1 list offsets in two registers per lane
       air_plan_chunks(&jb, jb.n, xc);
    }
    const i64 items = (i64)jb.nch * jb.tiles;
    if (items > 0x7fffffff) return (int)cudaErrorInvalidValue;
    jb.n_items = (int)items;
    const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>(t->slots, items));
-   kern<<<grid, C::THREADS, C::SMEM_BYTES, s>>>(t->map_u1[cur], t->map_u0[cur ^ 1], t->map_mk, u0, jb, a1, a2, eg);
+   kern<<<grid, C::THREADS, C::SMEM_BYTES, s>>>(t->map_u1[cur], t->map_u0[cur ^ 1], t->map_mk, u0, jb, a1, a2, eg,
+                                                use_lists ? t->sv : AirSvc{nullptr, nullptr, 0});
    return (int)cudaGetLastError();
 }
 
 // planes [xb, xe) of the slab; `cur` = index of the grid that currently is u1 (u0 = the other one)
 template <typename Real>
-static int air_tma_launch(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real a1, Real a2, const AirEdge<Real> &eg, cudaStream_t s) {
-#define X(id, RPT, NW, S, MAXR, LZ) \
-   if (t->cfg == id) return air_tma_launch_cfg<Real, RPT, NW, S, MAXR, LZ>(t, cur, u0, xb, xe, a1, a2, eg, s);
+static int air_tma_launch(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real a1, Real a2, const AirEdge<Real> &eg, bool use_lists,
+                          cudaStream_t s) {
+#define X(id, RPT, NW, S, MAXR, LZ, SVC) \
+   if (t->cfg == id) return air_tma_launch_cfg<Real, RPT, NW, S, MAXR, LZ, SVC>(t, cur, u0, xb, xe, a1, a2, eg, use_lists, s);
    PF_AIR_CONFIGS(X)
 #undef X
    return (int)cudaErrorInvalidValue;

@@ -157,6 +157,13 @@ struct pffdtd_engine {
    int abc_disjoint = 0, abc_pending = 0;
    cudaStream_t s_abc = nullptr;
    cudaEvent_t ev_abc0 = nullptr, ev_abc1 = nullptr;
+   // in-kernel boundary work (air_tma.cuh AirSvc): per tile-plane lists of the sparse rigid nodes + the shell's z faces, and the
+   // dense remainder of the boundary list that stays with k_rigid
+   int svc_want = 1, svc_on = 0, svc_cap = 64;
+   uint32_t *svc_list = nullptr, *svc_off = nullptr;
+   i64 *bn_left = nullptr;
+   uint16_t *adj_left = nullptr;
+   i64 Nb_left = 0, nbL_lo = 0, nbL_hi = 0, svc_entries = 0;
    // stats
    i64 steps_done = 0;  // next time index expected by run_steps
    double launches = 0;
@@ -188,6 +195,13 @@ static int dalloc_bytes(pffdtd_engine *e, void **p, size_t bytes, bool zero = tr
    e->allocs.push_back(*p);
    if (zero) CU(cudaMemset(*p, 0, bytes));
    return 0;
+}
+
+static void dfree(pffdtd_engine *e, void *p) {
+   if (!p) return;
+   auto it = std::find(e->allocs.begin(), e->allocs.end(), p);
+   if (it != e->allocs.end()) e->allocs.erase(it);
+   cudaFree(p);
 }
 
 // doubles holding Real-rounded values -> Real array on the device
@@ -278,6 +292,108 @@ extern "C" int pffdtd_destroy(pffdtd_engine *e) {
    if (e->s_comm) cudaStreamDestroy(e->s_comm);
    delete e;
    return PFFDTD_OK;
+}
+
+// Lists for the air kernel's service warp (air_tma.cuh AirSvc), for the tile shape of the current configuration.
+// Per (tile, plane): the z faces of the absorbing shell that lie in it (rows 2..Ny-3 of planes off the x shell: Q = 1) and, when
+// the tile-plane holds at most `svc_cap` boundary nodes, those nodes with their adjacency.  Boundary nodes of denser tile-planes
+// (walls perpendicular to x or y: contiguous runs along z) go to the "left" list for k_rigid, where they coalesce.
+// Only for the fused Cartesian step with the canonical shell and no boundary / source node on it (abc_disjoint): then the shell
+// update, the rigid update and the air update touch disjoint nodes and commute.
+static bool svc_eligible(const pffdtd_engine *e) {
+   return e->svc_want && e->fcc == 0 && e->fuse_ok && e->abc_disjoint && e->tma.ok && e->tma.svc && !e->tma.z_edge;
+}
+static int build_service(pffdtd_engine *e) {
+   dfree(e, e->svc_list), dfree(e, e->svc_off), dfree(e, e->bn_left), dfree(e, e->adj_left);
+   e->svc_list = e->svc_off = nullptr, e->bn_left = nullptr, e->adj_left = nullptr;
+   e->svc_on = 0, e->Nb_left = e->nbL_lo = e->nbL_hi = e->svc_entries = 0;
+   e->tma.sv = pf::AirSvc{nullptr, nullptr, 0};
+   if (!svc_eligible(e)) return 0;
+   const i64 Nx = e->Nx, Ny = e->Ny, Nz = e->Nz, Nzp = e->Nzp, TY = e->tma.ty, TZ = e->tma.tzn;
+   const i64 tzc = (Nz - 1 + TZ - 1) / TZ, tyc = (Ny - 2 + TY - 1) / TY, ntile = tzc * tyc, pitch = Nx + 1;
+   if (TY > 64 || TZ > 128 || Ny < 6) return 0;
+   std::vector<i64> bn((size_t)e->Nb);
+   std::vector<uint16_t> adj((size_t)e->Nb);
+   if (e->Nb) {
+      CU(cudaMemcpy(bn.data(), e->bn, (size_t)e->Nb * 8, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(adj.data(), e->adj, (size_t)e->Nb * 2, cudaMemcpyDeviceToHost));
+   }
+   auto key_of = [&](i64 c, i64 *r, i64 *col) {
+      const i64 row = c / Nzp, iz = c - row * Nzp, ix = row / Ny, iy = row - ix * Ny;
+      const i64 ty = (iy - 1) / TY, tz = iz / TZ;
+      *r = iy - 1 - ty * TY, *col = iz - tz * TZ;
+      return (ty * tzc + tz) * pitch + ix;
+   };
+   std::vector<uint32_t> cnt((size_t)(ntile * pitch), 0u);
+   for (i64 i = 0; i < e->Nb; i++) {
+      i64 r, c;
+      cnt[(size_t)key_of(bn[(size_t)i], &r, &c)]++;
+   }
+   // shell rows of a tile row: y in [2, Ny-3]
+   auto shell_rows = [&](i64 ty, i64 *ya, i64 *yb) {
+      *ya = std::max<i64>(2, 1 + ty * TY), *yb = std::min<i64>(Ny - 3, ty * TY + TY);
+   };
+   auto on_xshell = [&](i64 ix) { return (e->x_lo_edge && ix == 1) || (e->x_hi_edge && ix == Nx - 2); };
+   const i64 tz_hi = (Nz - 2) / TZ;
+   std::vector<uint32_t> off((size_t)(ntile * pitch), 0u);
+   uint64_t total = 0;
+   for (i64 t = 0; t < ntile; t++) {
+      const i64 ty = t / tzc, tz = t - ty * tzc;
+      i64 ya, yb;
+      shell_rows(ty, &ya, &yb);
+      const i64 nshell = std::max<i64>(0, yb - ya + 1) * ((tz == 0 ? 1 : 0) + (tz == tz_hi ? 1 : 0));
+      for (i64 x = 0; x <= Nx; x++) {
+         off[(size_t)(t * pitch + x)] = (uint32_t)total;
+         if (x >= 1 && x <= Nx - 2) {
+            if (!on_xshell(x)) total += (uint64_t)nshell;
+            const uint32_t k = cnt[(size_t)(t * pitch + x)];
+            if (k <= (uint32_t)e->svc_cap) total += k;
+         }
+      }
+      if (total > 0xfffffff0ull) return 0;  // (never on one device's slab; keep the list kernels)
+   }
+   std::vector<uint32_t> list((size_t)total, PF_SVC_NONE);
+   std::vector<uint32_t> fill(off);  // next free slot per (tile, plane)
+   for (i64 t = 0; t < ntile; t++) {
+      const i64 ty = t / tzc, tz = t - ty * tzc;
+      i64 ya, yb;
+      shell_rows(ty, &ya, &yb);
+      if (yb < ya || (tz != 0 && tz != tz_hi)) continue;
+      for (i64 x = 1; x <= Nx - 2; x++) {
+         if (on_xshell(x)) continue;
+         uint32_t &f = fill[(size_t)(t * pitch + x)];
+         for (i64 y = ya; y <= yb; y++) {
+            const uint32_t r = (uint32_t)(y - 1 - ty * TY);
+            if (tz == 0) list[f++] = (1u << 13) | (r << 7) | 1u;
+            if (tz == tz_hi) list[f++] = (1u << 13) | (r << 7) | (uint32_t)(Nz - 2 - tz * TZ);
+         }
+      }
+   }
+   std::vector<i64> bl;
+   std::vector<uint16_t> al;
+   for (i64 i = 0; i < e->Nb; i++) {
+      i64 r, c;
+      const i64 key = key_of(bn[(size_t)i], &r, &c);
+      if (cnt[(size_t)key] <= (uint32_t)e->svc_cap)
+         list[fill[(size_t)key]++] = ((uint32_t)(adj[(size_t)i] & 0xfffu) << 16) | ((uint32_t)r << 7) | (uint32_t)c;
+      else
+         bl.push_back(bn[(size_t)i]), al.push_back(adj[(size_t)i]);
+   }
+   int rc;
+   if ((rc = upload_raw(e, &e->svc_list, list.data(), (i64)list.size(), "svc_list"))) return rc;
+   if ((rc = upload_raw(e, &e->svc_off, off.data(), (i64)off.size(), "svc_off"))) return rc;
+   if ((rc = upload_raw(e, &e->bn_left, bl.data(), (i64)bl.size(), "bn_left"))) return rc;
+   if ((rc = upload_raw(e, &e->adj_left, al.data(), (i64)al.size(), "adj_left"))) return rc;
+   e->Nb_left = (i64)bl.size();
+   e->svc_entries = (i64)total;
+   if (e->sorted) {
+      const i64 P = Ny * Nzp;
+      e->nbL_lo = std::lower_bound(bl.begin(), bl.end(), 2 * P) - bl.begin();
+      e->nbL_hi = bl.end() - std::lower_bound(bl.begin(), bl.end(), (Nx - 2) * P);
+   }
+   e->tma.sv = pf::AirSvc{e->svc_list, e->svc_off, (int)pitch};
+   e->svc_on = 1;
+   return 0;
 }
 
 static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
@@ -486,11 +602,13 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    }
    if (dalloc(e, &e->tma.ctr, 2)) return PFFDTD_ECUDA;
    if (dalloc(e, &e->d_n, 1)) return PFFDTD_ECUDA;
-   if ((rc = pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask))) {
+   const int want_svc = e->svc_want && e->fcc == 0 && e->fuse_ok && e->abc_disjoint;
+   if ((rc = pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask, -1, want_svc))) {
       // not fatal: fall back to the generic kernel, remember why
       e->air_kernel = 0;
    }
    CU(cudaStreamSynchronize(e->s_main));
+   if ((rc = build_service(e))) return rc;
    return PFFDTD_OK;
 }
 
@@ -567,11 +685,22 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       e->profile_air = value != 0;
    } else if (k == "air_xc") {
       e->tma.xc = (int)value;
-   } else if (k == "air_cfg") {
+   } else if (k == "air_cfg" || k == "svc" || k == "svc_cap") {
+      // tile configuration (-1 = the default for this grid), in-kernel boundary work on / off, its density threshold: all three
+      // decide the shape of the service lists
       CU(cudaSetDevice(e->device));
       CU(cudaStreamSynchronize(e->s_main));
-      if (pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask, (int)value))
+      int cfg = e->tma.cfg;
+      if (k == "svc") e->svc_want = value != 0, cfg = -1;
+      else if (k == "svc_cap") e->svc_cap = (int)std::max<int64_t>(0, std::min<int64_t>(value, 4096));
+      else cfg = (int)value;
+      const int want_svc = e->svc_want && e->fcc == 0 && e->fuse_ok && e->abc_disjoint;
+      if (k != "svc_cap" &&
+          pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask, cfg, want_svc))
          return fail(PFFDTD_EINVAL, "air_cfg %lld: %s", (long long)value, e->tma.why.c_str());
+      int rc = build_service(e);
+      if (rc) return rc;
+      e->halo_dirty = 1;
    } else if (k == "fd_smem") {
       e->fd_smem = value != 0;
    } else if (k == "abc_overlap") {
@@ -629,6 +758,9 @@ extern "C" int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out) {
    else if (k == "energy") *out = e->energy_on;
    else if (k == "mirror_pairs") *out = (double)e->np;
    else if (k == "abc_disjoint") *out = e->abc_disjoint;
+   else if (k == "svc") *out = e->svc_on;
+   else if (k == "svc_entries") *out = (double)e->svc_entries;
+   else if (k == "nb_left") *out = (double)e->Nb_left;
    else return fail(PFFDTD_EINVAL, "unknown stat %s", key);
    return PFFDTD_OK;
 }
@@ -661,6 +793,7 @@ struct Step {
    cudaStream_t s;
    i64 n;
    bool fused;
+   bool svc;  // the air kernel's service warp does the sparse rigid nodes and the shell's z faces; k_rigid gets the dense rest
 
    // 4. air update of planes [xb, xe)
    int air(i64 xb, i64 xe) {
@@ -685,12 +818,13 @@ struct Step {
          pf::AirEdge<Real> eg;
          memset(&eg, 0, sizeof eg);
          eg.fuse = fused, eg.x_lo = e->x_lo_edge, eg.x_hi = e->x_hi_edge, eg.Nx = (int)e->Nx;
+         eg.zstash = svc ? 0 : 1, eg.sl2 = (Real)e->sl2;
          eg.zold = (Real *)e->zold, eg.yold = (Real *)e->yold, eg.xold = (Real *)e->xold;
          // cpu_engine.h:226-228: Real lQ = l*Q; ... /(1.0 + lQ)
          eg.lQ1 = (Real)((Real)e->l * (Real)1), eg.lQ2 = (Real)((Real)e->l * (Real)2), eg.lQ3 = (Real)((Real)e->l * (Real)3);
          eg.den1 = 1.0 + (double)eg.lQ1, eg.den2 = 1.0 + (double)eg.lQ2, eg.den3 = 1.0 + (double)eg.lQ3;
          eg.rden1 = 1.0 / eg.den1, eg.rden2 = 1.0 / eg.den2, eg.rden3 = 1.0 / eg.den3;
-         int rc = pf::air_tma_launch<Real>(&e->tma, e->cur, u0, xb, xe, (Real)e->a1, (Real)e->a2, eg, s);
+         int rc = pf::air_tma_launch<Real>(&e->tma, e->cur, u0, xb, xe, (Real)e->a1, (Real)e->a2, eg, svc, s);
          if (rc) return fail(PFFDTD_ECUDA, "tiled air kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
       } else {
          dim3 blk(64, 4, 1);
@@ -707,9 +841,9 @@ struct Step {
          pf::FacesArgs<Real> fa;
          fa.u0 = u0, fa.zold = (const Real *)e->zold, fa.yold = (const Real *)e->yold, fa.xold = (const Real *)e->xold;
          fa.Nx = (int)e->Nx, fa.Ny = (int)e->Ny, fa.Nz = (int)e->Nz, fa.Nzp = (int)e->Nzp, fa.xb = (int)xb, fa.xe = (int)xe;
-         fa.x_lo = e->x_lo_edge, fa.x_hi = e->x_hi_edge;
+         fa.x_lo = e->x_lo_edge, fa.x_hi = e->x_hi_edge, fa.do_z = svc ? 0 : 1;
          fa.lQ1 = (Real)((Real)e->l * (Real)1), fa.lQ2 = (Real)((Real)e->l * (Real)2), fa.lQ3 = (Real)((Real)e->l * (Real)3);
-         const i64 nt = (xe - xb) * e->Ny * 2 + (xe - xb) * 2 * e->Nz + 2 * e->Ny * e->Nz;
+         const i64 nt = (svc ? 0 : (xe - xb) * e->Ny * 2) + (xe - xb) * 2 * e->Nz + 2 * e->Ny * e->Nz;
          if (e->abc_overlap && e->abc_disjoint && !e->comm) {  // one GPU only: with slabs the edge parts order their work around the exchange
             // no boundary or source node lies on the shell: the shell update commutes with the boundary kernels
             CU(cudaEventRecord(e->ev_abc0, s));
@@ -733,10 +867,12 @@ struct Step {
          e->launches += 1;
       }
       if (p.nb > 0) {
+         const i64 *bn = svc ? e->bn_left : e->bn;
+         const uint16_t *adj = svc ? e->adj_left : e->adj;
          if (e->fcc)
-            pf::k_rigid<Real, 12><<<nblk(p.nb, 128), 128, 0, s>>>(u1, u0, e->bn, e->adj, p.b0, p.nb, (Real)e->sl2, (Real)e->a2, e->off);
+            pf::k_rigid<Real, 12><<<nblk(p.nb, 128), 128, 0, s>>>(u1, u0, bn, adj, p.b0, p.nb, (Real)e->sl2, (Real)e->a2, e->off);
          else
-            pf::k_rigid<Real, 6><<<nblk(p.nb, 128), 128, 0, s>>>(u1, u0, e->bn, e->adj, p.b0, p.nb, (Real)e->sl2, (Real)e->a2, e->off);
+            pf::k_rigid<Real, 6><<<nblk(p.nb, 128), 128, 0, s>>>(u1, u0, bn, adj, p.b0, p.nb, (Real)e->sl2, (Real)e->a2, e->off);
          e->launches += 1;
       }
       if (p.nbl > 0) {
@@ -903,7 +1039,9 @@ template <typename Real>
 static int step_impl(pffdtd_engine *e, i64 n) {
    if (n < 0 || n >= e->Nt) return fail(PFFDTD_EINVAL, "step %lld outside [0,%lld)", (long long)n, (long long)e->Nt);
    const bool fused = e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge && !e->energy_on;
-   Step<Real> st{e, (Real *)e->u[e->cur], (Real *)e->u[e->cur ^ 1], e->s_main, n, fused};
+   const bool svc = fused && e->svc_on;
+   Step<Real> st{e, (Real *)e->u[e->cur], (Real *)e->u[e->cur ^ 1], e->s_main, n, fused, svc};
+   const i64 NB = svc ? e->Nb_left : e->Nb, nb_lo = svc ? e->nbL_lo : e->nb_lo, nb_hi = svc ? e->nbL_hi : e->nb_hi;
    Real *u1 = st.u1, *u0 = st.u0;
    cudaStream_t s = e->s_main;
    const i64 Nx = e->Nx;
@@ -936,8 +1074,8 @@ static int step_impl(pffdtd_engine *e, i64 n) {
    const bool split = (lo || hi) && e->overlap && e->sorted && Nx >= 5;
    if (split) {
       // planes the neighbours need first, then the exchange on the comm stream while the interior runs
-      if (lo && (rc = st.part(Part{1, 2, 0, e->nb_lo, 0, e->nbl_lo, 0, e->nba_lo, 0, e->ns_lo, 0, e->np_lo, false}))) return rc;
-      if (hi && (rc = st.part(Part{Nx - 2, Nx - 1, e->Nb - e->nb_hi, e->nb_hi, e->Nbl - e->nbl_hi, e->nbl_hi, e->Nba - e->nba_hi,
+      if (lo && (rc = st.part(Part{1, 2, 0, nb_lo, 0, e->nbl_lo, 0, e->nba_lo, 0, e->ns_lo, 0, e->np_lo, false}))) return rc;
+      if (hi && (rc = st.part(Part{Nx - 2, Nx - 1, NB - nb_hi, nb_hi, e->Nbl - e->nbl_hi, e->nbl_hi, e->Nba - e->nba_hi,
                                    e->nba_hi, e->Ns - e->ns_hi, e->ns_hi, e->np - e->np_hi, e->np_hi, false})))
          return rc;
       CU(cudaGetLastError());
@@ -946,15 +1084,15 @@ static int step_impl(pffdtd_engine *e, i64 n) {
       if ((rc = exchange(e, u0, e->s_comm))) return rc;
       CU(cudaEventRecord(e->ev_comm, e->s_comm));
       e->comm_pending = 1;
-      const i64 b0 = lo ? e->nb_lo : 0, b1 = hi ? e->nb_hi : 0, l0 = lo ? e->nbl_lo : 0, l1 = hi ? e->nbl_hi : 0;
+      const i64 b0 = lo ? nb_lo : 0, b1 = hi ? nb_hi : 0, l0 = lo ? e->nbl_lo : 0, l1 = hi ? e->nbl_hi : 0;
       const i64 a0 = lo ? e->nba_lo : 0, a1 = hi ? e->nba_hi : 0, s0 = lo ? e->ns_lo : 0, s1 = hi ? e->ns_hi : 0;
       const i64 p0 = lo ? e->np_lo : 0, p1 = hi ? e->np_hi : 0;
-      if ((rc = st.part(Part{lo ? 2 : 1, hi ? Nx - 2 : Nx - 1, b0, e->Nb - b0 - b1, l0, e->Nbl - l0 - l1, a0, e->Nba - a0 - a1, s0,
+      if ((rc = st.part(Part{lo ? 2 : 1, hi ? Nx - 2 : Nx - 1, b0, NB - b0 - b1, l0, e->Nbl - l0 - l1, a0, e->Nba - a0 - a1, s0,
                              e->Ns - s0 - s1, p0, e->np - p0 - p1, true})))
          return rc;
       CU(cudaGetLastError());
    } else {
-      if ((rc = st.part(Part{1, Nx - 1, 0, e->Nb, 0, e->Nbl, 0, e->Nba, 0, e->Ns, 0, e->np, true}))) return rc;
+      if ((rc = st.part(Part{1, Nx - 1, 0, NB, 0, e->Nbl, 0, e->Nba, 0, e->Ns, 0, e->np, true}))) return rc;
       CU(cudaGetLastError());
       if ((rc = exchange(e, u0, s))) return rc;
    }

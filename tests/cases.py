@@ -67,7 +67,7 @@ def _open_halo_links(files):
 # cases without golden traces of the reference engine (checked against the oracle only)
 EXTRA_CASES = {
     # more planes than round 1's 96-chunk work plan covered in 16-plane chunks (1536): every x-chunk of the arithmetic plan, the guided tail
-    "cart_long": (dict(Nx=1700, Ny=16, Nz=24, Nt=20, nmat=1, mb=2), "cart"),
+    "cart_long": (dict(Nx=1700, Ny=16, Nz=24, Nt=30, nmat=1, mb=2), "cart"),
     # masked nodes ON the z shell with an open link to the z halo (the vector holding the halo is fully masked in fp64)
     "cart_open_halo": (dict(Nx=20, Ny=19, Nz=22, Nt=40, nmat=1, mb=2, wall_offset=0, _hook=_open_halo_links), "cart"),
 }

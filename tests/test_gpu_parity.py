@@ -14,15 +14,17 @@ pytestmark = pytest.mark.gpu
 
 
 def _kernels(sd):
-    """(air_kernel, fuse): generic kernel; tiled kernel with separate ABC / mirror kernels; tiled kernel with the
-    absorbing shell and the halo mirrors fused in (the default)"""
-    return ((0, 0), (1, 0), (1, 1)) if sd.fcc_flag == 0 else ((0, 0), (1, 0))  # FCC: generic and tiled 13-point kernels
+    """(air_kernel, fuse, svc): generic kernel; tiled kernel with separate ABC / mirror kernels; tiled kernel with the
+    absorbing shell and the halo mirrors fused in, boundary work by the list kernels (round 1's step); the same with the
+    sparse rigid nodes and the shell's z faces done by the air kernel's service warp (the default where the grid allows it)"""
+    return ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 1, 1)) if sd.fcc_flag == 0 else ((0, 0, 0), (1, 0, 0))  # FCC: generic and tiled 13-point kernels
 
 
-def _engine(sd, ak, fuse, cfg=None):
+def _engine(sd, ak, fuse, cfg=None, svc=1):
     e = Engine(sd)
     e.set_option("air_kernel", ak)
     e.set_option("fuse", fuse)
+    e.set_option("svc", svc)  # (also resets the tile configuration to the grid's default)
     if cfg is not None:
         e.set_option("air_cfg", cfg)
     return e
@@ -39,11 +41,11 @@ def test_traces_bit_exact(name, precision):
     sd = make_sim_data(name, precision)
     ref = Oracle(sd).run_all()
     assert np.abs(ref).max() > 0
-    for ak, fuse in _kernels(sd):
-        with _engine(sd, ak, fuse) as e:
+    for ak, fuse, svc in _kernels(sd):
+        with _engine(sd, ak, fuse, svc=svc) as e:
             e.run_steps(0, sd.Nt)
             got = e.read_outputs()
-        assert np.array_equal(got, ref), f"{name} p{precision} air_kernel={ak} fuse={fuse}: max|d|={np.abs(got - ref).max():.3e}"
+        assert np.array_equal(got, ref), f"{name} p{precision} air_kernel={ak} fuse={fuse} svc={svc}: max|d|={np.abs(got - ref).max():.3e}"
 
 
 @pytest.mark.parametrize("precision", (2, 1))
@@ -59,8 +61,10 @@ def test_full_state_bit_exact_from_noise(name, precision):
     o.write_grid(1, g1)
     o.write_grid(0, g0)
     o.run_steps(0, 25)
-    for ak, fuse in _kernels(sd):
-        with _engine(sd, ak, fuse) as e:
+    for ak, fuse, svc in _kernels(sd):
+        with _engine(sd, ak, fuse, svc=svc) as e:
+            if svc and name in ("cart_lossy", "cart_ragged", "cart_long", "cart_nz_a"):
+                assert e.stat("svc") == 1 and e.stat("svc_entries") > 0  # the service warp really is in use on the ordinary rooms
             e.write_grid(1, g1)
             e.write_grid(0, g0)
             e.run_steps(0, 25)
@@ -70,14 +74,15 @@ def test_full_state_bit_exact_from_noise(name, precision):
                     # the outer halo layer is scratch: the fused step mirrors it when a value is written,
                     # the reference before it is read, so only the nodes 1..N-2 are comparable
                     a, b = a[1:-1, 1:-1, 1:-1], b[1:-1, 1:-1, 1:-1]
-                assert np.array_equal(a, b), f"{name} p{precision} ak={ak} fuse={fuse} grid{which}: {np.abs(a - b).max():.3e}"
+                assert np.array_equal(a, b), f"{name} p{precision} ak={ak} fuse={fuse} svc={svc} grid{which}: {np.abs(a - b).max():.3e}"
             v, g = e.read_boundary_state()
             vo, go = o.read_boundary_state()
             assert np.array_equal(v, vo) and np.array_equal(g, go)
 
 
 # tile configurations of the TMA kernel: (id, lanes along z); 0/8/9 = 7-point defaults, 5/10/11 = FCC defaults (air_tma.cuh)
-TILE_CFGS = {"cart": ((0, 32), (8, 16), (9, 8)), "fcc": ((5, 32), (10, 16), (11, 8))}
+# 12/13/14 = the 7-point kernel with the service warp
+TILE_CFGS = {"cart": ((0, 32), (8, 16), (9, 8), (12, 32), (13, 16), (14, 8)), "fcc": ((5, 32), (10, 16), (11, 8))}
 
 
 @pytest.mark.parametrize("precision", (2, 1))
@@ -99,6 +104,8 @@ def test_every_tile_width_gives_the_same_bits(name, precision):
             with _engine(sd, 1, fuse, cfg) as e:
                 if fuse:
                     assert e.stat("fused") == (1 if _fused_expected(sd, lz) else 0)
+                    # the lists exist exactly when the kernel has the warp, the step is fused and no boundary / source node is on the shell
+                    assert e.stat("svc") == (1 if cfg >= 12 and _fused_expected(sd, lz) and e.stat("abc_disjoint") else 0)
                 e.write_grid(1, g1)
                 e.write_grid(0, g0)
                 e.run_steps(0, 25)
@@ -107,6 +114,31 @@ def test_every_tile_width_gives_the_same_bits(name, precision):
                     assert np.array_equal(a, want[1 - which]), f"{name} p{precision} cfg={cfg} fuse={fuse} grid{which}: {np.abs(a - want[1 - which]).max():.3e}"
                 v, g = e.read_boundary_state()
                 assert np.array_equal(v, vo) and np.array_equal(g, go)
+
+
+@pytest.mark.parametrize("precision", (2, 1))
+@pytest.mark.parametrize("cap", (0, 3, 17, 4096))
+def test_service_warp_density_threshold(cap, precision):
+    """svc_cap decides which tile-planes' boundary nodes the air kernel finishes itself: none (only the shell's z faces), a few, all
+    (walls perpendicular to x and y too: dozens of passes per plane) -- same bits every time; a room with solid blocks and three materials"""
+    from cases import OBSTACLE_CASES  # noqa: F401
+    sd = make_sim_data("cart_blobs", precision)
+    g1, g0 = noise_grids(sd)
+    o = Oracle(sd)
+    o.write_grid(1, g1)
+    o.write_grid(0, g0)
+    o.run_steps(0, 25)
+    with Engine(sd) as e:
+        e.set_option("svc_cap", cap)
+        assert e.stat("svc") == 1 and (e.stat("nb_left") == 0) == (cap == 4096) and (cap > 0 or e.stat("nb_left") == sd.Nb)
+        e.write_grid(1, g1)
+        e.write_grid(0, g0)
+        e.run_steps(0, 25)
+        for which in (1, 0):
+            assert np.array_equal(e.read_grid(which)[1:-1, 1:-1, 1:-1], o.read_grid(which)[1:-1, 1:-1, 1:-1])
+        v, g = e.read_boundary_state()
+        vo, go = o.read_boundary_state()
+        assert np.array_equal(v, vo) and np.array_equal(g, go)
 
 
 def test_step_host_matches_run_steps():
