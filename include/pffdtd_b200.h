@@ -94,14 +94,16 @@ int pffdtd_comm_init(pffdtd_engine *e, const void *id128, int rank, int nranks);
  * "overlap" (1 = edge planes first, halo exchange overlapped with the interior [default]),
  * "air_cfg" (tile configuration), "air_xc" (x-chunk length), "profile_air" (CUDA events around every air launch),
  * "manual_halo" (allow stepping a slab without a communicator; the caller moves the halo planes),
- * "use_graph" (1 = replay captured steps as CUDA graphs [default]), "fd_smem" (1 = the branch kernel keeps the material
- * table in shared memory [default]), "abc_overlap" (1 = the absorbing-shell kernel runs beside the boundary kernels when no
+ * "use_graph" (1 = replay captured steps as CUDA graphs [default]), "fd_fixed" (1 = the branch kernel is the compile-time
+ * 11-branch version when every material has 11 branches [default]), "svc" (1 = the air kernel's service warp finishes the sparse
+ * rigid-boundary nodes and the z faces of the absorbing shell from shared memory [default where the grid allows it]), "svc_cap"
+ * (tile-planes with more boundary nodes than this leave them to the list kernel [64]), "abc_overlap" (1 = the absorbing-shell kernel runs beside the boundary kernels when no
  * boundary / source node lies on the shell [default]). */
 int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t value);
 /* Counters/timers: "launches", "steps", "air_ms" / "air_launches_timed" (CUDA-event time of the air launches
  * since reset, with profile_air), "timer_start" / "timer_stop_ms" (device stopwatch on the engine's stream),
  * "fused", "mirror_pairs", "air_kernel", "air_cfg" / "air_lanes_z" (tile configuration in use: 32, 16 or 8 lanes of a warp along z),
- * "abc_disjoint", "Nzp", "energy". */
+ * "abc_disjoint", "Nzp", "energy", "svc" (service-warp lists in use), "svc_entries", "nb_left" (boundary nodes left to k_rigid). */
 int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out);
 int pffdtd_reset_stats(pffdtd_engine *e);
 

@@ -123,6 +123,54 @@ __device__ __forceinline__ void st_vec(Real *p, const Real (&d)[VEC]) {
    *reinterpret_cast<V *>(p) = v;
 }
 
+// ---------------------------------------------------------------- packed fp32 arithmetic (sm_100a: FFMA2 / FADD2)
+// Two fp32 operations per issued instruction.  The air kernels are issue-limited next to their HBM limit (round 1: 84 % of the
+// issue slots busy at 92 % of the copy bandwidth), and 56 of the ~90 instructions of a row-vector were scalar FMUL / FADD.
+// Every operation stays a separately rounded IEEE multiply or add in the reference's order (cpu_engine.h:182-189), element by
+// element, so the bits do not change:
+//  * a product a*b is fma.rn(a, b, nz) with nz = -0.0 (exactly RN(a*b), signed zeros included).  nz comes in as a kernel
+//    argument: ptxas contracts mul.rn.f32x2 / fma(.., -0.0 literal) + add.rn.f32x2 into ONE FFMA2 even under --fmad=false
+//    (verified in SASS), which would round once instead of twice; an addend it cannot see through keeps the two roundings;
+//  * sums are add.rn.f32x2 / sub.rn.f32x2 (FADD2).
+typedef unsigned long long u64;
+struct F4 {
+   u64 lo, hi;  // elements 0,1 and 2,3 of a 16-byte vector
+};
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+   u64 r;
+   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+   return r;
+}
+__device__ __forceinline__ void upk2(u64 p, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p)); }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b, u64 nz) {
+   u64 r;
+   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
+   return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+   u64 r;
+   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+   return r;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+   u64 r;
+   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+   return r;
+}
+__device__ __forceinline__ F4 f4_ld(const float *p) {
+   const float4 v = *reinterpret_cast<const float4 *>(p);
+   return F4{pk2(v.x, v.y), pk2(v.z, v.w)};
+}
+__device__ __forceinline__ F4 f4_ld(const double *) { return F4{0, 0}; }  // (never called: the packed path is fp32 only)
+__device__ __forceinline__ F4 f4_mul(F4 a, u64 c, u64 nz) { return F4{mul2(a.lo, c, nz), mul2(a.hi, c, nz)}; }
+__device__ __forceinline__ F4 f4_add(F4 a, F4 b) { return F4{add2(a.lo, b.lo), add2(a.hi, b.hi)}; }
+__device__ __forceinline__ F4 f4_sub(F4 a, F4 b) { return F4{sub2(a.lo, b.lo), sub2(a.hi, b.hi)}; }
+__device__ __forceinline__ void f4_get(F4 a, float (&d)[4]) {
+   upk2(a.lo, d[0], d[1]);
+   upk2(a.hi, d[2], d[3]);
+}
+__device__ __forceinline__ void f4_get(F4, double (&)[2]) {}
+
 // LZ = lanes of a warp along z (32, 16 or 8); the other 32/LZ = LR lane groups take further rows, so a warp covers
 // LZ vectors x LR*RPT rows.  Narrow tiles cut the padding a grid pays when Nz is not a multiple of 32 vectors.
 template <typename Real, int RPT, int NW, int S, int LZ = 32, bool SVC = false>
@@ -215,6 +263,7 @@ static void air_plan_chunks(AirJob *jb, int n, int xc) {
 template <typename Real>
 struct AirEdge {
    int fuse, x_lo, x_hi, Nx;
+   float negzero;  // -0.0f, opaque to the compiler: the addend that makes fma.rn.f32x2 a multiplication (see "packed fp32 arithmetic")
    int zstash;  // the consumers stash the pre-update values of the shell's z faces for k_abc_faces (0 when the service warp does them)
    Real sl2;    // rigid update: b1 = 2 - sl2*K
    // pre-update values of the shell nodes, for k_abc_faces:
@@ -677,12 +726,21 @@ __global__ void __maxnreg__(MAXR)
          g0.next();
          continue;
       }
+      // PK (fp32): the strip's columns are kept as PRODUCTS, made once when a plane arrives and reused while it is x+1, x and x-1:
+      // qp/qc/qm = a2*u1 of those planes, ac = a1*u1 of plane x.  Otherwise (fp64) um/uc/up hold the raw values.
+      constexpr bool PK = sizeof(Real) == 4;
       Real um[RPT][VEC], uc[RPT][VEC], up[RPT][VEC];
+      F4 qm[RPT], qc[RPT], qp[RPT], ac[RPT];
+      u64 A1 = 0, A2 = 0, NZ = 0;
+      if constexpr (PK) A1 = pk2((float)a1, (float)a1), A2 = pk2((float)a2, (float)a2), NZ = pk2(eg.negzero, eg.negzero);
       Ring gc = g0;  // plane xa-1 (already waited for)
       {
          const Real *s0 = (const Real *)stage(gc) + soff;
 #pragma unroll
-         for (int r = 0; r < RPT; r++) ld_vec<Real, VEC>(s0 + r * BZ, um[r]);
+         for (int r = 0; r < RPT; r++) {
+            if constexpr (PK) qm[r] = f4_mul(f4_ld(s0 + r * BZ), A2, NZ);
+            else ld_vec<Real, VEC>(s0 + r * BZ, um[r]);
+         }
       }
       release(gc);
       gc.next();  // plane xa: the first centre plane
@@ -690,7 +748,14 @@ __global__ void __maxnreg__(MAXR)
       {
          const Real *s1 = (const Real *)stage(gc) + soff;
 #pragma unroll
-         for (int r = 0; r < RPT; r++) ld_vec<Real, VEC>(s1 + r * BZ, uc[r]);
+         for (int r = 0; r < RPT; r++) {
+            if constexpr (PK) {
+               const F4 t = f4_ld(s1 + r * BZ);
+               qc[r] = f4_mul(t, A2, NZ), ac[r] = f4_mul(t, A1, NZ);
+            } else {
+               ld_vec<Real, VEC>(s1 + r * BZ, uc[r]);
+            }
+         }
       }
       Real *u0p = u0g + ((i64)sg.xa * Ny + ybase) * Nzp + zv;
       Real *zop = eg.zold + ((i64)sg.xa * Ny + ybase) * 2;  // stash of the z-shell values of this strip's rows
@@ -709,10 +774,22 @@ __global__ void __maxnreg__(MAXR)
          const Real *sc = (const Real *)stc + soff;
          const Real *su = (const Real *)stage(gu) + soff;
          Real rowm[VEC], rowp[VEC], zl[RPT], zr[RPT];
+         F4 an[RPT], qrm, qrp;  // PK: a1*u1 of plane x+1 (next centre), a2 * the rows next to the strip
 #pragma unroll
-         for (int r = 0; r < RPT; r++) ld_vec<Real, VEC>(su + r * BZ, up[r]);
-         ld_vec<Real, VEC>(sc - BZ, rowm);
-         ld_vec<Real, VEC>(sc + RPT * BZ, rowp);
+         for (int r = 0; r < RPT; r++) {
+            if constexpr (PK) {
+               const F4 t = f4_ld(su + r * BZ);
+               qp[r] = f4_mul(t, A2, NZ), an[r] = f4_mul(t, A1, NZ);
+            } else {
+               ld_vec<Real, VEC>(su + r * BZ, up[r]);
+            }
+         }
+         if constexpr (PK) {
+            qrm = f4_mul(f4_ld(sc - BZ), A2, NZ), qrp = f4_mul(f4_ld(sc + RPT * BZ), A2, NZ);
+         } else {
+            ld_vec<Real, VEC>(sc - BZ, rowm);
+            ld_vec<Real, VEC>(sc + RPT * BZ, rowp);
+         }
 #pragma unroll
          for (int r = 0; r < RPT; r++) {
             zl[r] = sc[r * BZ - 1];
@@ -728,20 +805,40 @@ __global__ void __maxnreg__(MAXR)
                ld_vec<Real, VEC>((const Real *)(stc + u0off) + r * TZ, u0v);
                const uint32_t m = (*(const uint32_t *)(stc + mkoff + r * C::MKW * 4) >> mshift) & VMASK;
                Real o[VEC];
+               if constexpr (PK) {
+                  // (a1*uc - u0) + a2*u[+x] + a2*u[-x] + a2*u[+y] + a2*u[-y] on two element pairs, then + a2*u[+z] + a2*u[-z]
+                  // per element (the z neighbours sit one element over: pairing them would cost more moves than it saves)
+                  F4 P = f4_sub(ac[r], F4{pk2((float)u0v[0], (float)u0v[1]), pk2((float)u0v[2], (float)u0v[3])});
+                  P = f4_add(P, qp[r]);
+                  P = f4_add(P, qm[r]);
+                  P = f4_add(P, (r < RPT - 1) ? qc[r + 1 < RPT ? r + 1 : r] : qrp);
+                  P = f4_add(P, (r > 0) ? qc[r > 0 ? r - 1 : 0] : qrm);
+                  Real pe[VEC], q[VEC];
+                  f4_get(P, pe);
+                  f4_get(qc[r], q);
+                  const Real qzl = O::mul(a2, zl[r]), qzr = O::mul(a2, zr[r]);
 #pragma unroll
-               for (int k = 0; k < VEC; k++) {
-                  const Real yp = (r < RPT - 1) ? uc[r + 1][k] : rowp[k];
-                  const Real ym = (r > 0) ? uc[r - 1][k] : rowm[k];
-                  const Real zp = (k < VEC - 1) ? uc[r][k + 1] : zr[r];
-                  const Real zm = (k > 0) ? uc[r][k - 1] : zl[r];
-                  Real p = O::sub(O::mul(a1, uc[r][k]), u0v[k]);
-                  p = O::add(p, O::mul(a2, up[r][k]));
-                  p = O::add(p, O::mul(a2, um[r][k]));
-                  p = O::add(p, O::mul(a2, yp));
-                  p = O::add(p, O::mul(a2, ym));
-                  p = O::add(p, O::mul(a2, zp));
-                  p = O::add(p, O::mul(a2, zm));
-                  o[k] = ((m >> k) & 1u) ? u0v[k] : p;
+                  for (int k = 0; k < VEC; k++) {
+                     Real p = O::add(pe[k], (k < VEC - 1) ? q[k + 1 < VEC ? k + 1 : k] : qzr);
+                     p = O::add(p, (k > 0) ? q[k > 0 ? k - 1 : 0] : qzl);
+                     o[k] = ((m >> k) & 1u) ? u0v[k] : p;
+                  }
+               } else {
+#pragma unroll
+                  for (int k = 0; k < VEC; k++) {
+                     const Real yp = (r < RPT - 1) ? uc[r + 1][k] : rowp[k];
+                     const Real ym = (r > 0) ? uc[r - 1][k] : rowm[k];
+                     const Real zp = (k < VEC - 1) ? uc[r][k + 1] : zr[r];
+                     const Real zm = (k > 0) ? uc[r][k - 1] : zl[r];
+                     Real p = O::sub(O::mul(a1, uc[r][k]), u0v[k]);
+                     p = O::add(p, O::mul(a2, up[r][k]));
+                     p = O::add(p, O::mul(a2, um[r][k]));
+                     p = O::add(p, O::mul(a2, yp));
+                     p = O::add(p, O::mul(a2, ym));
+                     p = O::add(p, O::mul(a2, zp));
+                     p = O::add(p, O::mul(a2, zm));
+                     o[k] = ((m >> k) & 1u) ? u0v[k] : p;
+                  }
                }
                Real *dst = u0p + (i64)r * Nzp;
                const unsigned rrole = ((yrole >> (3 * r)) & 7u) | xrole;  // uniform within a row group
@@ -812,10 +909,14 @@ __global__ void __maxnreg__(MAXR)
          zop += 2 * Ny;
 #pragma unroll
          for (int r = 0; r < RPT; r++) {
+            if constexpr (PK) {
+               qm[r] = qc[r], qc[r] = qp[r], ac[r] = an[r];
+            } else {
 #pragma unroll
-            for (int k = 0; k < VEC; k++) {
-               um[r][k] = uc[r][k];
-               uc[r][k] = up[r][k];
+               for (int k = 0; k < VEC; k++) {
+                  um[r][k] = uc[r][k];
+                  uc[r][k] = up[r][k];
+               }
             }
          }
       }
@@ -995,14 +1096,11 @@ static int air_tma_launch_cfg(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real
    jb.Ny = (int)t->Ny, jb.Nz = (int)t->Nz, jb.Nzp = (int)t->Nzp;
    jb.plane = t->Ny * t->Nzp;
    jb.ctr = t->ctr;
-   // x-chunk length: 16 planes on grids that give a CTA few items (two extra u1 planes per item: 4 % more traffic), longer on
-   // large grids where 16-plane items would be handed out by the hundred (c5: 64 planes, 1 % extra)
+   // x-chunk length: 16 planes.  Longer chunks save the two extra u1 planes an item loads (4 % of the traffic at 16) but let the
+   // CTAs drift apart along x, and neighbouring tiles stop finding each other's halo rows and columns in L2: measured on B200,
+   // c5 (2046 planes): 16 planes 0.975 of the copy peak, 32: 0.963, 60: 0.945; c4 (fp64 1024^3): 16: 0.976, 60: 0.946.
    {
-      int xc = t->xc;
-      if (xc <= 0) {
-         const i64 per_cta = (i64)jb.n * jb.tiles / std::max(1, t->slots);
-         xc = (int)std::max<i64>(16, std::min<i64>(60, per_cta / 24 / 4 * 4));
-      }
+      int xc = t->xc > 0 ? t->xc : 16;
       if (SVC) xc = std::min(xc, 60);  // the service warp keeps an item's cnt+1 list offsets in two registers per lane
       air_plan_chunks(&jb, jb.n, xc);
    }

@@ -152,7 +152,8 @@ struct pffdtd_engine {
    int rank = 0, nranks = 1, comm_pending = 0;
    // options
    int air_kernel = 1, overlap = 1, profile_air = 0, manual_halo = 0, fuse = 1;
-   int fd_smem = 1;      // k_fd reads the material table from shared memory
+   int fd_fixed = 1;     // k_fd with a compile-time branch count when every material has the same one (11: all shipped materials)
+   int mb_uniform = 0;   // that common branch count, 0 = materials differ
    int abc_overlap = 1;  // the absorbing-shell kernel runs beside the boundary kernels when their node sets are disjoint
    int abc_disjoint = 0, abc_pending = 0;
    cudaStream_t s_abc = nullptr;
@@ -160,6 +161,7 @@ struct pffdtd_engine {
    // in-kernel boundary work (air_tma.cuh AirSvc): per tile-plane lists of the sparse rigid nodes + the shell's z faces, and the
    // dense remainder of the boundary list that stays with k_rigid
    int svc_want = 1, svc_on = 0, svc_cap = 64;
+   float negzero = -0.0f;  // travels as a kernel argument so that the compiler cannot fold it (air_tma.cuh "packed fp32 arithmetic")
    uint32_t *svc_list = nullptr, *svc_off = nullptr;
    i64 *bn_left = nullptr;
    uint16_t *adj_left = nullptr;
@@ -427,6 +429,9 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    }
    for (int k = 0; k < d->Nm; k++)
       if (d->Mb[k] < 0 || d->Mb[k] > PFFDTD_MMB) return fail(PFFDTD_EINVAL, "Mb[%d]=%d out of range", k, d->Mb[k]);
+   e->mb_uniform = d->Nm > 0 ? d->Mb[0] : 0;
+   for (int k = 1; k < d->Nm; k++)
+      if (d->Mb[k] != d->Mb[0]) e->mb_uniform = 0;
 
    const i64 sx = e->Ny * e->Nzp, sy = e->Nzp;
    if (e->fcc == 0) {
@@ -701,8 +706,8 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       int rc = build_service(e);
       if (rc) return rc;
       e->halo_dirty = 1;
-   } else if (k == "fd_smem") {
-      e->fd_smem = value != 0;
+   } else if (k == "fd_fixed") {
+      e->fd_fixed = value != 0;
    } else if (k == "abc_overlap") {
       e->abc_overlap = value != 0;
    } else if (k == "manual_halo") {
@@ -818,7 +823,7 @@ struct Step {
          pf::AirEdge<Real> eg;
          memset(&eg, 0, sizeof eg);
          eg.fuse = fused, eg.x_lo = e->x_lo_edge, eg.x_hi = e->x_hi_edge, eg.Nx = (int)e->Nx;
-         eg.zstash = svc ? 0 : 1, eg.sl2 = (Real)e->sl2;
+         eg.zstash = svc ? 0 : 1, eg.sl2 = (Real)e->sl2, eg.negzero = e->negzero;
          eg.zold = (Real *)e->zold, eg.yold = (Real *)e->yold, eg.xold = (Real *)e->xold;
          // cpu_engine.h:226-228: Real lQ = l*Q; ... /(1.0 + lQ)
          eg.lQ1 = (Real)((Real)e->l * (Real)1), eg.lQ2 = (Real)((Real)e->l * (Real)2), eg.lQ3 = (Real)((Real)e->l * (Real)3);
@@ -877,14 +882,14 @@ struct Step {
       }
       if (p.nbl > 0) {
          const int nq = e->Nm * PFFDTD_MMB * 4;
-         if (e->fd_smem)
-            pf::k_fd<Real, PFFDTD_MMB, true><<<nblk(p.nbl, 128), 128, (size_t)nq * sizeof(Real), s>>>(
-                u0, e->bnl, e->matmb, (const Real *)e->lo2Kbg, (const Real *)e->facb, (Real *)e->hist[0], (Real *)e->hist[1], (Real *)e->vh1,
-                (Real *)e->gh1, p.l0, p.nbl, e->Nblp, (const Real *)e->quads, nq, e->d_n);
-         else
-            pf::k_fd<Real, PFFDTD_MMB, false><<<nblk(p.nbl, 128), 128, 0, s>>>(
-                u0, e->bnl, e->matmb, (const Real *)e->lo2Kbg, (const Real *)e->facb, (Real *)e->hist[0], (Real *)e->hist[1], (Real *)e->vh1,
-                (Real *)e->gh1, p.l0, p.nbl, e->Nblp, (const Real *)e->quads, nq, e->d_n);
+         const size_t sm = (size_t)(nq / 4 * 5) * sizeof(Real);
+#define PF_FD(MB)                                                                                                                        \
+   pf::k_fd<Real, PFFDTD_MMB, MB><<<nblk(p.nbl, 128), 128, sm, s>>>(u0, e->bnl, e->matmb, (const Real *)e->lo2Kbg, (const Real *)e->facb, \
+                                                                    (Real *)e->hist[0], (Real *)e->hist[1], (Real *)e->vh1, (Real *)e->gh1, \
+                                                                    p.l0, p.nbl, e->Nblp, (const Real *)e->quads, nq, e->d_n)
+         if (e->fd_fixed && e->mb_uniform == 11) PF_FD(11);
+         else PF_FD(0);
+#undef PF_FD
          e->launches += 1;
       }
       if (e->abc_pending) {  // join the absorbing-shell kernel running beside the boundary kernels

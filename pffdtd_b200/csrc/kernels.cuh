@@ -219,9 +219,13 @@ __global__ void k_fd_prep(const int8_t *__restrict__ mat_bnl, const Real *__rest
 }
 
 // `Nbl` below is the PITCH of the branch-major state arrays (the node count rounded up to 32 elements, so that a warp's
-// 32 consecutive nodes are one aligned 128-byte line for every branch).  SQ: the material table is staged in shared
-// memory (4*Mb coefficient reads per node become LDS instead of L1 hits).
-template <typename Real, int MMB, bool SQ>
+// 32 consecutive nodes are one aligned 128-byte line for every branch).
+// Round 1's version issued ~1000 instructions per thread and ran issue-limited (56 % issue-active at 4.1 TB/s): twelve of its
+// thirteen IEEE divisions were divisions by 2, every branch carried a predicate for "m < Mb", and the doubled coefficients
+// were recomputed per node.  Here: x/2 is x*0.5 (the same correctly rounded value), the block stages (2*bDh, bFh, b, bd, 2*bFh)
+// per (material, branch) in shared memory once (2*x is exact), and MB > 0 fixes the branch count at compile time for problems
+// whose materials all have MB branches (every shipped material has 11); MB = 0 keeps the per-node count.
+template <typename Real, int MMB, int MB>
 __global__ void __launch_bounds__(128) k_fd(Real *__restrict__ u0, const i64 *__restrict__ bnl, const uint16_t *__restrict__ matmb,
                                             const Real *__restrict__ lo2Kbg_bnl, const Real *__restrict__ fac_bnl,
                                             Real *__restrict__ hist0, Real *__restrict__ hist1, Real *__restrict__ vh1,
@@ -229,27 +233,30 @@ __global__ void __launch_bounds__(128) k_fd(Real *__restrict__ u0, const i64 *__
                                             const i64 *__restrict__ d_n) {
    typedef Ops<Real> O;
    extern __shared__ __align__(16) unsigned char fd_smem[];
-   if (SQ) {
-      Real *qs = reinterpret_cast<Real *>(fd_smem);
-      for (int t = threadIdx.x; t < nquads; t += blockDim.x) qs[t] = quads[t];
-      __syncthreads();
+   Real *qs = reinterpret_cast<Real *>(fd_smem);  // [Nm][MMB][5] = 2*bDh, bFh, b, bd, 2*bFh
+   const Real one = (Real)1.0, two = (Real)2.0, half = (Real)0.5;
+   for (int t = threadIdx.x; t < nquads / 4; t += blockDim.x) {
+      const Real b = quads[4 * t + 0], bd = quads[4 * t + 1], bDh = quads[4 * t + 2], bFh = quads[4 * t + 3];
+      qs[5 * t + 0] = O::mul(two, bDh), qs[5 * t + 1] = bFh, qs[5 * t + 2] = b, qs[5 * t + 3] = bd, qs[5 * t + 4] = O::mul(two, bFh);
    }
+   __syncthreads();
    const i64 i = i0 + n - 1 - ((i64)blockIdx.x * blockDim.x + threadIdx.x);  // descending, see k_rigid
    if (i < i0) return;
-   const Real one = (Real)1.0, two = (Real)2.0;
    Real *hist = (*d_n & 1) ? hist1 : hist0;  // the value two steps back lives in the buffer of the step's parity
    const unsigned mm = matmb[i];
-   const int Mb = (int)(mm >> 8);
-   const Real *q = (SQ ? reinterpret_cast<const Real *>(fd_smem) : quads) + (i64)(mm & 0xffu) * MMB * 4;
+   const int Mb = MB > 0 ? MB : (int)(mm >> 8);
+   const Real *q = qs + (mm & 0xffu) * (MMB * 5);
    // everything this node needs from memory is requested up front; the dependent gather (index -> u0) first
    const i64 c = bnl[i];
    const Real u0c = u0[c];
-   Real v1[MMB], g1[MMB];
+   constexpr int NB = MB > 0 ? MB : MMB;
+   Real v1[NB], g1[NB];
+   Real *pv = vh1 + i, *pg = gh1 + i;
 #pragma unroll
-   for (int m = 0; m < MMB; m++) {
-      if (m < Mb) {
-         v1[m] = vh1[(i64)m * Nbl + i];
-         g1[m] = gh1[(i64)m * Nbl + i];
+   for (int m = 0; m < NB; m++) {
+      if (MB > 0 || m < Mb) {
+         v1[m] = pv[(i64)m * Nbl];
+         g1[m] = pg[(i64)m * Nbl];
       }
    }
    const Real lo2Kbg = lo2Kbg_bnl[i], fac = fac_bnl[i];
@@ -257,22 +264,18 @@ __global__ void __launch_bounds__(128) k_fd(Real *__restrict__ u0, const i64 *__
    const Real den = O::add(one, lo2Kbg);
    Real u = O::div(O::add(u0c, O::mul(lo2Kbg, u2)), den);
 #pragma unroll
-   for (int m = 0; m < MMB; m++) {
-      if (m < Mb) {
-         const Real bDh = q[4 * m + 2], bFh = q[4 * m + 3];
-         u = O::sub(u, O::mul(fac, O::sub(O::mul(O::mul(two, bDh), v1[m]), O::mul(bFh, g1[m]))));
-      }
+   for (int m = 0; m < NB; m++) {
+      if (MB > 0 || m < Mb) u = O::sub(u, O::mul(fac, O::sub(O::mul(q[5 * m + 0], v1[m]), O::mul(q[5 * m + 1], g1[m]))));
    }
    const Real du = O::sub(u, u2);
    hist[i] = u;
    u0[c] = u;
 #pragma unroll
-   for (int m = 0; m < MMB; m++) {
-      if (m < Mb) {
-         const Real b = q[4 * m + 0], bd = q[4 * m + 1], bFh = q[4 * m + 3];
-         const Real v0 = O::sub(O::add(O::mul(b, du), O::mul(bd, v1[m])), O::mul(O::mul(two, bFh), g1[m]));
-         gh1[(i64)m * Nbl + i] = O::add(g1[m], O::div(O::add(v0, v1[m]), two));
-         vh1[(i64)m * Nbl + i] = v0;
+   for (int m = 0; m < NB; m++) {
+      if (MB > 0 || m < Mb) {
+         const Real v0 = O::sub(O::add(O::mul(q[5 * m + 2], du), O::mul(q[5 * m + 3], v1[m])), O::mul(q[5 * m + 4], g1[m]));
+         pg[(i64)m * Nbl] = O::add(g1[m], O::mul(O::add(v0, v1[m]), half));
+         pv[(i64)m * Nbl] = v0;
       }
    }
 }

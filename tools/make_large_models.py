@@ -5,7 +5,8 @@ UNMODIFIED reference tool chain (python/sim_setup.py) under the shims of tests/r
 tests/test_large_models.py runs them through the CUDA engine and the unmodified reference CPU engine.
 
     python tools/make_large_models.py ctk [h] [duration]        (build container only: needs /root/reference)
-    python tools/make_large_models.py mv  [h] [duration]
+    python tools/make_large_models.py mv  [h] [duration] [folder name under data_large/]
+    python tools/make_large_models.py mv 0.03 0.01 mv_fcc_gpu_big        (bench workload "mv_big": about 3e8 stored nodes)
 """
 import os
 import sys
@@ -68,7 +69,7 @@ def main():
         R.rotate_sim_data(tmp / "gpu")
         R.fold_fcc_sim_data(tmp / "gpu")
         R.sort_sim_data(tmp / "gpu")
-        name = "mv_fcc_gpu"
+        name = sys.argv[4] if len(sys.argv) > 4 else "mv_fcc_gpu"
     files = folder_prep.load_folder(tmp / "gpu")
     dst = ROOT / "data_large" / name
     dst.mkdir(parents=True, exist_ok=True)
