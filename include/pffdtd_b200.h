@@ -94,10 +94,9 @@ int pffdtd_comm_init(pffdtd_engine *e, const void *id128, int rank, int nranks);
  * "overlap" (1 = edge planes first, halo exchange overlapped with the interior [default]),
  * "air_cfg" (tile configuration), "air_xc" (x-chunk length), "profile_air" (CUDA events around every air launch),
  * "manual_halo" (allow stepping a slab without a communicator; the caller moves the halo planes),
- * "use_graph" (1 = replay captured steps as CUDA graphs [default]), "fd_fixed" (1 = the branch kernel is the compile-time
- * 11-branch version when every material has 11 branches [default]), "svc" (1 = the air kernel's service warp finishes the sparse
+ * "use_graph" (1 = replay captured steps as CUDA graphs [default]), "svc" (1 = the air kernel's service warp finishes the sparse
  * rigid-boundary nodes and the z faces of the absorbing shell from shared memory [default where the grid allows it]), "svc_cap"
- * (tile-planes with more boundary nodes than this leave them to the list kernel [64]), "abc_overlap" (1 = the absorbing-shell kernel runs beside the boundary kernels when no
+ * (tile-planes with more boundary nodes than this leave them to the list kernel [64, at most 192 minus two per tile row]), "abc_overlap" (1 = the absorbing-shell kernel runs beside the boundary kernels when no
  * boundary / source node lies on the shell [default]). */
 int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t value);
 /* Counters/timers: "launches", "steps", "air_ms" / "air_launches_timed" (CUDA-event time of the air launches
@@ -163,6 +162,28 @@ int64_t pffdtd_air_chunk_plan(int64_t n_planes, int xc, int64_t *bounds, int64_t
 /* Whole-run convenience with the reference's run_sim() shape: create, run Nt steps, write
  * u_out[Nr*Nt], destroy; returns elapsed seconds of the loop through *elapsed_s. */
 int pffdtd_run_sim(const pffdtd_desc *desc, int device, double *u_out, double *elapsed_s);
+
+/* ---- Multi-GPU from ONE host thread, the reference's own model: run_sim counts the visible devices (gpu_engine.h:679-691;
+ * CUDA_VISIBLE_DEVICES selects them), split_data cuts the grid into x-slabs (:516-662), the step loop walks the devices (:994) and
+ * the halo planes move by peer copies (:1086-1126).  Here: one engine per slab, the edge planes of a slab are computed first and pushed
+ * into the neighbours' halo planes (cudaMemcpyPeerAsync over NVLink) on a second stream while the interior runs; the neighbour's next
+ * step waits on an event -- no host synchronisation in the loop.  `desc` describes the WHOLE grid with sorted node lists (what the
+ * reference requires of a multi-GPU folder, :497-513).  nslabs <= 0: one slab per visible device.  devices = NULL: slab r on device
+ * r % visible (several slabs may share a device).  balance != 0: slabs of about equal cost (air nodes + weighted boundary / lossy /
+ * shell nodes per plane) instead of the reference's equal-plane split; the results are the same bits either way. */
+typedef struct pffdtd_multi pffdtd_multi; /* opaque */
+int pffdtd_multi_create(const pffdtd_desc *desc, int nslabs, const int *devices, int balance, pffdtd_multi **out);
+int pffdtd_multi_destroy(pffdtd_multi *m);
+/* number of slabs; planes[r] = owned planes of slab r (up to `max` entries) */
+int pffdtd_multi_slabs(pffdtd_multi *m, int64_t *planes, int max);
+/* the engine of one slab, for pffdtd_set_option / pffdtd_get_stat / pffdtd_read_grid (do not step or destroy it directly) */
+int pffdtd_multi_engine(pffdtd_multi *m, int slab, pffdtd_engine **e);
+int pffdtd_multi_run_steps(pffdtd_multi *m, int64_t nstart, int64_t nsteps);
+int pffdtd_multi_sync(pffdtd_multi *m);
+/* receiver traces of the whole grid, sorted receiver order (rows of the slabs in slab order): u_out[nr*(n1-n0) + (n-n0)] */
+int pffdtd_multi_read_outputs(pffdtd_multi *m, int64_t n0, int64_t n1, double *u_out);
+/* run_sim() over every visible device (nslabs <= 0) or `nslabs` slabs: create, run Nt steps, write u_out[Nr*Nt], destroy */
+int pffdtd_run_sim_multi(const pffdtd_desc *desc, int nslabs, const int *devices, double *u_out, double *elapsed_s);
 
 #ifdef __cplusplus
 }

@@ -43,7 +43,7 @@ double run_sim(const struct SimData *sd) {
    d.Nb = sd->Nb, d.Nbl = sd->Nbl, d.Nba = sd->Nba, d.Ns = sd->Ns, d.Nr = sd->Nr, d.Nt = sd->Nt;
    d.l = sd->l, d.l2 = sd->l2;
    d.a1 = (double)sd->a1, d.a2 = (double)sd->a2, d.sl2 = (double)sd->sl2, d.lo2 = (double)sd->lo2;
-   d.ix0 = 0, d.x_lo_edge = 1, d.x_hi_edge = 1; /* the whole grid on one device */
+   d.ix0 = 0, d.x_lo_edge = 1, d.x_hi_edge = 1; /* the whole grid; the library cuts it into one slab per visible device */
    d.bn_ixyz = sd->bn_ixyz, d.adj_bn = sd->adj_bn;
    d.bnl_ixyz = sd->bnl_ixyz, d.mat_bnl = sd->mat_bnl;
    d.bna_ixyz = sd->bna_ixyz, d.Q_bna = sd->Q_bna;
@@ -56,7 +56,9 @@ double run_sim(const struct SimData *sd) {
    d.ssaf_bnl = ssaf, d.mat_beta = beta, d.mat_quads = quads;
    double seconds = 0.0;
    /* u_out comes back in the engine's receiver order, like the other engines'; write_outputs applies out_reorder */
-   if (pffdtd_run_sim(&d, /*device*/ 0, sd->u_out, &seconds) != PFFDTD_OK) {
+   /* nslabs = 0: every device CUDA_VISIBLE_DEVICES shows, like the reference's own GPU engine (gpu_engine.h:679-691); more than one
+    * device needs the sorted "gpu folder" the reference needs too (gpu_engine.h:497-513) */
+   if (pffdtd_run_sim_multi(&d, /*nslabs*/ 0, /*devices*/ NULL, sd->u_out, &seconds) != PFFDTD_OK) {
       fprintf(stderr, "b200 engine: %s\n", pffdtd_last_error());
       exit(EXIT_FAILURE); /* the reference's error convention (gpu_engine.h:192-200) */
    }

@@ -47,6 +47,7 @@ struct AirSvc {
    int pitch;             // Nx + 1
 };
 #define PF_SVC_NONE 0xE000u
+#define PF_SVC_CAP 192  // most entries of one tile-plane (a stage holds them; segments are padded to 4 entries = 16 bytes)
 
 struct AirTma {
    bool ok = false;
@@ -92,6 +93,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
           : "r"(a), "r"(parity)
           : "memory");
    } while (!ok);
+}
+// plain bulk copy global -> shared, completing on the same mbarrier as the stage's tensor loads (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                "r"(bytes), "r"(smem_u32(bar))
+                : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
    asm volatile(
@@ -187,8 +194,11 @@ struct AirCfg {
    static constexpr int MK_BYTES = TY * MKW * 4;
    static constexpr int U0_OFF = (U1_BYTES + 127) / 128 * 128;
    static constexpr int MK_OFF = U0_OFF + U0_BYTES;
-   static constexpr int STAGE_PITCH = (MK_OFF + MK_BYTES + 127) / 128 * 128;
-   static constexpr int SMEM_BYTES = S * STAGE_PITCH + 3 * S * 8 + S * 16 + 128;  // stages, full/empty/patched barriers, item headers
+   static constexpr int SV_CAP = 192;       // (SVC) most list entries of one tile-plane (PF_SVC_CAP: the engine's builder keeps to it)
+   static constexpr int SV_OFF = (MK_OFF + MK_BYTES + 15) / 16 * 16;
+   static constexpr int STAGE_PITCH = (SV_OFF + (SVC ? SV_CAP * 4 : 0) + 127) / 128 * 128;
+   // stages, full/empty/patched barriers, item headers, entry counts
+   static constexpr int SMEM_BYTES = S * STAGE_PITCH + 3 * S * 8 + S * 16 + S * 4 + 128;
    static constexpr int THREADS = (NW + 1 + (SVC ? 1 : 0)) * 32;  // NW consumer warps + 1 TMA producer warp (+ 1 service warp)
 };
 
@@ -402,6 +412,7 @@ __global__ void __maxnreg__(MAXR)
    uint64_t *patched = empty + S;  // (SVC) flips when the service warp is done with the load in stage s
 
    int4 *hdr = (int4 *)(patched + S);  // per stage: the item (xa, cnt, z0, y0) whose first plane it holds; cnt < 0 = stop
+   int *nent = (int *)(hdr + S);       // (SVC) per stage: list entries that came with the centre plane
 
    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
    const int lz = lane % LZ;                     // this thread's vector within its row
@@ -419,38 +430,61 @@ __global__ void __maxnreg__(MAXR)
    __syncthreads();
 
    if (w == NW) {
-      // ---------------- producer: fetch items, stream their planes
-      if (lane == 0) {
-         int s = 0;
-         uint32_t ph = 1u;  // parity of the "previous round released" phase; the first round needs no wait
-         bool first = true;
-         for (;;) {
-            const int item = atomicAdd(&jb.ctr[0], 1);
-            const bool stop = item >= jb.n_items;
-            AirSeg sg = {0, -1, 0, 0};
-            if (!stop) sg = air_item<C::TZ, C::TY>(jb, item);
-            const int nq = stop ? 1 : sg.cnt + 2;  // planes xa-1 .. xa+cnt, or the stop marker
-            for (int q = 0; q < nq; q++) {
+      // ---------------- producer: fetch items, stream their planes (lane 0 issues; with SVC the whole warp holds the item's list
+      // offsets, one or two per lane, and the plane's list entries travel into the stage with a bulk copy on the same barrier)
+      int s = 0;
+      uint32_t ph = 1u;  // parity of the "previous round released" phase; the first round needs no wait
+      bool first = true;
+      for (;;) {
+         int item = 0;
+         if (lane == 0) item = atomicAdd(&jb.ctr[0], 1);
+         item = __shfl_sync(0xffffffffu, item, 0);
+         const bool stop = item >= jb.n_items;
+         AirSeg sg = {0, -1, 0, 0};
+         if (!stop) sg = air_item<C::TZ, C::TY>(jb, item);
+         const int nq = stop ? 1 : sg.cnt + 2;  // planes xa-1 .. xa+cnt, or the stop marker
+         uint32_t o0 = 0u, o1 = 0u;
+         const bool lists = SVC && sv.list != nullptr && !stop;
+         if (lists) {
+            const int tile = ((sg.y0 - 1) / C::TY) * jb.tz + sg.z0 / C::TZ;
+            const uint32_t *ob = sv.off + (size_t)tile * sv.pitch + sg.xa;  // ob[j], ob[j+1]: entries of plane xa + j
+            o0 = lane <= sg.cnt ? ob[lane] : 0u, o1 = lane + 32 <= sg.cnt ? ob[lane + 32] : 0u;
+         }
+         for (int q = 0; q < nq; q++) {
+            const bool centre = !stop && q >= 1 && q <= sg.cnt;
+            uint32_t eb = 0u, ee = 0u;
+            if (SVC) {  // (warp-uniform: every lane takes part in the shuffles)
+               const int j = centre ? q - 1 : 0;
+               const uint32_t a0 = __shfl_sync(0xffffffffu, o0, j & 31), a1 = __shfl_sync(0xffffffffu, o1, j & 31);
+               const uint32_t b0 = __shfl_sync(0xffffffffu, o0, (j + 1) & 31), b1 = __shfl_sync(0xffffffffu, o1, (j + 1) & 31);
+               eb = j < 32 ? a0 : a1, ee = j + 1 < 32 ? b0 : b1;
+               if (!centre || !lists) eb = ee = 0u;
+            }
+            if (lane == 0) {
                unsigned char *st = smem + s * C::STAGE_PITCH;
                if (!first) mbar_wait(&empty[s], ph);
                if (q == 0) hdr[s] = make_int4(sg.xa, sg.cnt, sg.z0, sg.y0);
                if (stop) {
                   mbar_arrive(&full[s]);
                } else {
-                  const bool centre = q >= 1 && q <= sg.cnt;
-                  mbar_expect_tx(&full[s], centre ? C::U1_BYTES + C::U0_BYTES + C::MK_BYTES : C::U1_BYTES);
+                  const uint32_t lbytes = (ee - eb) * 4u;  // segments start and end on multiples of 4 entries
+                  if (SVC) nent[s] = (int)(ee - eb);
+                  mbar_expect_tx(&full[s], (centre ? C::U1_BYTES + C::U0_BYTES + C::MK_BYTES : C::U1_BYTES) + lbytes);
                   const int x = sg.xa - 1 + q;
                   tma_load_3d(st, &map_u1, &full[s], sg.z0 - VEC, sg.y0 - 1, x);
                   if (centre) {
                      tma_load_3d(st + C::U0_OFF, &map_u0, &full[s], sg.z0, sg.y0, x);
                      tma_load_3d(st + C::MK_OFF, &map_mk, &full[s], (sg.z0 >> 7) << 2, sg.y0, x);  // box start must be 16-byte aligned
+                     if (lbytes) bulk_load(st + C::SV_OFF, sv.list + eb, lbytes, &full[s]);
                   }
                }
-               if (++s == S) s = 0, ph ^= 1u, first = false;
             }
-            if (stop) break;
+            if (++s == S) s = 0, ph ^= 1u, first = false;
          }
-         // the last CTA out re-arms the counters for the next launch
+         if (stop) break;
+      }
+      // the last CTA out re-arms the counters for the next launch
+      if (lane == 0) {
          __threadfence();
          if (atomicAdd(&jb.ctr[1], 1) == (int)gridDim.x - 1) {
             jb.ctr[0] = 0;
@@ -488,18 +522,6 @@ __global__ void __maxnreg__(MAXR)
             const int4 h = hdr[g0.s];
             if (h.y < 0) break;
             const int cnt = h.y;
-            const int tile = ((h.w - 1) / C::TY) * jb.tz + h.z / C::TZ;
-            const uint32_t *ob = sv.off + (size_t)tile * sv.pitch + h.x;  // ob[j], ob[j+1]: entries of plane xa + j
-            const bool have = sv.list != nullptr;  // no list (unfused step, energy mode): the warp only keeps the barriers moving
-            const uint32_t o0 = have && lane <= cnt ? ob[lane] : 0u, o1 = have && lane + 32 <= cnt ? ob[lane + 32] : 0u;
-            auto off_at = [&](int j) {
-               const uint32_t a = __shfl_sync(0xffffffffu, o0, j & 31), b = __shfl_sync(0xffffffffu, o1, j & 31);
-               return j < 32 ? a : b;
-            };
-            // the first two passes of a plane are fetched one plane ahead (a dependent global load per plane would make this warp the
-            // pacemaker of the CTA)
-            uint32_t b0 = off_at(0), e0 = off_at(1);
-            uint32_t n0 = b0 + lane < e0 ? sv.list[b0 + lane] : PF_SVC_NONE, n1 = b0 + 32 + lane < e0 ? sv.list[b0 + 32 + lane] : PF_SVC_NONE;
             done(&patched[g0.s]);
             R2 gm = g0, gc = g0;
             gc.next();
@@ -508,20 +530,15 @@ __global__ void __maxnreg__(MAXR)
                R2 gu = gc;
                gu.next();
                mbar_wait(&full[gu.s], gu.ph);
-               const uint32_t b = b0, e = e0;
-               const uint32_t c0 = n0, c1 = n1;
-               if (j + 1 < cnt) {
-                  b0 = e0, e0 = off_at(j + 2);
-                  n0 = b0 + lane < e0 ? sv.list[b0 + lane] : PF_SVC_NONE;
-                  n1 = b0 + 32 + lane < e0 ? sv.list[b0 + 32 + lane] : PF_SVC_NONE;
-               }
+               const int ne = nent[gc.s];  // the plane's entries came into its stage with the plane (no global load in this warp)
                unsigned char *stc = smem + gc.s * C::STAGE_PITCH;
                const Real *sc = (const Real *)stc, *sm = (const Real *)(smem + gm.s * C::STAGE_PITCH),
                           *su = (const Real *)(smem + gu.s * C::STAGE_PITCH);
                Real *u0s = (Real *)(stc + C::U0_OFF);
                uint32_t *mks = (uint32_t *)(stc + C::MK_OFF);
-               for (uint32_t i = b; i < e; i += 32) {
-                  const uint32_t ent = i == b ? c0 : (i == b + 32 ? c1 : (i + lane < e ? sv.list[i + lane] : PF_SVC_NONE));
+               const uint32_t *ents = (const uint32_t *)(stc + C::SV_OFF);
+               for (int i = lane; i < ne; i += 32) {
+                  const uint32_t ent = ents[i];
                   const unsigned kind = (ent >> 13) & 7u;
                   if (kind < 2u) {
                      const int c = (int)(ent & 127u), r = (int)((ent >> 7) & 63u);
@@ -638,6 +655,110 @@ __global__ void __maxnreg__(MAXR)
             const Real t = __shfl_down_sync(0xffffffffu, v[0], 1);
             return lz == LZ - 1 ? e : t;
          };
+         if constexpr (sizeof(Real) == 4) {
+            // ---- packed fp32 version (see "packed fp32 arithmetic"): the nine rows are kept as PRODUCTS a2*u1, made once when a plane
+            // arrives (3 row vectors per plane) instead of 12 times per node; the four same-column terms of each half of the sum
+            // are FADD2s on element pairs, the eight z-shifted terms stay per element (their neighbours sit one element over).
+            // 54 floating-point instructions per row-vector instead of 104; the order of the sum is the reference's.
+            const u64 A1 = pk2((float)a1, (float)a1), A2 = pk2((float)a2, (float)a2), NZ = pk2(eg.negzero, eg.negzero);
+            Ring gm = g0;  // plane x-1
+            Ring gc = g0;  // plane x
+            gc.next();
+            wait_full(gc);
+            F4 qm0[RPT], qm1[RPT], qm2[RPT], qc0[RPT], qc1[RPT], qc2[RPT], ac1[RPT];
+            {
+               const Real *sm = (const Real *)stage(gm) + soff;
+               const Real *sc = (const Real *)stage(gc) + soff;
+#pragma unroll
+               for (int r = 0; r < RPT; r++) {
+                  qm0[r] = f4_mul(f4_ld(sm + (r - 1) * BZ), A2, NZ);
+                  qm1[r] = f4_mul(f4_ld(sm + r * BZ), A2, NZ);
+                  qm2[r] = f4_mul(f4_ld(sm + (r + 1) * BZ), A2, NZ);
+                  qc0[r] = f4_mul(f4_ld(sc + (r - 1) * BZ), A2, NZ);
+                  const F4 t = f4_ld(sc + r * BZ);
+                  qc1[r] = f4_mul(t, A2, NZ), ac1[r] = f4_mul(t, A1, NZ);
+                  qc2[r] = f4_mul(f4_ld(sc + (r + 1) * BZ), A2, NZ);
+               }
+            }
+            Real *u0p = u0g + ((i64)sg.xa * Ny + ybase) * Nzp + zv;
+            for (int j = 0; j < sg.cnt; j++) {
+               Ring gu = gc;  // plane x+1
+               gu.next();
+               wait_full(gu);
+               wait_patched(gc);
+               const unsigned char *stc = stage(gc);
+               const Real *sm = (const Real *)stage(gm) + soff;
+               const Real *sc = (const Real *)stc + soff;
+               const Real *su = (const Real *)stage(gu) + soff;
+#pragma unroll
+               for (int r = 0; r < RPT; r++) {
+                  const F4 t1 = f4_ld(su + r * BZ);
+                  const F4 qp0 = f4_mul(f4_ld(su + (r - 1) * BZ), A2, NZ), qp1 = f4_mul(t1, A2, NZ),
+                           qp2 = f4_mul(f4_ld(su + (r + 1) * BZ), A2, NZ), an1 = f4_mul(t1, A1, NZ);
+                  // products of the out-of-row z neighbours (edge lanes; the others get theirs by shuffle)
+                  Real em1 = (Real)0, ec0 = (Real)0, ec2 = (Real)0, ep1 = (Real)0;
+                  if (edge_lane) {
+                     em1 = sm[r * BZ + eoff];
+                     ec0 = sc[(r - 1) * BZ + eoff];
+                     ec2 = sc[(r + 1) * BZ + eoff];
+                     ep1 = su[r * BZ + eoff];
+                  }
+                  em1 = O::mul(a2, em1), ec0 = O::mul(a2, ec0), ec2 = O::mul(a2, ec2), ep1 = O::mul(a2, ep1);
+                  Real m1[VEC], c0[VEC], c2[VEC], p1[VEC];
+                  f4_get(qm1[r], m1);
+                  f4_get(qc0[r], c0);
+                  f4_get(qc2[r], c2);
+                  f4_get(qp1, p1);
+                  const Real m1l = zleft(m1, em1), m1r = zright(m1, em1);
+                  const Real c0l = zleft(c0, ec0), c0r = zright(c0, ec0);
+                  const Real c2l = zleft(c2, ec2), c2r = zright(c2, ec2);
+                  const Real p1l = zleft(p1, ep1), p1r = zright(p1, ep1);
+                  Real u0v[VEC];
+                  ld_vec<Real, VEC>((const Real *)(stc + u0off) + r * TZ, u0v);
+                  const uint32_t m = (*(const uint32_t *)(stc + mkoff + r * C::MKW * 4) >> mshift) & VMASK;
+                  F4 P = f4_sub(ac1[r], F4{pk2((float)u0v[0], (float)u0v[1]), pk2((float)u0v[2], (float)u0v[3])});
+                  P = f4_add(P, qp2);     // +x +y
+                  P = f4_add(P, qm0[r]);  // -x -y
+                  Real pe[VEC];
+                  f4_get(P, pe);
+#pragma unroll
+                  for (int k = 0; k < VEC; k++) {
+                     Real p = pe[k];
+                     p = O::add(p, (k < VEC - 1) ? c2[k + 1 < VEC ? k + 1 : k] : c2r);  // +y +z
+                     p = O::add(p, (k > 0) ? c0[k > 0 ? k - 1 : 0] : c0l);              // -y -z
+                     p = O::add(p, (k < VEC - 1) ? p1[k + 1 < VEC ? k + 1 : k] : p1r);  // +x +z
+                     p = O::add(p, (k > 0) ? m1[k > 0 ? k - 1 : 0] : m1l);              // -x -z
+                     pe[k] = p;
+                  }
+                  P = F4{pk2((float)pe[0], (float)pe[1]), pk2((float)pe[2], (float)pe[3])};
+                  P = f4_add(P, qp0);     // +x -y
+                  P = f4_add(P, qm2[r]);  // -x +y
+                  f4_get(P, pe);
+                  Real o[VEC];
+#pragma unroll
+                  for (int k = 0; k < VEC; k++) {
+                     Real p = pe[k];
+                     p = O::add(p, (k > 0) ? c2[k > 0 ? k - 1 : 0] : c2l);              // +y -z
+                     p = O::add(p, (k < VEC - 1) ? c0[k + 1 < VEC ? k + 1 : k] : c0r);  // -y +z
+                     p = O::add(p, (k > 0) ? p1[k > 0 ? k - 1 : 0] : p1l);              // +x -z
+                     p = O::add(p, (k < VEC - 1) ? m1[k + 1 < VEC ? k + 1 : k] : m1r);  // -x +z
+                     o[k] = ((m >> k) & 1u) ? u0v[k] : p;
+                  }
+                  if (r < nrow && (SVC || m != VMASK)) st_vec<Real, VEC>(u0p + (i64)r * Nzp, o);
+                  qm0[r] = qc0[r], qm1[r] = qc1[r], qm2[r] = qc2[r];
+                  qc0[r] = qp0, qc1[r] = qp1, qc2[r] = qp2, ac1[r] = an1;
+               }
+               release(gm);
+               gm = gc;
+               gc = gu;
+               u0p += jb.plane;
+            }
+            release(gm);  // the two planes still held: the last centre plane and the last "x+1" plane
+            release(gc);
+            g0 = gc;
+            g0.next();
+            continue;
+         }
          Ring gm = g0;  // plane x-1
          Ring gc = g0;  // plane x
          gc.next();

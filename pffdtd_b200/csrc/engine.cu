@@ -13,6 +13,7 @@
 #include <vector>
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <dlfcn.h>
 #include <cuda_runtime.h>
 
@@ -147,13 +148,16 @@ struct pffdtd_engine {
    // streams / events
    cudaStream_t s_main = nullptr, s_comm = nullptr;
    cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_step = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+   cudaEvent_t ev_push = nullptr;  // (single-process slabs) this slab's edge planes have landed in the neighbours' halos
+   i64 first_step = 0;             // first step of the current pffdtd_multi_run_steps batch (no neighbour event to wait for before it)
    // comm
    void *comm = nullptr;
    int rank = 0, nranks = 1, comm_pending = 0;
+   // single-process multi-GPU (pffdtd_multi_*): the engines of the neighbouring slabs; halo planes are pushed into their grids
+   // with peer copies instead of NCCL send/recv
+   pffdtd_engine *peer_lo = nullptr, *peer_hi = nullptr;
    // options
    int air_kernel = 1, overlap = 1, profile_air = 0, manual_halo = 0, fuse = 1;
-   int fd_fixed = 1;     // k_fd with a compile-time branch count when every material has the same one (11: all shipped materials)
-   int mb_uniform = 0;   // that common branch count, 0 = materials differ
    int abc_overlap = 1;  // the absorbing-shell kernel runs beside the boundary kernels when their node sets are disjoint
    int abc_disjoint = 0, abc_pending = 0;
    cudaStream_t s_abc = nullptr;
@@ -288,6 +292,7 @@ extern "C" int pffdtd_destroy(pffdtd_engine *e) {
    if (e->ev_edge) cudaEventDestroy(e->ev_edge);
    if (e->ev_comm) cudaEventDestroy(e->ev_comm);
    if (e->ev_step) cudaEventDestroy(e->ev_step);
+   if (e->ev_push) cudaEventDestroy(e->ev_push);
    if (e->ev_t0) cudaEventDestroy(e->ev_t0);
    if (e->ev_t1) cudaEventDestroy(e->ev_t1);
    if (e->s_main) cudaStreamDestroy(e->s_main);
@@ -337,6 +342,8 @@ static int build_service(pffdtd_engine *e) {
    };
    auto on_xshell = [&](i64 ix) { return (e->x_lo_edge && ix == 1) || (e->x_hi_edge && ix == Nx - 2); };
    const i64 tz_hi = (Nz - 2) / TZ;
+   // a tile-plane's entries travel into its shared-memory stage (PF_SVC_CAP of them at most, segments padded to 16 bytes)
+   const uint32_t cap = (uint32_t)std::max<i64>(0, std::min<i64>(e->svc_cap, PF_SVC_CAP - 2 * TY));
    std::vector<uint32_t> off((size_t)(ntile * pitch), 0u);
    uint64_t total = 0;
    for (i64 t = 0; t < ntile; t++) {
@@ -347,9 +354,10 @@ static int build_service(pffdtd_engine *e) {
       for (i64 x = 0; x <= Nx; x++) {
          off[(size_t)(t * pitch + x)] = (uint32_t)total;
          if (x >= 1 && x <= Nx - 2) {
-            if (!on_xshell(x)) total += (uint64_t)nshell;
+            uint64_t n = on_xshell(x) ? 0 : (uint64_t)nshell;
             const uint32_t k = cnt[(size_t)(t * pitch + x)];
-            if (k <= (uint32_t)e->svc_cap) total += k;
+            if (k <= cap) n += k;
+            total += (n + 3) / 4 * 4;
          }
       }
       if (total > 0xfffffff0ull) return 0;  // (never on one device's slab; keep the list kernels)
@@ -376,7 +384,7 @@ static int build_service(pffdtd_engine *e) {
    for (i64 i = 0; i < e->Nb; i++) {
       i64 r, c;
       const i64 key = key_of(bn[(size_t)i], &r, &c);
-      if (cnt[(size_t)key] <= (uint32_t)e->svc_cap)
+      if (cnt[(size_t)key] <= cap)
          list[fill[(size_t)key]++] = ((uint32_t)(adj[(size_t)i] & 0xfffu) << 16) | ((uint32_t)r << 7) | (uint32_t)c;
       else
          bl.push_back(bn[(size_t)i]), al.push_back(adj[(size_t)i]);
@@ -429,9 +437,7 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    }
    for (int k = 0; k < d->Nm; k++)
       if (d->Mb[k] < 0 || d->Mb[k] > PFFDTD_MMB) return fail(PFFDTD_EINVAL, "Mb[%d]=%d out of range", k, d->Mb[k]);
-   e->mb_uniform = d->Nm > 0 ? d->Mb[0] : 0;
-   for (int k = 1; k < d->Nm; k++)
-      if (d->Mb[k] != d->Mb[0]) e->mb_uniform = 0;
+
 
    const i64 sx = e->Ny * e->Nzp, sy = e->Nzp;
    if (e->fcc == 0) {
@@ -450,6 +456,7 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    CU(cudaEventCreateWithFlags(&e->ev_edge, cudaEventDisableTiming));
    CU(cudaEventCreateWithFlags(&e->ev_comm, cudaEventDisableTiming));
    CU(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
+   CU(cudaEventCreateWithFlags(&e->ev_push, cudaEventDisableTiming));
    CU(cudaEventCreate(&e->ev_t0));
    CU(cudaEventCreate(&e->ev_t1));
 
@@ -697,7 +704,7 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       CU(cudaStreamSynchronize(e->s_main));
       int cfg = e->tma.cfg;
       if (k == "svc") e->svc_want = value != 0, cfg = -1;
-      else if (k == "svc_cap") e->svc_cap = (int)std::max<int64_t>(0, std::min<int64_t>(value, 4096));
+      else if (k == "svc_cap") e->svc_cap = (int)std::max<int64_t>(0, std::min<int64_t>(value, PF_SVC_CAP));
       else cfg = (int)value;
       const int want_svc = e->svc_want && e->fcc == 0 && e->fuse_ok && e->abc_disjoint;
       if (k != "svc_cap" &&
@@ -706,8 +713,6 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       int rc = build_service(e);
       if (rc) return rc;
       e->halo_dirty = 1;
-   } else if (k == "fd_fixed") {
-      e->fd_fixed = value != 0;
    } else if (k == "abc_overlap") {
       e->abc_overlap = value != 0;
    } else if (k == "manual_halo") {
@@ -883,13 +888,9 @@ struct Step {
       if (p.nbl > 0) {
          const int nq = e->Nm * PFFDTD_MMB * 4;
          const size_t sm = (size_t)(nq / 4 * 5) * sizeof(Real);
-#define PF_FD(MB)                                                                                                                        \
-   pf::k_fd<Real, PFFDTD_MMB, MB><<<nblk(p.nbl, 128), 128, sm, s>>>(u0, e->bnl, e->matmb, (const Real *)e->lo2Kbg, (const Real *)e->facb, \
-                                                                    (Real *)e->hist[0], (Real *)e->hist[1], (Real *)e->vh1, (Real *)e->gh1, \
-                                                                    p.l0, p.nbl, e->Nblp, (const Real *)e->quads, nq, e->d_n)
-         if (e->fd_fixed && e->mb_uniform == 11) PF_FD(11);
-         else PF_FD(0);
-#undef PF_FD
+         pf::k_fd<Real, PFFDTD_MMB><<<nblk(p.nbl, 128), 128, sm, s>>>(u0, e->bnl, e->matmb, (const Real *)e->lo2Kbg, (const Real *)e->facb,
+                                                                      (Real *)e->hist[0], (Real *)e->hist[1], (Real *)e->vh1, (Real *)e->gh1,
+                                                                      p.l0, p.nbl, e->Nblp, (const Real *)e->quads, nq, e->d_n);
          e->launches += 1;
       }
       if (e->abc_pending) {  // join the absorbing-shell kernel running beside the boundary kernels
@@ -1024,9 +1025,22 @@ static void mirror_pass(pffdtd_engine *e, Real *u, cudaStream_t s) {
 // plane 1 -> lower neighbour's plane Nx-1, plane Nx-2 -> upper neighbour's plane 0.
 // Replaces the four cudaMemcpyPeerAsync waves of gpu_engine.h:1086-1126.
 static int exchange(pffdtd_engine *e, void *unew, cudaStream_t s) {
-   if (!e->comm) return 0;
    const size_t pb = (size_t)(e->Ny * e->Nzp) * e->rs;
    char *g = (char *)unew;
+   if (e->peer_lo || e->peer_hi) {
+      // one host thread drives every slab (gpu_engine.h:994, 1086-1126): push the new edge planes into the neighbours' halo planes of
+      // the grid with the same role (all slabs step in lockstep, so `cur` agrees).  The neighbour's next step waits for ev_comm.
+      const int role = e->cur ^ 1;
+      auto push = [&](pffdtd_engine *to, size_t dst_plane, size_t src_plane) -> cudaError_t {
+         char *dst = (char *)to->u[role] + dst_plane * pb;
+         if (to->device == e->device) return cudaMemcpyAsync(dst, g + src_plane * pb, pb, cudaMemcpyDeviceToDevice, s);
+         return cudaMemcpyPeerAsync(dst, to->device, g + src_plane * pb, e->device, pb, s);
+      };
+      if (e->peer_lo) CU(push(e->peer_lo, (size_t)(e->peer_lo->Nx - 1), 1));
+      if (e->peer_hi) CU(push(e->peer_hi, 0, (size_t)(e->Nx - 2)));
+      return 0;
+   }
+   if (!e->comm) return 0;
    NC(g_nccl.GroupStart());
    if (!e->x_lo_edge) {
       NC(g_nccl.Send(g + pb, pb, /*ncclInt8*/ 0, e->rank - 1, e->comm, s));
@@ -1062,6 +1076,9 @@ static int step_impl(pffdtd_engine *e, i64 n) {
       CU(cudaStreamWaitEvent(s, e->ev_comm, 0));
       e->comm_pending = 0;
    }
+   // (single process: the neighbours pushed them; their events were recorded when the host queued their previous step)
+   if (e->peer_lo && n > e->first_step) CU(cudaStreamWaitEvent(s, e->peer_lo->ev_push, 0));
+   if (e->peer_hi && n > e->first_step) CU(cudaStreamWaitEvent(s, e->peer_hi->ev_push, 0));
    if (!fused) {
       // 1. previous-state values at the ABC nodes; 2.+3. seam row and halo mirrors of u1
       if (e->Nba) {
@@ -1075,7 +1092,8 @@ static int step_impl(pffdtd_engine *e, i64 n) {
       e->halo_dirty = 0;
    }
    if (e->energy_on && (rc = energy_pre<Real>(e, u1, u0, n, s))) return rc;
-   const bool lo = e->comm && !e->x_lo_edge, hi = e->comm && !e->x_hi_edge;
+   const bool linked = e->comm || e->peer_lo || e->peer_hi;
+   const bool lo = linked && !e->x_lo_edge, hi = linked && !e->x_hi_edge;
    const bool split = (lo || hi) && e->overlap && e->sorted && Nx >= 5;
    if (split) {
       // planes the neighbours need first, then the exchange on the comm stream while the interior runs
@@ -1088,6 +1106,7 @@ static int step_impl(pffdtd_engine *e, i64 n) {
       CU(cudaStreamWaitEvent(e->s_comm, e->ev_edge, 0));
       if ((rc = exchange(e, u0, e->s_comm))) return rc;
       CU(cudaEventRecord(e->ev_comm, e->s_comm));
+      if (e->peer_lo || e->peer_hi) CU(cudaEventRecord(e->ev_push, e->s_comm));
       e->comm_pending = 1;
       const i64 b0 = lo ? nb_lo : 0, b1 = hi ? nb_hi : 0, l0 = lo ? e->nbl_lo : 0, l1 = hi ? e->nbl_hi : 0;
       const i64 a0 = lo ? e->nba_lo : 0, a1 = hi ? e->nba_hi : 0, s0 = lo ? e->ns_lo : 0, s1 = hi ? e->ns_hi : 0;
@@ -1100,6 +1119,7 @@ static int step_impl(pffdtd_engine *e, i64 n) {
       if ((rc = st.part(Part{1, Nx - 1, 0, NB, 0, e->Nbl, 0, e->Nba, 0, e->Ns, 0, e->np, true}))) return rc;
       CU(cudaGetLastError());
       if ((rc = exchange(e, u0, s))) return rc;
+      if (e->peer_lo || e->peer_hi) CU(cudaEventRecord(e->ev_push, s));
    }
    if (e->energy_on && (rc = energy_post<Real>(e, u0, n, s))) return rc;
    // 10. advance the device step counter, swap (the boundary history rotates with the counter's parity)
@@ -1115,7 +1135,7 @@ static int step_any(pffdtd_engine *e, i64 n) { return e->precision == 1 ? step_i
 
 // can a step starting now be replayed from a captured graph?
 static bool graphable(const pffdtd_engine *e) {
-   return e->use_graph && !e->energy_on && !e->profile_air && !e->manual_halo && e->steps_plain >= 2 &&
+   return e->use_graph && !e->energy_on && !e->profile_air && !e->manual_halo && !e->peer_lo && !e->peer_hi && e->steps_plain >= 2 &&
           !(e->halo_dirty && e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge);
 }
 
@@ -1187,7 +1207,8 @@ extern "C" int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps
    if (nsteps < 0 || nstart < 0 || nstart + nsteps > e->Nt)
       return fail(PFFDTD_EINVAL, "steps [%lld,%lld) outside [0,%lld)", (long long)nstart, (long long)(nstart + nsteps), (long long)e->Nt);
    if ((!e->x_lo_edge || !e->x_hi_edge) && !e->comm && !e->manual_halo)
-      return fail(PFFDTD_ESTATE, "slab engine without communicator: call pffdtd_comm_init");
+      return fail(PFFDTD_ESTATE, e->peer_lo || e->peer_hi ? "slab of a pffdtd_multi: step it with pffdtd_multi_run_steps"
+                                                         : "slab engine without communicator: call pffdtd_comm_init");
    CU(cudaSetDevice(e->device));
    i64 n = nstart;
    const i64 nend = nstart + nsteps;
@@ -1401,6 +1422,241 @@ extern "C" int pffdtd_run_sim(const pffdtd_desc *desc, int device, double *u_out
    if (rc == PFFDTD_OK) rc = pffdtd_read_outputs(e, 0, desc->Nt, u_out);
    std::string keep = g_err;
    pffdtd_destroy(e);
+   g_err = keep;
+   return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-process multi-GPU: one host thread drives every slab, as the reference's run_sim does
+// (gpu_engine.h:679-691 device count, :516-662 split_data, :994 the per-step loop over devices, :1086-1126 the exchange)
+// ------------------------------------------------------------------------------------------------
+struct SlabData {
+   pffdtd_desc d{};
+   std::vector<int64_t> bn, bnl, bna, in, out;
+   std::vector<uint16_t> adj;
+   std::vector<int8_t> mat, Q;
+   std::vector<double> ssaf, insig;
+};
+struct pffdtd_multi {
+   std::vector<pffdtd_engine *> eng;
+   std::vector<i64> x0, nx;  // first owned plane and owned planes per slab
+   i64 Nr = 0, Nt = 0;
+};
+
+// per x-plane cost, the C++ twin of SimData.plane_costs (pffdtd_b200/sim_data.py): air nodes + weighted list entries
+static std::vector<double> plane_costs(const pffdtd_desc *d) {
+   const double COST_BN = 3.0, COST_BNL_BASE = 4.0, COST_BNL_BRANCH = 1.5, COST_BNA = 2.0;
+   const i64 P = d->Ny * d->Nz;
+   std::vector<double> c((size_t)d->Nx, (double)P);
+   if (d->x_lo_edge) c[0] = 0.0;
+   if (d->x_hi_edge) c[(size_t)d->Nx - 1] = 0.0;
+   int mb = 0;
+   for (int k = 0; k < d->Nm; k++) mb = std::max<int>(mb, d->Mb[k]);
+   for (i64 i = 0; i < d->Nb; i++) c[(size_t)(d->bn_ixyz[i] / P)] += COST_BN;
+   for (i64 i = 0; i < d->Nbl; i++) c[(size_t)(d->bnl_ixyz[i] / P)] += COST_BNL_BASE + COST_BNL_BRANCH * mb;
+   for (i64 i = 0; i < d->Nba; i++) c[(size_t)(d->bna_ixyz[i] / P)] += COST_BNA;
+   return c;
+}
+
+// owned planes per slab: the reference's equal split (gpu_engine.h:532-543) or, with `cost`, slabs of about equal cost
+// (the twin of SimData.slab_planes)
+static int slab_planes(i64 Nx, int n, const std::vector<double> *cost, std::vector<i64> *starts, std::vector<i64> *sizes) {
+   sizes->assign((size_t)n, 0);
+   if (!cost) {
+      for (int r = 0; r < n; r++) (*sizes)[(size_t)r] = Nx / n + (r < Nx % n ? 1 : 0);
+   } else {
+      if (Nx < 2 * (i64)n) return fail(PFFDTD_EINVAL, "too many slabs for this grid");
+      std::vector<double> cum((size_t)Nx + 1, 0.0);
+      for (i64 x = 0; x < Nx; x++) cum[(size_t)x + 1] = cum[(size_t)x] + (*cost)[(size_t)x];
+      std::vector<i64> cuts{0};
+      for (int r = 1; r < n; r++) {
+         const double target = cum[(size_t)Nx] * r / n;
+         i64 x = std::lower_bound(cum.begin(), cum.end(), target) - cum.begin();
+         if (x > 0 && std::fabs(cum[(size_t)x - 1] - target) <= std::fabs(cum[(size_t)x] - target)) x--;
+         x = std::min(std::max(x, cuts.back() + 2), Nx - 2 * (i64)(n - r));
+         cuts.push_back(x);
+      }
+      cuts.push_back(Nx);
+      for (int r = 0; r < n; r++) (*sizes)[(size_t)r] = cuts[(size_t)r + 1] - cuts[(size_t)r];
+   }
+   starts->assign((size_t)n, 0);
+   for (int r = 1; r < n; r++) (*starts)[(size_t)r] = (*starts)[(size_t)r - 1] + (*sizes)[(size_t)r - 1];
+   for (int r = 0; r < n; r++)
+      if ((*sizes)[(size_t)r] < 2) return fail(PFFDTD_EINVAL, "too many slabs for this grid");
+   return 0;
+}
+
+// the part of `d` slab r owns, re-based to slab-local indices, one halo plane towards each neighbour (gpu_engine.h:755-823;
+// the twin of SimData.slab).  The node lists must be sorted (check_sorted, gpu_engine.h:497-513).
+static void slab_desc(const pffdtd_desc *d, i64 start, i64 size, bool first, bool last, SlabData *s) {
+   const i64 P = d->Ny * d->Nz, lo = start * P, hi = (start + size) * P;
+   const i64 first_plane = start - (first ? 0 : 1), off = first_plane * P;
+   auto own = [&](const int64_t *a, i64 n, i64 *b, i64 *e) {
+      *b = std::lower_bound(a, a + n, lo) - a;
+      *e = std::lower_bound(a, a + n, hi) - a;
+   };
+   auto rebase = [&](const int64_t *a, i64 b, i64 e, std::vector<int64_t> *out) {
+      out->resize((size_t)(e - b));
+      for (i64 i = b; i < e; i++) (*out)[(size_t)(i - b)] = a[i] - off;
+   };
+   i64 b, e;
+   s->d = *d;
+   s->d.Nx = size + (first ? 0 : 1) + (last ? 0 : 1);
+   s->d.ix0 = d->ix0 + first_plane;
+   s->d.x_lo_edge = d->x_lo_edge && first, s->d.x_hi_edge = d->x_hi_edge && last;
+   own(d->bn_ixyz, d->Nb, &b, &e);
+   rebase(d->bn_ixyz, b, e, &s->bn);
+   s->adj.assign(d->adj_bn + b, d->adj_bn + e);
+   s->d.Nb = e - b;
+   own(d->bnl_ixyz, d->Nbl, &b, &e);
+   rebase(d->bnl_ixyz, b, e, &s->bnl);
+   s->mat.assign(d->mat_bnl + b, d->mat_bnl + e);
+   s->ssaf.assign(d->ssaf_bnl + b, d->ssaf_bnl + e);
+   s->d.Nbl = e - b;
+   own(d->bna_ixyz, d->Nba, &b, &e);
+   rebase(d->bna_ixyz, b, e, &s->bna);
+   s->Q.assign(d->Q_bna + b, d->Q_bna + e);
+   s->d.Nba = e - b;
+   own(d->in_ixyz, d->Ns, &b, &e);
+   rebase(d->in_ixyz, b, e, &s->in);
+   s->insig.assign(d->in_sigs + b * d->Nt, d->in_sigs + e * d->Nt);
+   s->d.Ns = e - b;
+   own(d->out_ixyz, d->Nr, &b, &e);
+   rebase(d->out_ixyz, b, e, &s->out);
+   s->d.Nr = e - b;
+   s->d.bn_ixyz = s->bn.data(), s->d.adj_bn = s->adj.data(), s->d.bnl_ixyz = s->bnl.data(), s->d.mat_bnl = s->mat.data();
+   s->d.ssaf_bnl = s->ssaf.data(), s->d.bna_ixyz = s->bna.data(), s->d.Q_bna = s->Q.data(), s->d.in_ixyz = s->in.data();
+   s->d.out_ixyz = s->out.data(), s->d.in_sigs = s->insig.data();
+}
+
+extern "C" int pffdtd_multi_destroy(pffdtd_multi *m) {
+   if (!m) return PFFDTD_OK;
+   for (pffdtd_engine *e : m->eng)
+      if (e) {
+         cudaSetDevice(e->device);
+         cudaStreamSynchronize(e->s_main);
+         cudaStreamSynchronize(e->s_comm);
+      }
+   for (pffdtd_engine *e : m->eng) pffdtd_destroy(e);
+   delete m;
+   return PFFDTD_OK;
+}
+
+extern "C" int pffdtd_multi_create(const pffdtd_desc *desc, int nslabs, const int *devices, int balance, pffdtd_multi **out) {
+   if (!desc || !out) return fail(PFFDTD_EINVAL, "NULL argument");
+   if (desc->struct_size != (int32_t)sizeof(pffdtd_desc)) return fail(PFFDTD_EINVAL, "pffdtd_desc size mismatch");
+   int ndev = 0;
+   CU(cudaGetDeviceCount(&ndev));
+   if (ndev < 1) return fail(PFFDTD_ECUDA, "no CUDA device");
+   if (nslabs <= 0) nslabs = ndev;  // every visible device, the reference's rule (CUDA_VISIBLE_DEVICES picks them)
+   if (nslabs > 1 && (!ascending(desc->bn_ixyz, desc->Nb) || !ascending(desc->bnl_ixyz, desc->Nbl) || !ascending(desc->bna_ixyz, desc->Nba) ||
+                      !ascending(desc->in_ixyz, desc->Ns, false) || !ascending(desc->out_ixyz, desc->Nr, false)))
+      return fail(PFFDTD_EINVAL, "more than one slab needs sorted node lists (a sort_sim_data'd gpu folder, gpu_engine.h:497-513)");
+   pffdtd_multi *m = new pffdtd_multi();
+   m->Nr = desc->Nr, m->Nt = desc->Nt;
+   int rc = PFFDTD_OK;
+   if (nslabs == 1) {
+      m->x0 = {0}, m->nx = {desc->Nx};
+      pffdtd_engine *e = nullptr;
+      rc = pffdtd_create(desc, devices ? devices[0] : 0, &e);
+      m->eng.push_back(e);
+   } else {
+      std::vector<double> cost;
+      if (balance) cost = plane_costs(desc);
+      rc = slab_planes(desc->Nx, nslabs, balance ? &cost : nullptr, &m->x0, &m->nx);
+      for (int r = 0; r < nslabs && rc == PFFDTD_OK; r++) {
+         SlabData sd;
+         slab_desc(desc, m->x0[(size_t)r], m->nx[(size_t)r], r == 0, r == nslabs - 1, &sd);
+         pffdtd_engine *e = nullptr;
+         rc = pffdtd_create(&sd.d, devices ? devices[r] : r % ndev, &e);
+         m->eng.push_back(e);
+      }
+      for (int r = 0; r < nslabs && rc == PFFDTD_OK; r++) {
+         pffdtd_engine *e = m->eng[(size_t)r];
+         e->peer_lo = r > 0 ? m->eng[(size_t)r - 1] : nullptr;
+         e->peer_hi = r < nslabs - 1 ? m->eng[(size_t)r + 1] : nullptr;
+         for (pffdtd_engine *p : {e->peer_lo, e->peer_hi})
+            if (p && p->device != e->device) {
+               cudaSetDevice(e->device);
+               int can = 0;
+               cudaDeviceCanAccessPeer(&can, e->device, p->device);
+               if (can && cudaDeviceEnablePeerAccess(p->device, 0) != cudaSuccess) cudaGetLastError();  // (already enabled is fine)
+            }
+      }
+   }
+   if (rc != PFFDTD_OK) {
+      std::string keep = g_err;
+      pffdtd_multi_destroy(m);
+      g_err = keep;
+      return rc;
+   }
+   *out = m;
+   return PFFDTD_OK;
+}
+
+extern "C" int pffdtd_multi_slabs(pffdtd_multi *m, int64_t *planes, int max) {
+   if (!m) return fail(PFFDTD_EINVAL, "NULL argument");
+   for (size_t r = 0; r < m->eng.size() && planes && (int)r < max; r++) planes[r] = m->nx[r];
+   return (int)m->eng.size();
+}
+
+extern "C" int pffdtd_multi_engine(pffdtd_multi *m, int slab, pffdtd_engine **e) {
+   if (!m || !e || slab < 0 || slab >= (int)m->eng.size()) return fail(PFFDTD_EINVAL, "no such slab");
+   *e = m->eng[(size_t)slab];
+   return PFFDTD_OK;
+}
+
+extern "C" int pffdtd_multi_run_steps(pffdtd_multi *m, int64_t nstart, int64_t nsteps) {
+   if (!m) return fail(PFFDTD_EINVAL, "NULL argument");
+   if (m->eng.size() == 1) return pffdtd_run_steps(m->eng[0], nstart, nsteps);
+   if (nsteps < 0 || nstart < 0 || nstart + nsteps > m->Nt)
+      return fail(PFFDTD_EINVAL, "steps [%lld,%lld) outside [0,%lld)", (long long)nstart, (long long)(nstart + nsteps), (long long)m->Nt);
+   // all slabs step in lockstep, queued by this one thread; nothing here waits for the devices
+   for (pffdtd_engine *e : m->eng) e->first_step = nstart == 0 ? 0 : -1;  // later batches: the neighbours' events of the previous batch hold
+   for (i64 n = nstart; n < nstart + nsteps; n++)
+      for (pffdtd_engine *e : m->eng) {
+         CU(cudaSetDevice(e->device));
+         int rc = step_any(e, n);
+         if (rc) return rc;
+         e->steps_plain++;
+      }
+   return PFFDTD_OK;
+}
+
+extern "C" int pffdtd_multi_sync(pffdtd_multi *m) {
+   if (!m) return fail(PFFDTD_EINVAL, "NULL argument");
+   for (pffdtd_engine *e : m->eng) {
+      int rc = pffdtd_sync(e);
+      if (rc) return rc;
+   }
+   return PFFDTD_OK;
+}
+
+// rows in slab order == the sorted receiver order of the whole grid (slabs are contiguous in x, lists sorted)
+extern "C" int pffdtd_multi_read_outputs(pffdtd_multi *m, int64_t n0, int64_t n1, double *u_out) {
+   if (!m || !u_out) return fail(PFFDTD_EINVAL, "NULL argument");
+   int rc = pffdtd_multi_sync(m);
+   i64 row = 0;
+   for (size_t r = 0; r < m->eng.size() && rc == PFFDTD_OK; r++) {
+      rc = pffdtd_read_outputs(m->eng[r], n0, n1, u_out + row * (n1 - n0));
+      row += m->eng[r]->Nr;
+   }
+   return rc;
+}
+
+extern "C" int pffdtd_run_sim_multi(const pffdtd_desc *desc, int nslabs, const int *devices, double *u_out, double *elapsed_s) {
+   if (!desc || !u_out) return fail(PFFDTD_EINVAL, "NULL argument");
+   pffdtd_multi *m = nullptr;
+   int rc = pffdtd_multi_create(desc, nslabs, devices, 1, &m);
+   if (rc) return rc;
+   auto t0 = std::chrono::steady_clock::now();
+   rc = pffdtd_multi_run_steps(m, 0, desc->Nt);
+   if (rc == PFFDTD_OK) rc = pffdtd_multi_sync(m);
+   auto t1 = std::chrono::steady_clock::now();
+   if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+   if (rc == PFFDTD_OK) rc = pffdtd_multi_read_outputs(m, 0, desc->Nt, u_out);
+   std::string keep = g_err;
+   pffdtd_multi_destroy(m);
    g_err = keep;
    return rc;
 }

@@ -220,17 +220,18 @@ __global__ void k_fd_prep(const int8_t *__restrict__ mat_bnl, const Real *__rest
 
 // `Nbl` below is the PITCH of the branch-major state arrays (the node count rounded up to 32 elements, so that a warp's
 // 32 consecutive nodes are one aligned 128-byte line for every branch).
-// Round 1's version issued ~1000 instructions per thread and ran issue-limited (56 % issue-active at 4.1 TB/s): twelve of its
-// thirteen IEEE divisions were divisions by 2, every branch carried a predicate for "m < Mb", and the doubled coefficients
-// were recomputed per node.  Here: x/2 is x*0.5 (the same correctly rounded value), the block stages (2*bDh, bFh, b, bd, 2*bFh)
-// per (material, branch) in shared memory once (2*x is exact), and MB > 0 fixes the branch count at compile time for problems
-// whose materials all have MB branches (every shipped material has 11); MB = 0 keeps the per-node count.
-template <typename Real, int MMB, int MB>
+// x/2 is written x*0.5 (the same correctly rounded value; twelve of round 1's thirteen IEEE divisions per node were divisions by
+// two) and the block stages (2*bDh, bFh, b, bd, 2*bFh) per (material, branch) in shared memory once (2*x is exact).  A version
+// with the branch count fixed at compile time (11, every shipped material) was tried: 584 instead of 952 instructions, but the
+// compiler wants 128 registers for it and spills at every cap that keeps the occupancy -- measured slower (c2: 0.291 vs 0.249 ms
+// per step), dropped.
+template <typename Real, int MMB>
 __global__ void __launch_bounds__(128) k_fd(Real *__restrict__ u0, const i64 *__restrict__ bnl, const uint16_t *__restrict__ matmb,
                                             const Real *__restrict__ lo2Kbg_bnl, const Real *__restrict__ fac_bnl,
                                             Real *__restrict__ hist0, Real *__restrict__ hist1, Real *__restrict__ vh1,
                                             Real *__restrict__ gh1, i64 i0, i64 n, i64 Nbl, const Real *__restrict__ quads, int nquads,
                                             const i64 *__restrict__ d_n) {
+   constexpr int MB = 0;
    typedef Ops<Real> O;
    extern __shared__ __align__(16) unsigned char fd_smem[];
    Real *qs = reinterpret_cast<Real *>(fd_smem);  // [Nm][MMB][5] = 2*bDh, bFh, b, bd, 2*bFh

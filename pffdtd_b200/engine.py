@@ -76,6 +76,15 @@ def lib():
     L.pffdtd_run_sim.argtypes = [C.POINTER(pffdtd_desc), C.c_int, vp, dp]
     L.pffdtd_energy_enable.argtypes = [vp, C.POINTER(pffdtd_energy_desc)]
     L.pffdtd_read_energy.argtypes = [vp, vp, vp, vp]
+    ip = C.POINTER(C.c_int)
+    L.pffdtd_multi_create.argtypes = [C.POINTER(pffdtd_desc), C.c_int, ip, C.c_int, C.POINTER(vp)]
+    L.pffdtd_multi_destroy.argtypes = [vp]
+    L.pffdtd_multi_slabs.argtypes = [vp, C.POINTER(i64), C.c_int]
+    L.pffdtd_multi_engine.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.pffdtd_multi_run_steps.argtypes = [vp, i64, i64]
+    L.pffdtd_multi_sync.argtypes = [vp]
+    L.pffdtd_multi_read_outputs.argtypes = [vp, i64, i64, vp]
+    L.pffdtd_run_sim_multi.argtypes = [C.POINTER(pffdtd_desc), C.c_int, ip, vp, dp]
     L.pffdtd_air_chunk_plan.argtypes = [i64, C.c_int, C.POINTER(i64), i64]
     L.pffdtd_air_chunk_plan.restype = i64
     _lib = L
@@ -226,4 +235,80 @@ def run_sim(sd: SimData, device: int = 0):
     out = np.zeros((sd.Nr, sd.Nt), np.float64)
     t = C.c_double()
     _check(lib().pffdtd_run_sim(C.byref(d), int(device), out.ctypes.data, C.byref(t)))
+    return out, t.value
+
+
+class MultiEngine:
+    """All slabs of a grid driven by ONE host thread (pffdtd_multi_*): the reference's single-process multi-GPU model
+    (gpu_engine.h:679-691, 994, 1086-1126).  `sd` describes the whole grid with sorted node lists; `nslabs` <= 0 takes one
+    slab per visible device; `devices` may name a device several times (slabs sharing a GPU)."""
+
+    def __init__(self, sd: SimData, nslabs: int = 0, devices=None, balance: bool = True):
+        self.sd = sd
+        self.L = lib()
+        self._desc = sd.desc()
+        dv = None
+        if devices is not None:
+            dv = (C.c_int * len(devices))(*[int(d) for d in devices])
+            nslabs = len(devices)
+        h = C.c_void_p()
+        _check(self.L.pffdtd_multi_create(C.byref(self._desc), int(nslabs), dv, int(bool(balance)), C.byref(h)))
+        self.h = h
+        buf = (C.c_int64 * 64)()
+        self.nslabs = self.L.pffdtd_multi_slabs(self.h, buf, 64)
+        self.planes = [int(buf[i]) for i in range(min(self.nslabs, 64))]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pffdtd_multi_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value: int):
+        """the option on every slab's engine"""
+        for r in range(self.nslabs):
+            e = C.c_void_p()
+            _check(self.L.pffdtd_multi_engine(self.h, r, C.byref(e)))
+            _check(self.L.pffdtd_set_option(e, key.encode(), int(value)))
+
+    def stat(self, slab: int, key: str) -> float:
+        e, v = C.c_void_p(), C.c_double()
+        _check(self.L.pffdtd_multi_engine(self.h, slab, C.byref(e)))
+        _check(self.L.pffdtd_get_stat(e, key.encode(), C.byref(v)))
+        return v.value
+
+    def run_steps(self, nstart: int, nsteps: int):
+        _check(self.L.pffdtd_multi_run_steps(self.h, int(nstart), int(nsteps)))
+
+    def sync(self):
+        _check(self.L.pffdtd_multi_sync(self.h))
+
+    def read_outputs(self, n0=0, n1=None):
+        n1 = self.sd.Nt if n1 is None else n1
+        out = np.zeros((self.sd.Nr, n1 - n0), np.float64)
+        _check(self.L.pffdtd_multi_read_outputs(self.h, n0, n1, out.ctypes.data))
+        return out
+
+
+def run_sim_multi(sd: SimData, nslabs: int = 0, devices=None):
+    """pffdtd_run_sim_multi: the reference's run_sim() over every visible device -> (u_out [Nr,Nt] sorted order, seconds)"""
+    d = sd.desc()
+    out = np.zeros((sd.Nr, sd.Nt), np.float64)
+    t = C.c_double()
+    dv = None
+    if devices is not None:
+        dv = (C.c_int * len(devices))(*[int(x) for x in devices])
+        nslabs = len(devices)
+    _check(lib().pffdtd_run_sim_multi(C.byref(d), int(nslabs), dv, out.ctypes.data, C.byref(t)))
     return out, t.value

@@ -117,10 +117,10 @@ def test_every_tile_width_gives_the_same_bits(name, precision):
 
 
 @pytest.mark.parametrize("precision", (2, 1))
-@pytest.mark.parametrize("cap", (0, 3, 17, 4096))
+@pytest.mark.parametrize("cap", (0, 3, 17, 192))
 def test_service_warp_density_threshold(cap, precision):
     """svc_cap decides which tile-planes' boundary nodes the air kernel finishes itself: none (only the shell's z faces), a few, all
-    (walls perpendicular to x and y too: dozens of passes per plane) -- same bits every time; a room with solid blocks and three materials"""
+    (as many as a stage holds) -- same bits every time; a room with solid blocks and three materials"""
     from cases import OBSTACLE_CASES  # noqa: F401
     sd = make_sim_data("cart_blobs", precision)
     g1, g0 = noise_grids(sd)
@@ -130,7 +130,7 @@ def test_service_warp_density_threshold(cap, precision):
     o.run_steps(0, 25)
     with Engine(sd) as e:
         e.set_option("svc_cap", cap)
-        assert e.stat("svc") == 1 and (e.stat("nb_left") == 0) == (cap == 4096) and (cap > 0 or e.stat("nb_left") == sd.Nb)
+        assert e.stat("svc") == 1 and (cap > 0 or e.stat("nb_left") == sd.Nb) and (cap == 0 or e.stat("nb_left") < sd.Nb)
         e.write_grid(1, g1)
         e.write_grid(0, g0)
         e.run_steps(0, 25)

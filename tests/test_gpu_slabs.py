@@ -48,6 +48,43 @@ def test_two_slabs_on_one_device_manual_halo(name, precision, fuse):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("name,precision,devices,balance", (("cart_lossy_mb11", 1, (0, 0), True), ("cart_lossy_mb11", 2, (0, 0, 0), False),
+                                                             ("cart_tight", 1, (0, 0, 0), True), ("fcc2_lossy", 2, (0, 0), True),
+                                                             ("cart_long", 1, (0, 0, 0, 0, 0), True)))
+def test_single_process_multi_slab_engine(name, precision, devices, balance):
+    """pffdtd_multi_*: one host thread, one engine per slab, edge planes pushed into the neighbours' halos by (peer) copies on a second
+    stream, the next step waiting on events -- the reference's own multi-GPU model (gpu_engine.h:994, 1086-1126).  Here the slabs share
+    device 0 (the test box has one GPU; with more, `devices` names them); batches of steps, bit-exact against the oracle"""
+    from pffdtd_b200.engine import MultiEngine
+    sd = make_sim_data(name, precision).sorted()
+    ref = Oracle(sd).run_all()
+    with MultiEngine(sd, devices=devices, balance=balance) as m:
+        assert m.nslabs == len(devices) and sum(m.planes) == sd.Nx and min(m.planes) >= 2
+        for n in range(0, sd.Nt, 7):
+            m.run_steps(n, min(7, sd.Nt - n))
+        got = m.read_outputs()
+    assert np.array_equal(got, ref)
+
+
+def test_run_sim_multi_uses_every_visible_device():
+    """nslabs = 0: one slab per visible device (1 on the test box: then it is pffdtd_run_sim)"""
+    from pffdtd_b200.engine import run_sim_multi
+    sd = make_sim_data("cart_lossy", 2).sorted()
+    out, t = run_sim_multi(sd)
+    assert np.array_equal(out, Oracle(sd).run_all()) and t > 0
+    out3, _ = run_sim_multi(sd, devices=(0, 0, 0))
+    assert np.array_equal(out3, out)
+
+
+def test_multi_refuses_unsorted_lists():
+    from pffdtd_b200.engine import MultiEngine, PffdtdError
+    sd = make_sim_data("cart_lossy", 2)
+    sd.bn_ixyz = sd.bn_ixyz[::-1].copy()
+    sd.adj_bn = sd.adj_bn[::-1].copy()
+    with pytest.raises(PffdtdError):
+        MultiEngine(sd, devices=(0, 0))
+
+
 WORKER = r'''
 import sys, numpy as np
 sys.path.insert(0, "{root}")
