@@ -165,6 +165,8 @@ struct pffdtd_engine {
    // in-kernel boundary work (air_tma.cuh AirSvc): per tile-plane lists of the sparse rigid nodes + the shell's z faces, and the
    // dense remainder of the boundary list that stays with k_rigid
    int svc_want = 1, svc_on = 0, svc_cap = 64;
+   int svc_shell = 0;   // the lists hold the shell's z faces too (fused Cartesian step); otherwise rigid nodes only (any step)
+   int bn_off_abc = 0;  // no boundary node is also an absorbing-shell node: the rigid update commutes with the shell update
    float negzero = -0.0f;  // travels as a kernel argument so that the compiler cannot fold it (air_tma.cuh "packed fp32 arithmetic")
    uint32_t *svc_list = nullptr, *svc_off = nullptr;
    i64 *bn_left = nullptr;
@@ -307,15 +309,20 @@ extern "C" int pffdtd_destroy(pffdtd_engine *e) {
 // (walls perpendicular to x or y: contiguous runs along z) go to the "left" list for k_rigid, where they coalesce.
 // Only for the fused Cartesian step with the canonical shell and no boundary / source node on it (abc_disjoint): then the shell
 // update, the rigid update and the air update touch disjoint nodes and commute.
-static bool svc_eligible(const pffdtd_engine *e) {
-   return e->svc_want && e->fcc == 0 && e->fuse_ok && e->abc_disjoint && e->tma.ok && e->tma.svc && !e->tma.z_edge;
+// Rigid nodes may go to the service warp whenever no boundary node is a shell node (bn_off_abc); the shell's z faces go with them
+// when the step is the fused Cartesian one (then the air kernel stashes nothing for them and k_abc_faces skips them).
+static bool step_fused(const pffdtd_engine *e) {
+   return e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge && !e->energy_on;
 }
+static bool svc_eligible(const pffdtd_engine *e) { return e->svc_want && e->bn_off_abc && e->tma.ok && e->tma.svc && !e->energy_on; }
 static int build_service(pffdtd_engine *e) {
    dfree(e, e->svc_list), dfree(e, e->svc_off), dfree(e, e->bn_left), dfree(e, e->adj_left);
    e->svc_list = e->svc_off = nullptr, e->bn_left = nullptr, e->adj_left = nullptr;
    e->svc_on = 0, e->Nb_left = e->nbL_lo = e->nbL_hi = e->svc_entries = 0;
    e->tma.sv = pf::AirSvc{nullptr, nullptr, 0};
    if (!svc_eligible(e)) return 0;
+   const bool with_shell = e->fcc == 0 && step_fused(e) && e->abc_disjoint;
+   e->svc_shell = with_shell;
    const i64 Nx = e->Nx, Ny = e->Ny, Nz = e->Nz, Nzp = e->Nzp, TY = e->tma.ty, TZ = e->tma.tzn;
    const i64 tzc = (Nz - 1 + TZ - 1) / TZ, tyc = (Ny - 2 + TY - 1) / TY, ntile = tzc * tyc, pitch = Nx + 1;
    if (TY > 64 || TZ > 128 || Ny < 6) return 0;
@@ -350,7 +357,7 @@ static int build_service(pffdtd_engine *e) {
       const i64 ty = t / tzc, tz = t - ty * tzc;
       i64 ya, yb;
       shell_rows(ty, &ya, &yb);
-      const i64 nshell = std::max<i64>(0, yb - ya + 1) * ((tz == 0 ? 1 : 0) + (tz == tz_hi ? 1 : 0));
+      const i64 nshell = !with_shell ? 0 : std::max<i64>(0, yb - ya + 1) * ((tz == 0 ? 1 : 0) + (tz == tz_hi ? 1 : 0));
       for (i64 x = 0; x <= Nx; x++) {
          off[(size_t)(t * pitch + x)] = (uint32_t)total;
          if (x >= 1 && x <= Nx - 2) {
@@ -368,7 +375,7 @@ static int build_service(pffdtd_engine *e) {
       const i64 ty = t / tzc, tz = t - ty * tzc;
       i64 ya, yb;
       shell_rows(ty, &ya, &yb);
-      if (yb < ya || (tz != 0 && tz != tz_hi)) continue;
+      if (!with_shell || yb < ya || (tz != 0 && tz != tz_hi)) continue;
       for (i64 x = 1; x <= Nx - 2; x++) {
          if (on_xshell(x)) continue;
          uint32_t &f = fill[(size_t)(t * pitch + x)];
@@ -563,6 +570,14 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
       for (i64 i = 0; clear && i < e->Ns; i++) clear = !on_shell(d->in_ixyz[i]);
       e->abc_disjoint = clear;
    }
+   // does any boundary node also sit in the absorbing-shell list?  (a bitmap of the shell list; any layout, any order)
+   {
+      std::vector<uint8_t> bits((size_t)((e->Nx * e->Ny * e->Nz + 7) / 8), 0);
+      for (i64 i = 0; i < e->Nba; i++) bits[(size_t)(d->bna_ixyz[i] >> 3)] |= (uint8_t)(1u << (d->bna_ixyz[i] & 7));
+      bool off = true;
+      for (i64 i = 0; off && i < e->Nb; i++) off = !((bits[(size_t)(d->bn_ixyz[i] >> 3)] >> (d->bn_ixyz[i] & 7)) & 1u);
+      e->bn_off_abc = off;
+   }
    // late halo mirrors: nodes written after the air kernel (boundary, source) whose value belongs in a halo
    if (e->fcc == 0) {
       std::vector<std::pair<i64, i64>> pr;  // (src, dst) in the padded layout
@@ -614,7 +629,7 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    }
    if (dalloc(e, &e->tma.ctr, 2)) return PFFDTD_ECUDA;
    if (dalloc(e, &e->d_n, 1)) return PFFDTD_ECUDA;
-   const int want_svc = e->svc_want && e->fcc == 0 && e->fuse_ok && e->abc_disjoint;
+   const int want_svc = e->svc_want && e->bn_off_abc && e->Nb > 0;
    if ((rc = pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask, -1, want_svc))) {
       // not fatal: fall back to the generic kernel, remember why
       e->air_kernel = 0;
@@ -688,9 +703,13 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       if (value < 0 || value > 1) return fail(PFFDTD_EINVAL, "air_kernel must be 0 or 1");
       e->air_kernel = (int)value;
       e->halo_dirty = 1;
+      int rc = build_service(e);  // (whether the lists carry the shell's z faces follows the kind of step)
+      if (rc) return rc;
    } else if (k == "fuse") {
       e->fuse = value != 0;
       e->halo_dirty = 1;
+      int rc = build_service(e);
+      if (rc) return rc;
    } else if (k == "overlap") {
       e->overlap = value != 0;
    } else if (k == "profile_air") {
@@ -706,7 +725,7 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       if (k == "svc") e->svc_want = value != 0, cfg = -1;
       else if (k == "svc_cap") e->svc_cap = (int)std::max<int64_t>(0, std::min<int64_t>(value, PF_SVC_CAP));
       else cfg = (int)value;
-      const int want_svc = e->svc_want && e->fcc == 0 && e->fuse_ok && e->abc_disjoint;
+      const int want_svc = e->svc_want && e->bn_off_abc && e->Nb > 0;
       if (k != "svc_cap" &&
           pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask, cfg, want_svc))
          return fail(PFFDTD_EINVAL, "air_cfg %lld: %s", (long long)value, e->tma.why.c_str());
@@ -990,7 +1009,7 @@ extern "C" int pffdtd_energy_enable(pffdtd_engine *e, const pffdtd_energy_desc *
    drop_graphs(e);
    e->halo_dirty = 1;
    e->energy_on = 1;
-   return PFFDTD_OK;
+   return build_service(e);  // (energy steps use the list kernels only)
 }
 
 extern "C" int pffdtd_read_energy(pffdtd_engine *e, double *H_tot, double *E_lost, double *E_in) {
@@ -1057,8 +1076,8 @@ static int exchange(pffdtd_engine *e, void *unew, cudaStream_t s) {
 template <typename Real>
 static int step_impl(pffdtd_engine *e, i64 n) {
    if (n < 0 || n >= e->Nt) return fail(PFFDTD_EINVAL, "step %lld outside [0,%lld)", (long long)n, (long long)e->Nt);
-   const bool fused = e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge && !e->energy_on;
-   const bool svc = fused && e->svc_on;
+   const bool fused = step_fused(e);
+   const bool svc = e->svc_on && e->air_kernel == 1 && (e->svc_shell != 0) == fused;
    Step<Real> st{e, (Real *)e->u[e->cur], (Real *)e->u[e->cur ^ 1], e->s_main, n, fused, svc};
    const i64 NB = svc ? e->Nb_left : e->Nb, nb_lo = svc ? e->nbL_lo : e->nb_lo, nb_hi = svc ? e->nbL_hi : e->nb_hi;
    Real *u1 = st.u1, *u0 = st.u0;

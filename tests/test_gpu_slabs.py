@@ -20,6 +20,11 @@ from pffdtd_b200.engine import Engine
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
 GOLD = np.load(ROOT / "tests" / "golden" / "traces_ref_cpu_engine.npz")
 
 
@@ -76,6 +81,21 @@ def test_run_sim_multi_uses_every_visible_device():
     assert np.array_equal(out3, out)
 
 
+def test_single_process_multi_gpu_on_distinct_devices():
+    """the same API with one slab per visible GPU (peer copies over NVLink); skipped on a one-GPU box"""
+    from pffdtd_b200.engine import MultiEngine
+    n = min(_ngpu(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    for name, precision in (("cart_lossy_mb11", 1), ("fcc2_lossy", 2), ("cart_long", 1)):
+        sd = make_sim_data(name, precision).sorted()
+        ref = Oracle(sd).run_all()
+        with MultiEngine(sd, nslabs=0) as m:
+            assert m.nslabs == _ngpu() or m.nslabs == n
+            m.run_steps(0, sd.Nt)
+            assert np.array_equal(m.read_outputs(), ref), name
+
+
 def test_multi_refuses_unsorted_lists():
     from pffdtd_b200.engine import MultiEngine, PffdtdError
     sd = make_sim_data("cart_lossy", 2)
@@ -98,11 +118,6 @@ if eng.rank == 0:
     np.save(out, eng.sd_full.reorder_output(eng.u_out))
 eng.close()
 '''
-
-
-def _ngpu():
-    import torch
-    return torch.cuda.device_count()
 
 
 @pytest.mark.parametrize("name,precision,overlap", (("cart_lossy_mb11", 1, 1), ("cart_lossy_mb11", 2, 0), ("cart_tight", 2, 1), ("fcc2_lossy", 1, 1)))
