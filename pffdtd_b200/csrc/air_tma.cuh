@@ -1072,9 +1072,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
    X(12, 1, 14, 6, 64, 32, true)  \
    X(13, 1, 14, 6, 64, 16, true)  \
    X(14, 1, 14, 6, 64, 8, true)   \
-   X(15, 1, 10, 6, 80, 32, true)  \
-   X(16, 1, 10, 6, 80, 16, true)  \
-   X(17, 1, 10, 6, 80, 8, true)
+   X(15, 1, 11, 6, 72, 32, true)  \
+   X(16, 1, 11, 6, 72, 16, true)  \
+   X(17, 1, 11, 6, 72, 8, true)
 #define PF_AIR_NCFG 18
 
 template <typename Real>

@@ -164,6 +164,7 @@ struct pffdtd_engine {
    cudaEvent_t ev_abc0 = nullptr, ev_abc1 = nullptr;
    // in-kernel boundary work (air_tma.cuh AirSvc): per tile-plane lists of the sparse rigid nodes + the shell's z faces, and the
    // dense remainder of the boundary list that stays with k_rigid
+   int mb_max = 0;  // largest branch count among the materials
    int svc_want = 1, svc_on = 0, svc_cap = 64;
    int svc_shell = 0;   // the lists hold the shell's z faces too (fused Cartesian step); otherwise rigid nodes only (any step)
    int bn_off_abc = 0;  // no boundary node is also an absorbing-shell node: the rigid update commutes with the shell update
@@ -442,8 +443,10 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
       const int k = d->mat_bnl[i];
       if (k < 0 || k >= d->Nm) return fail(PFFDTD_EINVAL, "mat_bnl[%lld]=%d out of range", (long long)i, k);
    }
-   for (int k = 0; k < d->Nm; k++)
+   for (int k = 0; k < d->Nm; k++) {
       if (d->Mb[k] < 0 || d->Mb[k] > PFFDTD_MMB) return fail(PFFDTD_EINVAL, "Mb[%d]=%d out of range", k, d->Mb[k]);
+      e->mb_max = std::max<int>(e->mb_max, d->Mb[k]);
+   }
 
 
    const i64 sx = e->Ny * e->Nzp, sy = e->Nzp;
@@ -909,7 +912,7 @@ struct Step {
          const size_t sm = (size_t)(nq / 4 * 5) * sizeof(Real);
          pf::k_fd<Real, PFFDTD_MMB><<<nblk(p.nbl, 128), 128, sm, s>>>(u0, e->bnl, e->matmb, (const Real *)e->lo2Kbg, (const Real *)e->facb,
                                                                       (Real *)e->hist[0], (Real *)e->hist[1], (Real *)e->vh1, (Real *)e->gh1,
-                                                                      p.l0, p.nbl, e->Nblp, (const Real *)e->quads, nq, e->d_n);
+                                                                      p.l0, p.nbl, e->Nblp, (const Real *)e->quads, nq, e->d_n, e->mb_max);
          e->launches += 1;
       }
       if (e->abc_pending) {  // join the absorbing-shell kernel running beside the boundary kernels

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(128) k_fd(Real *__restrict__ u0, const i64 *__
                                             const Real *__restrict__ lo2Kbg_bnl, const Real *__restrict__ fac_bnl,
                                             Real *__restrict__ hist0, Real *__restrict__ hist1, Real *__restrict__ vh1,
                                             Real *__restrict__ gh1, i64 i0, i64 n, i64 Nbl, const Real *__restrict__ quads, int nquads,
-                                            const i64 *__restrict__ d_n) {
+                                            const i64 *__restrict__ d_n, int mb_max) {
    constexpr int MB = 0;
    typedef Ops<Real> O;
    extern __shared__ __align__(16) unsigned char fd_smem[];
@@ -244,24 +244,27 @@ __global__ void __launch_bounds__(128) k_fd(Real *__restrict__ u0, const i64 *__
    const i64 i = i0 + n - 1 - ((i64)blockIdx.x * blockDim.x + threadIdx.x);  // descending, see k_rigid
    if (i < i0) return;
    Real *hist = (*d_n & 1) ? hist1 : hist0;  // the value two steps back lives in the buffer of the step's parity
-   const unsigned mm = matmb[i];
-   const int Mb = MB > 0 ? MB : (int)(mm >> 8);
-   const Real *q = qs + (mm & 0xffu) * (MMB * 5);
-   // everything this node needs from memory is requested up front; the dependent gather (index -> u0) first
+   // everything this node needs from memory is requested up front and nothing waits for anything else: the state loads are
+   // predicated on the LARGEST branch count of the problem's materials (a kernel argument; the arrays hold MMB branches for every
+   // node, unused ones zero), not on this node's own count, which is itself a load (round 1: the 2*Mb state loads of a thread were
+   // issued only after its material word had arrived); the one dependent load, index -> u0, goes last
    const i64 c = bnl[i];
-   const Real u0c = u0[c];
+   const unsigned mm = matmb[i];
    constexpr int NB = MB > 0 ? MB : MMB;
    Real v1[NB], g1[NB];
    Real *pv = vh1 + i, *pg = gh1 + i;
 #pragma unroll
    for (int m = 0; m < NB; m++) {
-      if (MB > 0 || m < Mb) {
+      if (m < mb_max) {
          v1[m] = pv[(i64)m * Nbl];
          g1[m] = pg[(i64)m * Nbl];
       }
    }
    const Real lo2Kbg = lo2Kbg_bnl[i], fac = fac_bnl[i];
    const Real u2 = hist[i];
+   const Real u0c = u0[c];
+   const int Mb = MB > 0 ? MB : (int)(mm >> 8);
+   const Real *q = qs + (mm & 0xffu) * (MMB * 5);
    const Real den = O::add(one, lo2Kbg);
    Real u = O::div(O::add(u0c, O::mul(lo2Kbg, u2)), den);
 #pragma unroll
