@@ -274,6 +274,7 @@ template <typename Real>
 struct AirEdge {
    int fuse, x_lo, x_hi, Nx;
    float negzero;  // -0.0f, opaque to the compiler: the addend that makes fma.rn.f32x2 a multiplication (see "packed fp32 arithmetic")
+   int folded;  // folded FCC grid (fcc_flag 2): seam row instead of a mirror / shell at the high y end
    int zstash;  // the consumers stash the pre-update values of the shell's z faces for k_abc_faces (0 when the service warp does them)
    Real sl2;    // rigid update: b1 = 2 - sl2*K
    // pre-update values of the shell nodes, for k_abc_faces:
@@ -336,7 +337,9 @@ struct FacesArgs {
    Real *u0;
    const Real *zold, *yold, *xold;
    int Nx, Ny, Nz, Nzp, xb, xe, x_lo, x_hi;
-   int do_z;  // 0: the z faces were finished inside the air kernel (service warp)
+   int do_z;    // 0: the z faces were finished inside the air kernel (service warp)
+   int folded;  // folded FCC grid: no shell and no mirror at the high y end, row Ny-2 is copied to the seam row Ny-1
+   int edges;   // 13-point stencil: halo edges are read too, a changed node is copied to its doubly mirrored positions as well
    Real lQ1, lQ2, lQ3;
 };
 template <typename Real>
@@ -351,16 +354,17 @@ __global__ void k_abc_faces(const FacesArgs<Real> a) {
    int x, y, z;
    Real old;
    auto on_xshell = [&](int xx) { return (a.x_lo && xx == 1) || (a.x_hi && xx == a.Nx - 2); };
+   const bool fold = a.folded != 0;
    if (t < nZ) {
       const i64 row = t >> 1;
       x = a.xb + (int)(row / a.Ny), y = (int)(row % a.Ny), z = (t & 1) ? a.Nz - 2 : 1;
-      if (y < 2 || y > a.Ny - 3 || on_xshell(x)) return;
+      if (y < 2 || y > (fold ? a.Ny - 2 : a.Ny - 3) || on_xshell(x)) return;
       old = a.zold[((i64)x * a.Ny + y) * 2 + (t & 1)];
    } else if (t < nZ + nY) {
       const i64 q = t - nZ;
       const int side = (int)((q / a.Nz) & 1);
       x = a.xb + (int)(q / (2 * (i64)a.Nz)), y = side ? a.Ny - 2 : 1, z = (int)(q % a.Nz);
-      if (z < 1 || z > a.Nz - 2 || on_xshell(x)) return;
+      if (z < 1 || z > a.Nz - 2 || on_xshell(x) || (fold && side)) return;
       old = a.yold[((i64)x * 2 + side) * a.Nzp + z];
    } else if (t < nZ + nY + nX) {
       const i64 q = t - nZ - nY;
@@ -374,20 +378,29 @@ __global__ void k_abc_faces(const FacesArgs<Real> a) {
    } else {
       return;
    }
-   const int Q = (on_xshell(x) ? 1 : 0) + ((y == 1 || y == a.Ny - 2) ? 1 : 0) + ((z == 1 || z == a.Nz - 2) ? 1 : 0);
+   const int Q = (on_xshell(x) ? 1 : 0) + ((y == 1 || (!fold && y == a.Ny - 2)) ? 1 : 0) + ((z == 1 || z == a.Nz - 2) ? 1 : 0);
    const Real lQ = Q == 1 ? a.lQ1 : (Q == 2 ? a.lQ2 : a.lQ3);
    const i64 P = (i64)a.Ny * a.Nzp;
    Real *p = a.u0 + ((i64)x * a.Ny + y) * a.Nzp + z;
    const Real num = O::add(*p, O::mul(lQ, old));
    const Real v = (Real)__ddiv_rn((double)num, __dadd_rn(1.0, (double)lQ));
    *p = v;
-   // halo mirrors of the changed node (faces only; the 7-point stencil never reads halo edges)
-   if (z == 2) p[-2] = v;
-   if (z == a.Nz - 3) p[2] = v;
-   if (y == 2) p[-2 * (i64)a.Nzp] = v;
-   if (y == a.Ny - 3) p[2 * (i64)a.Nzp] = v;
-   if (a.x_lo && x == 2) p[-2 * P] = v;
-   if (a.x_hi && x == a.Nx - 3) p[2 * P] = v;
+   // halo mirrors of the changed node: one copy per axis on which its index is 2 / N-3 (the seam copy for row Ny-2 of a folded
+   // grid); the 13-point stencil also reads halo edges, so there the copies combine
+   const i64 oz[3] = {0, z == 2 ? -2 : 0, z == a.Nz - 3 ? 2 : 0};
+   const i64 oy[3] = {0, y == 2 ? -2 * (i64)a.Nzp : 0, fold ? (y == a.Ny - 2 ? (i64)a.Nzp : 0) : (y == a.Ny - 3 ? 2 * (i64)a.Nzp : 0)};
+   const i64 ox[3] = {0, (a.x_lo && x == 2) ? -2 * P : 0, (a.x_hi && x == a.Nx - 3) ? 2 * P : 0};
+#pragma unroll
+   for (int ix = 0; ix < 3; ix++)
+#pragma unroll
+      for (int iy = 0; iy < 3; iy++)
+#pragma unroll
+         for (int iz = 0; iz < 3; iz++) {
+            const int axes = (ix ? 1 : 0) + (iy ? 1 : 0) + (iz ? 1 : 0);
+            if (axes == 0 || (ix && !ox[ix]) || (iy && !oy[iy]) || (iz && !oz[iz])) continue;
+            if (axes > 1 && !a.edges) continue;
+            p[ox[ix] + oy[iy] + oz[iz]] = v;
+         }
 }
 
 // ---------------------------------------------------------------- the kernel (7-point Cartesian)
@@ -622,7 +635,8 @@ __global__ void __maxnreg__(MAXR)
       // Roles of the fused step:
       //   zlo_tile / zhi_tile (warp-uniform): the tile holds the low / high z end;
       //   khs, khm (per thread): position of z=Nz-2 (shell) and z=Nz-3 (mirror source) in this vector, else -1;
-      //   yrole (per row, 3 bits each): bit0 row on the y shell, bit1 y==2, bit2 y==Ny-3 (mirror sources)
+      //   yrole (per row, 4 bits each): bit0 row on the y shell, bit1 y==2, bit2 y==Ny-3 (mirror sources), bit3 y==Ny-2 of a folded
+      //   FCC grid (the seam: its row is copied to Ny-1; the folded grid has neither a shell nor a mirror at its high y end)
       const bool zlo_tile = fuse && sg.z0 == 0;
       const bool zhi_tile = fuse && sg.z0 + TZ > Nz - 3;
       const int khs = (unsigned)(Nz - 2 - zv) < (unsigned)VEC ? Nz - 2 - zv : -1;
@@ -632,9 +646,88 @@ __global__ void __maxnreg__(MAXR)
 #pragma unroll
          for (int r = 0; r < RPT; r++) {
             const int y = ybase + r;
-            yrole |= (((y == 1 || y == Ny - 2) ? 1u : 0u) | (y == 2 ? 2u : 0u) | (y == Ny - 3 ? 4u : 0u)) << (3 * r);
+            const bool fold = eg.folded != 0;
+            yrole |= (((y == 1 || (!fold && y == Ny - 2)) ? 1u : 0u) | (y == 2 ? 2u : 0u) | ((!fold && y == Ny - 3) ? 4u : 0u) |
+                      ((fold && y == Ny - 2) ? 8u : 0u))
+                     << (4 * r);
          }
       }
+
+      // ---- the end of a row-vector's update, shared by the 7-point and the 13-point paths: the fused step's extras, then the
+      // stores.  `o` = the new values (masked elements carry their stage value), `u0v` = the old ones.
+      //  * rows / planes on the absorbing shell keep the plain air value and stash their old values for k_abc_faces;
+      //  * mirror-on-write: whoever holds index 2 / N-3 of an axis also writes the halo at 0 / N-1 -- inside the vector (or by a
+      //    shuffle / one scalar store) for z, as whole-row copies for y and x; the 13-point stencil also reads halo EDGES, so its
+      //    x copies carry the y copies too (the row vector already carries the z mirror); the seam row of a folded grid is one
+      //    more row copy.
+      // Everything lane-dependent is written as selects / single predicated stores: a divergent branch here would make the
+      // one lane at a z end run the rest of the step on its own.
+      auto emit = [&](const int r, const int x, const unsigned xrole, const unsigned am, Real(&o)[VEC], const Real(&u0v)[VEC], Real *dst,
+                      Real *zo) {
+         const unsigned yr = (yrole >> (4 * r)) & 15u;
+         const bool shell = ((yr | xrole) & 1u) != 0;  // uniform within a row group
+         if (shell) {
+            // row / plane on the absorbing shell: one extra vector store (the planes on the x shell take precedence)
+            Real *sp = (xrole & 1u) ? eg.xold + (((i64)(x == 1 ? 0 : 1) * Ny + (ybase + r)) * Nzp + zv)
+                                    : eg.yold + ((((i64)x * 2 + ((ybase + r) == 1 ? 0 : 1)) * Nzp) + zv);
+            st_vec<Real, VEC>(sp, u0v);
+         }
+         // Mirror targets that live in ANOTHER active lane's vector are delivered by a shuffle (that lane stores
+         // its whole vector; a scalar store from here would race with it); only a target in a vector nobody
+         // stores (the row's far padding) is written directly.
+         __syncwarp(am);  // the row groups may have diverged on `shell`
+         if (zlo_tile) {  // warp-uniform: the tile starts at z = 0
+            // lane 0 holds z=1 (shell): stash its pre-update value; z=2 -> z=0 mirror
+            if (eg.zstash && lz == 0 && !shell) zo[0] = u0v[1];
+            if constexpr (VEC >= 4) {
+               o[0] = (lz == 0) ? o[2] : o[0];
+            } else {
+               const Real t = __shfl_down_sync(am, o[0], 1);  // fp64: z=2 is the first element of the next lane
+               o[0] = (lz == 0) ? t : o[0];
+            }
+         }
+         Real vm = o[0];  // value of z = Nz-3 if this thread holds it
+         if (zhi_tile) {  // warp-uniform: the tile contains z = Nz-3 .. Nz-1
+            Real vs = u0v[0];
+#pragma unroll
+            for (int k = 1; k < VEC; k++) {
+               vs = (k == khs) ? u0v[k] : vs;
+               vm = (k == khm) ? o[k] : vm;
+            }
+            if (eg.zstash && khs >= 0 && !shell) zo[1] = vs;  // z = Nz-2 (shell)
+#pragma unroll
+            for (int k = 0; k + 2 < VEC; k++) o[k + 2] = (k == khm) ? o[k] : o[k + 2];  // z=Nz-3 -> z=Nz-1 inside the vector
+            // a vector that starts at z=Nz-2 holds z=Nz-1 as element 1 and finds z=Nz-3 at the end of the previous lane's
+            // (never the first vector of a tile: the engine refuses the fused step for such grids, AirTma::z_edge)
+            __syncwarp(am);
+            const Real t = __shfl_up_sync(am, o[VEC - 1], 1);
+            o[1] = (khs == 0) ? t : o[1];
+         }
+         // Every vector of an active row is stored, fully masked ones too: it may hold the z halo (mirror-on-write: a masked
+         // node at z = 1 / Nz-2 must not keep the halo next to it from being refreshed) or a node the service warp finished
+         // in the stage.  Masked elements carry their stage value.
+         const bool tailz = zhi_tile && khm + 2 == VEC;  // z=Nz-1 opens the next vector, which nobody stores
+         st_vec<Real, VEC>(dst, o);
+         if (tailz) dst[VEC] = vm;
+         if (((yr | xrole) & 14u) != 0u) {
+            // mirror source of a y / x halo (or the seam): the same row goes there as well (warp-uniform, a few rows / planes)
+#pragma unroll 1
+            for (int tx = 0; tx < 3; tx++) {
+               const bool xon = tx == 0 || (tx == 1 ? (xrole & 2u) != 0 : (xrole & 4u) != 0);
+               const i64 xo = tx == 0 ? 0 : (tx == 1 ? -2 * jb.plane : 2 * jb.plane);
+#pragma unroll 1
+               for (int ty = 0; ty < 4; ty++) {
+                  const bool yon = ty == 0 || (ty == 1 ? (yr & 2u) != 0 : ty == 2 ? (yr & 4u) != 0 : (yr & 8u) != 0);
+                  const i64 yo = ty == 0 ? 0 : (ty == 1 ? -2 * (i64)Nzp : ty == 2 ? 2 * (i64)Nzp : (i64)Nzp);
+                  if (xon && yon && (tx | ty) != 0 && (FCC || tx == 0 || ty == 0)) {
+                     Real *d = dst + xo + yo;
+                     st_vec<Real, VEC>(d, o);
+                     if (tailz) d[VEC] = vm;
+                  }
+               }
+            }
+         }
+      };
 
       if constexpr (FCC) {
          // ---- 13-point FCC (cpu_engine.h:205-216; the same stencil on the checkerboard and on the folded grid):
@@ -682,6 +775,10 @@ __global__ void __maxnreg__(MAXR)
             }
             Real *u0p = u0g + ((i64)sg.xa * Ny + ybase) * Nzp + zv;
             for (int j = 0; j < sg.cnt; j++) {
+               const int x = sg.xa + j;
+               const unsigned xrole = !fuse ? 0u
+                                            : ((((eg.x_lo && x == 1) || (eg.x_hi && x == eg.Nx - 2)) ? 1u : 0u) | ((eg.x_lo && x == 2) ? 2u : 0u) |
+                                               ((eg.x_hi && x == eg.Nx - 3) ? 4u : 0u));
                Ring gu = gc;  // plane x+1
                gu.next();
                wait_full(gu);
@@ -744,7 +841,11 @@ __global__ void __maxnreg__(MAXR)
                      p = O::add(p, (k < VEC - 1) ? m1[k + 1 < VEC ? k + 1 : k] : m1r);  // -x +z
                      o[k] = ((m >> k) & 1u) ? u0v[k] : p;
                   }
-                  if (r < nrow && (SVC || m != VMASK)) st_vec<Real, VEC>(u0p + (i64)r * Nzp, o);
+                  if (r < nrow) {
+                     const unsigned am = __activemask();
+                     if (fuse) emit(r, x, xrole, am, o, u0v, u0p + (i64)r * Nzp, nullptr);
+                     else if (SVC || m != VMASK) st_vec<Real, VEC>(u0p + (i64)r * Nzp, o);
+                  }
                   qm0[r] = qc0[r], qm1[r] = qc1[r], qm2[r] = qc2[r];
                   qc0[r] = qp0, qc1[r] = qp1, qc2[r] = qp2, ac1[r] = an1;
                }
@@ -779,6 +880,10 @@ __global__ void __maxnreg__(MAXR)
          }
          Real *u0p = u0g + ((i64)sg.xa * Ny + ybase) * Nzp + zv;
          for (int j = 0; j < sg.cnt; j++) {
+            const int x = sg.xa + j;
+            const unsigned xrole = !fuse ? 0u
+                                      : ((((eg.x_lo && x == 1) || (eg.x_hi && x == eg.Nx - 2)) ? 1u : 0u) | ((eg.x_lo && x == 2) ? 2u : 0u) |
+                                      ((eg.x_hi && x == eg.Nx - 3) ? 4u : 0u));
             Ring gu = gc;  // plane x+1
             gu.next();
             wait_full(gu);
@@ -828,7 +933,11 @@ __global__ void __maxnreg__(MAXR)
                      o[k] = ((m >> k) & 1u) ? u0v[k] : p;
                   }
                   // (also a fully masked vector is stored: the service warp may have finished one of its nodes in the stage)
-                  if (r < nrow && (SVC || m != VMASK)) st_vec<Real, VEC>(u0p + (i64)r * Nzp, o);
+                  if (r < nrow) {
+                     const unsigned am = __activemask();
+                     if (fuse) emit(r, x, xrole, am, o, u0v, u0p + (i64)r * Nzp, nullptr);
+                     else if (SVC || m != VMASK) st_vec<Real, VEC>(u0p + (i64)r * Nzp, o);
+                  }
                }
 #pragma unroll
                for (int k = 0; k < VEC; k++) {
@@ -961,67 +1070,7 @@ __global__ void __maxnreg__(MAXR)
                      o[k] = ((m >> k) & 1u) ? u0v[k] : p;
                   }
                }
-               Real *dst = u0p + (i64)r * Nzp;
-               const unsigned rrole = ((yrole >> (3 * r)) & 7u) | xrole;  // uniform within a row group
-               // Fused extras.  Everything lane-dependent below is written as selects / single predicated stores:
-               // a divergent branch here would make the one lane at a z end run the rest of the step on its own.
-               const bool shell = (rrole & 1u) != 0;
-               if (shell) {
-                  // row / plane on the absorbing shell: keep the plain air value, stash the pre-update values for
-                  // k_abc_faces (one extra vector store; the planes on the x shell take precedence)
-                  Real *sp = (xrole & 1u) ? eg.xold + (((i64)(x == 1 ? 0 : 1) * Ny + (ybase + r)) * Nzp + zv)
-                                          : eg.yold + ((((i64)x * 2 + ((ybase + r) == 1 ? 0 : 1)) * Nzp) + zv);
-                  st_vec<Real, VEC>(sp, u0v);
-               }
-               // Mirror targets that live in ANOTHER active lane's vector are delivered by a shuffle (that lane stores
-               // its whole vector; a scalar store from here would race with it); only a target in a vector nobody
-               // stores (the row's far padding) is written directly.
-               __syncwarp(am);  // the row groups may have diverged on `shell`
-               if (zlo_tile) {  // warp-uniform: the tile starts at z = 0
-                  // lane 0 holds z=1 (shell): stash its pre-update value; z=2 -> z=0 mirror
-                  if (eg.zstash && lz == 0 && !shell) zop[2 * r] = u0v[1];
-                  if constexpr (VEC >= 4) {
-                     o[0] = (lz == 0) ? o[2] : o[0];
-                  } else {
-                     const Real t = __shfl_down_sync(am, o[0], 1);  // fp64: z=2 is the first element of the next lane
-                     o[0] = (lz == 0) ? t : o[0];
-                  }
-               }
-               Real vm = o[0];  // value of z = Nz-3 if this thread holds it
-               if (zhi_tile) {  // warp-uniform: the tile contains z = Nz-3 .. Nz-1
-                  Real vs = u0v[0];
-#pragma unroll
-                  for (int k = 1; k < VEC; k++) {
-                     vs = (k == khs) ? u0v[k] : vs;
-                     vm = (k == khm) ? o[k] : vm;
-                  }
-                  if (eg.zstash && khs >= 0 && !shell) zop[2 * r + 1] = vs;  // z = Nz-2 (shell)
-#pragma unroll
-                  for (int k = 0; k + 2 < VEC; k++) o[k + 2] = (k == khm) ? o[k] : o[k + 2];  // z=Nz-3 -> z=Nz-1 inside the vector
-                  // a vector that starts at z=Nz-2 holds z=Nz-1 as element 1 and finds z=Nz-3 at the end of the previous lane's
-                  // (never the first vector of a tile: the engine refuses the fused step for such grids, AirTma::z_edge)
-                  __syncwarp(am);
-                  const Real t = __shfl_up_sync(am, o[VEC - 1], 1);
-                  o[1] = (khs == 0) ? t : o[1];
-               }
-               // Every vector of an active row is stored, fully masked ones too: it may hold the z halo (mirror-on-write: a masked
-               // node at z = 1 / Nz-2 must not keep the halo next to it from being refreshed) or a node the service warp finished
-               // in the stage.  Masked elements carry their stage value.
-               st_vec<Real, VEC>(dst, o);
-               if (zhi_tile && khm + 2 == VEC) dst[VEC] = vm;  // z=Nz-1 opens the next vector, which nobody stores
-               if (rrole & 6u) {
-                  // mirror source of a y / x halo: the same row goes there as well (warp-uniform, a few rows / planes)
-                  const int y = ybase + r;
-#pragma unroll 1
-                  for (int t = 1; t < 5; t++) {
-                     const bool on = t == 1 ? y == 2 : t == 2 ? y == Ny - 3 : t == 3 ? (xrole & 2u) != 0 : (xrole & 4u) != 0;
-                     if (on) {
-                        Real *d = dst + (t == 1 ? -2 * (i64)Nzp : t == 2 ? 2 * (i64)Nzp : t == 3 ? -2 * jb.plane : 2 * jb.plane);
-                        st_vec<Real, VEC>(d, o);
-                        if (zhi_tile && khm + 2 == VEC) d[VEC] = vm;
-                     }
-                  }
-               }
+               emit(r, x, xrole, am, o, u0v, u0p + (i64)r * Nzp, zop + 2 * r);
             }
          }
          release(gc);  // plane x's stage may be refilled; x-1 and x+1 live in registers / the next stage

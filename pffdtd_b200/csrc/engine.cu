@@ -127,6 +127,8 @@ struct pffdtd_engine {
    i64 *d_n = nullptr;   // device step counter read by k_io / k_fd
    i64 n_dev = -1;       // value the host knows it holds (-1 unknown)
    cudaGraphExec_t graph[2] = {nullptr, nullptr};  // two consecutive steps starting with cur = 0 / 1
+   cudaGraphExec_t graphA[2] = {nullptr, nullptr}, graphB[2] = {nullptr, nullptr};  // NCCL slabs: one step's work before / after the exchange
+   double graphA_launches[2] = {0, 0}, graphB_launches[2] = {0, 0};
    cudaGraphExec_t hgraph[2] = {nullptr, nullptr};  // one host-driven step (H2D samples, step, D2H samples) with cur = 0 / 1
    double hgraph_launches[2] = {0, 0};
    void *in_stage = nullptr, *out_stage = nullptr;  // device staging of one step's source / receiver samples
@@ -288,6 +290,8 @@ extern "C" int pffdtd_destroy(pffdtd_engine *e) {
    for (int c = 0; c < 2; c++) {
       if (e->graph[c]) cudaGraphExecDestroy(e->graph[c]);
       if (e->hgraph[c]) cudaGraphExecDestroy(e->hgraph[c]);
+      if (e->graphA[c]) cudaGraphExecDestroy(e->graphA[c]);
+      if (e->graphB[c]) cudaGraphExecDestroy(e->graphB[c]);
    }
    if (e->ev_abc0) cudaEventDestroy(e->ev_abc0);
    if (e->ev_abc1) cudaEventDestroy(e->ev_abc1);
@@ -313,7 +317,9 @@ extern "C" int pffdtd_destroy(pffdtd_engine *e) {
 // Rigid nodes may go to the service warp whenever no boundary node is a shell node (bn_off_abc); the shell's z faces go with them
 // when the step is the fused Cartesian one (then the air kernel stashes nothing for them and k_abc_faces skips them).
 static bool step_fused(const pffdtd_engine *e) {
-   return e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge && !e->energy_on;
+   // (the 13-point kernel has no stash for the shell's z faces: its fused step needs the service warp to do them)
+   const bool fcc_ok = e->fcc == 0 || (e->svc_want && e->tma.svc && e->bn_off_abc && e->abc_disjoint);
+   return e->fuse && e->fuse_ok && fcc_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge && !e->energy_on;
 }
 static bool svc_eligible(const pffdtd_engine *e) { return e->svc_want && e->bn_off_abc && e->tma.ok && e->tma.svc && !e->energy_on; }
 static int build_service(pffdtd_engine *e) {
@@ -322,7 +328,8 @@ static int build_service(pffdtd_engine *e) {
    e->svc_on = 0, e->Nb_left = e->nbL_lo = e->nbL_hi = e->svc_entries = 0;
    e->tma.sv = pf::AirSvc{nullptr, nullptr, 0};
    if (!svc_eligible(e)) return 0;
-   const bool with_shell = e->fcc == 0 && step_fused(e) && e->abc_disjoint;
+   const bool with_shell = step_fused(e) && e->abc_disjoint;
+   const bool fold = e->fcc == 2, checker = e->fcc == 1;
    e->svc_shell = with_shell;
    const i64 Nx = e->Nx, Ny = e->Ny, Nz = e->Nz, Nzp = e->Nzp, TY = e->tma.ty, TZ = e->tma.tzn;
    const i64 tzc = (Nz - 1 + TZ - 1) / TZ, tyc = (Ny - 2 + TY - 1) / TY, ntile = tzc * tyc, pitch = Nx + 1;
@@ -346,23 +353,26 @@ static int build_service(pffdtd_engine *e) {
    }
    // shell rows of a tile row: y in [2, Ny-3]
    auto shell_rows = [&](i64 ty, i64 *ya, i64 *yb) {
-      *ya = std::max<i64>(2, 1 + ty * TY), *yb = std::min<i64>(Ny - 3, ty * TY + TY);
+      *ya = std::max<i64>(2, 1 + ty * TY), *yb = std::min<i64>(fold ? Ny - 2 : Ny - 3, ty * TY + TY);
    };
    auto on_xshell = [&](i64 ix) { return (e->x_lo_edge && ix == 1) || (e->x_hi_edge && ix == Nx - 2); };
    const i64 tz_hi = (Nz - 2) / TZ;
+   auto shell_node = [&](i64 x, i64 y, i64 z) { return !checker || ((e->ix0 + x + y + z) & 1) == 0; };  // (stored nodes of the layout)
    // a tile-plane's entries travel into its shared-memory stage (PF_SVC_CAP of them at most, segments padded to 16 bytes)
-   const uint32_t cap = (uint32_t)std::max<i64>(0, std::min<i64>(e->svc_cap, PF_SVC_CAP - 2 * TY));
+   const uint32_t cap = (uint32_t)std::max<i64>(0, std::min<i64>(e->svc_cap, PF_SVC_CAP - (with_shell ? 2 * TY : 0)));
    std::vector<uint32_t> off((size_t)(ntile * pitch), 0u);
    uint64_t total = 0;
    for (i64 t = 0; t < ntile; t++) {
       const i64 ty = t / tzc, tz = t - ty * tzc;
       i64 ya, yb;
       shell_rows(ty, &ya, &yb);
-      const i64 nshell = !with_shell ? 0 : std::max<i64>(0, yb - ya + 1) * ((tz == 0 ? 1 : 0) + (tz == tz_hi ? 1 : 0));
       for (i64 x = 0; x <= Nx; x++) {
          off[(size_t)(t * pitch + x)] = (uint32_t)total;
          if (x >= 1 && x <= Nx - 2) {
-            uint64_t n = on_xshell(x) ? 0 : (uint64_t)nshell;
+            uint64_t n = 0;
+            if (with_shell && !on_xshell(x))
+               for (i64 y = ya; y <= yb; y++)
+                  n += ((tz == 0 && shell_node(x, y, 1)) ? 1 : 0) + ((tz == tz_hi && shell_node(x, y, Nz - 2)) ? 1 : 0);
             const uint32_t k = cnt[(size_t)(t * pitch + x)];
             if (k <= cap) n += k;
             total += (n + 3) / 4 * 4;
@@ -382,8 +392,8 @@ static int build_service(pffdtd_engine *e) {
          uint32_t &f = fill[(size_t)(t * pitch + x)];
          for (i64 y = ya; y <= yb; y++) {
             const uint32_t r = (uint32_t)(y - 1 - ty * TY);
-            if (tz == 0) list[f++] = (1u << 13) | (r << 7) | 1u;
-            if (tz == tz_hi) list[f++] = (1u << 13) | (r << 7) | (uint32_t)(Nz - 2 - tz * TZ);
+            if (tz == 0 && shell_node(x, y, 1)) list[f++] = (1u << 13) | (r << 7) | 1u;
+            if (tz == tz_hi && shell_node(x, y, Nz - 2)) list[f++] = (1u << 13) | (r << 7) | (uint32_t)(Nz - 2 - tz * TZ);
          }
       }
    }
@@ -546,27 +556,39 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
       CU(cudaGetLastError());
    }
    // can the tiled kernel apply the absorbing shell itself?  Only if the list handed in is exactly the
-   // canonical shell of this slab (fdtd_data.h:620-675) -- every interior node with an index of 1 or N-2.
-   if (e->fcc == 0) {
+   // canonical shell of this slab (fdtd_data.h:620-675): every interior node with an index of 1 or N-2 -- on the checkerboard FCC grid
+   // the even-parity ones, on the folded FCC grid every stored node, whose y shell is row 1 alone (both physical y faces fold onto
+   // it; the high end of the folded grid is the seam).
+   {
       const i64 Nx = e->Nx, Ny = e->Ny, Nz = e->Nz;
+      const bool fold = e->fcc == 2, checker = e->fcc == 1;
       auto qx = [&](i64 ix) { return ((e->x_lo_edge && ix == 1) || (e->x_hi_edge && ix == Nx - 2)) ? 1 : 0; };
+      auto qy = [&](i64 iy) { return (iy == 1 || (!fold && iy == Ny - 2)) ? 1 : 0; };
+      auto qz = [&](i64 iz) { return (iz == 1 || iz == Nz - 2) ? 1 : 0; };
+      auto even = [&](i64 ix, i64 iy, i64 iz) { return !checker || ((e->ix0 + ix + iy + iz) & 1) == 0; };
       i64 expect = 0;
-      for (i64 ix = 1; ix <= Nx - 2; ix++) {
-         const i64 inner = (Ny - 4) * (Nz - 4);  // nodes of the plane with neither y nor z on the shell
-         expect += qx(ix) ? (Ny - 2) * (Nz - 2) : (Ny - 2) * (Nz - 2) - std::max<i64>(inner, 0);
-      }
+      for (i64 ix = 1; ix <= Nx - 2; ix++)
+         for (i64 iy = 1; iy <= Ny - 2; iy++) {
+            if (qx(ix) || qy(iy)) {
+               if (!checker) expect += Nz - 2;
+               else
+                  for (i64 iz = 1; iz <= Nz - 2; iz++) expect += even(ix, iy, iz) ? 1 : 0;
+            } else {
+               expect += (even(ix, iy, 1) ? 1 : 0) + ((Nz - 2 != 1 && even(ix, iy, Nz - 2)) ? 1 : 0);
+            }
+         }
       bool ok = (Ny >= 4 && Nz >= 4) && expect == e->Nba && ascending(d->bna_ixyz, e->Nba);
       for (i64 i = 0; ok && i < e->Nba; i++) {
          const i64 v = d->bna_ixyz[i], row = v / Nz, iz = v - row * Nz, ix = row / Ny, iy = row - ix * Ny;
-         const int Q = qx(ix) + ((iy == 1 || iy == Ny - 2) ? 1 : 0) + ((iz == 1 || iz == Nz - 2) ? 1 : 0);
-         ok = Q > 0 && Q == d->Q_bna[i];
+         const int Q = qx(ix) + qy(iy) + qz(iz);
+         ok = Q > 0 && Q == d->Q_bna[i] && even(ix, iy, iz);
       }
       e->fuse_ok = ok;
       // do boundary / source nodes stay clear of the shell (the usual case; the reference's Python engine assumes it,
-      // sim_fdtd.py:152)?  Then the shell kernel may run beside the boundary kernels.
+      // sim_fdtd.py:152)?  Then the shell update commutes with the boundary kernels.
       auto on_shell = [&](i64 v) {
          const i64 row = v / Nz, iz = v - row * Nz, ix = row / Ny, iy = row - ix * Ny;
-         return qx(ix) || iy == 1 || iy == Ny - 2 || iz == 1 || iz == Nz - 2;
+         return qx(ix) || qy(iy) || qz(iz);
       };
       bool clear = ok;
       for (i64 i = 0; clear && i < e->Nb; i++) clear = !on_shell(d->bn_ixyz[i]);
@@ -581,8 +603,9 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
       for (i64 i = 0; off && i < e->Nb; i++) off = !((bits[(size_t)(d->bn_ixyz[i] >> 3)] >> (d->bn_ixyz[i] & 7)) & 1u);
       e->bn_off_abc = off;
    }
-   // late halo mirrors: nodes written after the air kernel (boundary, source) whose value belongs in a halo
-   if (e->fcc == 0) {
+   // late halo mirrors: nodes written after the air kernel (boundary, source) whose value belongs in a halo (all the combinations:
+   // the 13-point stencil reads halo edges; on the folded grid row Ny-2 goes to the seam row Ny-1 and the high y end has no mirror)
+   {
       std::vector<std::pair<i64, i64>> pr;  // (src, dst) in the padded layout
       auto add_node = [&](i64 v) {
          const i64 row = v / e->Nz, iz = v - row * e->Nz, ix = row / e->Ny, iy = row - ix * e->Ny;
@@ -593,7 +616,8 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
          if (e->x_hi_edge && ix == e->Nx - 3) ox[nx++] = e->Nx - 1;
          oy[ny++] = iy;
          if (iy == 2) oy[ny++] = 0;
-         if (iy == e->Ny - 3) oy[ny++] = e->Ny - 1;
+         if (e->fcc != 2 && iy == e->Ny - 3) oy[ny++] = e->Ny - 1;
+         if (e->fcc == 2 && iy == e->Ny - 2) oy[ny++] = e->Ny - 1;
          oz[nz++] = iz;
          if (iz == 2) oz[nz++] = 0;
          if (iz == e->Nz - 3) oz[nz++] = e->Nz - 1;
@@ -689,7 +713,9 @@ static void drop_graphs(pffdtd_engine *e) {
    for (int c = 0; c < 2; c++) {
       if (e->graph[c]) cudaGraphExecDestroy(e->graph[c]);
       if (e->hgraph[c]) cudaGraphExecDestroy(e->hgraph[c]);
-      e->graph[c] = e->hgraph[c] = nullptr;
+      if (e->graphA[c]) cudaGraphExecDestroy(e->graphA[c]);
+      if (e->graphB[c]) cudaGraphExecDestroy(e->graphB[c]);
+      e->graph[c] = e->hgraph[c] = e->graphA[c] = e->graphB[c] = nullptr;
    }
 }
 
@@ -786,7 +812,7 @@ extern "C" int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out) {
       pf::air_cfg_shape(e->tma.cfg, &rpt, &nw, &lz);
       *out = e->tma.ok ? lz : 0;
    } else if (k == "Nzp") *out = (double)e->Nzp;
-   else if (k == "fused") *out = (e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge && !e->energy_on) ? 1 : 0;
+   else if (k == "fused") *out = (step_fused(e) && (e->fcc == 0 || (e->svc_on && e->svc_shell))) ? 1 : 0;
    else if (k == "energy") *out = e->energy_on;
    else if (k == "mirror_pairs") *out = (double)e->np;
    else if (k == "abc_disjoint") *out = e->abc_disjoint;
@@ -850,7 +876,7 @@ struct Step {
          pf::AirEdge<Real> eg;
          memset(&eg, 0, sizeof eg);
          eg.fuse = fused, eg.x_lo = e->x_lo_edge, eg.x_hi = e->x_hi_edge, eg.Nx = (int)e->Nx;
-         eg.zstash = svc ? 0 : 1, eg.sl2 = (Real)e->sl2, eg.negzero = e->negzero;
+         eg.zstash = svc ? 0 : 1, eg.sl2 = (Real)e->sl2, eg.negzero = e->negzero, eg.folded = e->fcc == 2;
          eg.zold = (Real *)e->zold, eg.yold = (Real *)e->yold, eg.xold = (Real *)e->xold;
          // cpu_engine.h:226-228: Real lQ = l*Q; ... /(1.0 + lQ)
          eg.lQ1 = (Real)((Real)e->l * (Real)1), eg.lQ2 = (Real)((Real)e->l * (Real)2), eg.lQ3 = (Real)((Real)e->l * (Real)3);
@@ -873,7 +899,7 @@ struct Step {
          pf::FacesArgs<Real> fa;
          fa.u0 = u0, fa.zold = (const Real *)e->zold, fa.yold = (const Real *)e->yold, fa.xold = (const Real *)e->xold;
          fa.Nx = (int)e->Nx, fa.Ny = (int)e->Ny, fa.Nz = (int)e->Nz, fa.Nzp = (int)e->Nzp, fa.xb = (int)xb, fa.xe = (int)xe;
-         fa.x_lo = e->x_lo_edge, fa.x_hi = e->x_hi_edge, fa.do_z = svc ? 0 : 1;
+         fa.x_lo = e->x_lo_edge, fa.x_hi = e->x_hi_edge, fa.do_z = svc ? 0 : 1, fa.folded = e->fcc == 2, fa.edges = e->fcc != 0;
          fa.lQ1 = (Real)((Real)e->l * (Real)1), fa.lQ2 = (Real)((Real)e->l * (Real)2), fa.lQ3 = (Real)((Real)e->l * (Real)3);
          const i64 nt = (svc ? 0 : (xe - xb) * e->Ny * 2) + (xe - xb) * 2 * e->Nz + 2 * e->Ny * e->Nz;
          if (e->abc_overlap && e->abc_disjoint && !e->comm) {  // one GPU only: with slabs the edge parts order their work around the exchange
@@ -1076,10 +1102,21 @@ static int exchange(pffdtd_engine *e, void *unew, cudaStream_t s) {
    return 0;
 }
 
+// Phases of a step: PH_A the work before the halo exchange (with slabs: the two edge planes and everything that lives in them),
+// PH_X the exchange itself, PH_B the rest.  One call normally does all three.  A slab with an NCCL communicator replays PH_A and
+// PH_B from captured graphs and issues PH_X eagerly between them: NCCL send/recv captured INSIDE a graph hung on the 2-GPU box
+// (NCCL 2.28.9, B200), so the exchange stays outside the graphs.
+enum { PH_A = 1, PH_X = 2, PH_B = 4, PH_ALL = 7 };
+
+static bool step_split(const pffdtd_engine *e) {
+   const bool linked = e->comm || e->peer_lo || e->peer_hi;
+   return linked && (!e->x_lo_edge || !e->x_hi_edge) && e->overlap && e->sorted && e->Nx >= 5;
+}
+
 template <typename Real>
-static int step_impl(pffdtd_engine *e, i64 n) {
+static int step_impl(pffdtd_engine *e, i64 n, int phases) {
    if (n < 0 || n >= e->Nt) return fail(PFFDTD_EINVAL, "step %lld outside [0,%lld)", (long long)n, (long long)e->Nt);
-   const bool fused = step_fused(e);
+   const bool fused = step_fused(e) && (e->fcc == 0 || (e->svc_on && e->svc_shell));
    const bool svc = e->svc_on && e->air_kernel == 1 && (e->svc_shell != 0) == fused;
    Step<Real> st{e, (Real *)e->u[e->cur], (Real *)e->u[e->cur ^ 1], e->s_main, n, fused, svc};
    const i64 NB = svc ? e->Nb_left : e->Nb, nb_lo = svc ? e->nbL_lo : e->nb_lo, nb_hi = svc ? e->nbL_hi : e->nb_hi;
@@ -1087,78 +1124,95 @@ static int step_impl(pffdtd_engine *e, i64 n) {
    cudaStream_t s = e->s_main;
    const i64 Nx = e->Nx;
    int rc;
-
-   if (e->n_dev != n) {
-      pf::k_set_n<<<1, 1, 0, s>>>(e->d_n, n);
-      e->launches += 1;
-      e->n_dev = n;
-   }
-   // the halo planes of u1 come from the previous step's exchange
-   if (e->comm_pending) {
-      CU(cudaStreamWaitEvent(s, e->ev_comm, 0));
-      e->comm_pending = 0;
-   }
-   // (single process: the neighbours pushed them; their events were recorded when the host queued their previous step)
-   if (e->peer_lo && n > e->first_step) CU(cudaStreamWaitEvent(s, e->peer_lo->ev_push, 0));
-   if (e->peer_hi && n > e->first_step) CU(cudaStreamWaitEvent(s, e->peer_hi->ev_push, 0));
-   if (!fused) {
-      // 1. previous-state values at the ABC nodes; 2.+3. seam row and halo mirrors of u1
-      if (e->Nba) {
-         pf::k_gather<Real><<<nblk(e->Nba, 128), 128, 0, s>>>(u0, e->bna, (Real *)e->u2ba, e->Nba);
-         e->launches += 1;
-      }
-      mirror_pass<Real>(e, u1, s);
-      e->halo_dirty = 1;  // the state this step produces has no mirrored halos yet
-   } else if (e->halo_dirty) {
-      mirror_pass<Real>(e, u1, s);
-      e->halo_dirty = 0;
-   }
-   if (e->energy_on && (rc = energy_pre<Real>(e, u1, u0, n, s))) return rc;
    const bool linked = e->comm || e->peer_lo || e->peer_hi;
    const bool lo = linked && !e->x_lo_edge, hi = linked && !e->x_hi_edge;
-   const bool split = (lo || hi) && e->overlap && e->sorted && Nx >= 5;
-   if (split) {
-      // planes the neighbours need first, then the exchange on the comm stream while the interior runs
-      if (lo && (rc = st.part(Part{1, 2, 0, nb_lo, 0, e->nbl_lo, 0, e->nba_lo, 0, e->ns_lo, 0, e->np_lo, false}))) return rc;
-      if (hi && (rc = st.part(Part{Nx - 2, Nx - 1, NB - nb_hi, nb_hi, e->Nbl - e->nbl_hi, e->nbl_hi, e->Nba - e->nba_hi,
-                                   e->nba_hi, e->Ns - e->ns_hi, e->ns_hi, e->np - e->np_hi, e->np_hi, false})))
-         return rc;
-      CU(cudaGetLastError());
-      CU(cudaEventRecord(e->ev_edge, s));
-      CU(cudaStreamWaitEvent(e->s_comm, e->ev_edge, 0));
-      if ((rc = exchange(e, u0, e->s_comm))) return rc;
-      CU(cudaEventRecord(e->ev_comm, e->s_comm));
-      if (e->peer_lo || e->peer_hi) CU(cudaEventRecord(e->ev_push, e->s_comm));
-      e->comm_pending = 1;
-      const i64 b0 = lo ? nb_lo : 0, b1 = hi ? nb_hi : 0, l0 = lo ? e->nbl_lo : 0, l1 = hi ? e->nbl_hi : 0;
-      const i64 a0 = lo ? e->nba_lo : 0, a1 = hi ? e->nba_hi : 0, s0 = lo ? e->ns_lo : 0, s1 = hi ? e->ns_hi : 0;
-      const i64 p0 = lo ? e->np_lo : 0, p1 = hi ? e->np_hi : 0;
-      if ((rc = st.part(Part{lo ? 2 : 1, hi ? Nx - 2 : Nx - 1, b0, NB - b0 - b1, l0, e->Nbl - l0 - l1, a0, e->Nba - a0 - a1, s0,
-                             e->Ns - s0 - s1, p0, e->np - p0 - p1, true})))
-         return rc;
-      CU(cudaGetLastError());
-   } else {
-      if ((rc = st.part(Part{1, Nx - 1, 0, NB, 0, e->Nbl, 0, e->Nba, 0, e->Ns, 0, e->np, true}))) return rc;
-      CU(cudaGetLastError());
-      if ((rc = exchange(e, u0, s))) return rc;
-      if (e->peer_lo || e->peer_hi) CU(cudaEventRecord(e->ev_push, s));
+   const bool split = step_split(e);
+   // the step's opening belongs to PH_A when the step is split around the exchange, else to PH_B (PH_A is then empty)
+   if (phases & (split ? PH_A : PH_B)) {
+      if (e->n_dev != n) {
+         pf::k_set_n<<<1, 1, 0, s>>>(e->d_n, n);
+         e->launches += 1;
+         e->n_dev = n;
+      }
+      // the halo planes of u1 come from the previous step's exchange
+      if (e->comm_pending) {
+         CU(cudaStreamWaitEvent(s, e->ev_comm, 0));
+         e->comm_pending = 0;
+      }
+      // (single process: the neighbours pushed them; their events were recorded when the host queued their previous step)
+      if (e->peer_lo && n > e->first_step) CU(cudaStreamWaitEvent(s, e->peer_lo->ev_push, 0));
+      if (e->peer_hi && n > e->first_step) CU(cudaStreamWaitEvent(s, e->peer_hi->ev_push, 0));
+      if (!fused) {
+         // 1. previous-state values at the ABC nodes; 2.+3. seam row and halo mirrors of u1
+         if (e->Nba) {
+            pf::k_gather<Real><<<nblk(e->Nba, 128), 128, 0, s>>>(u0, e->bna, (Real *)e->u2ba, e->Nba);
+            e->launches += 1;
+         }
+         mirror_pass<Real>(e, u1, s);
+         e->halo_dirty = 1;  // the state this step produces has no mirrored halos yet
+      } else if (e->halo_dirty) {
+         mirror_pass<Real>(e, u1, s);
+         e->halo_dirty = 0;
+      }
+      if (e->energy_on && (rc = energy_pre<Real>(e, u1, u0, n, s))) return rc;
    }
-   if (e->energy_on && (rc = energy_post<Real>(e, u0, n, s))) return rc;
-   // 10. advance the device step counter, swap (the boundary history rotates with the counter's parity)
-   pf::k_tick<<<1, 1, 0, s>>>(e->d_n);
-   e->launches += 1;
-   e->n_dev = n + 1;
-   e->cur ^= 1;
-   e->steps_done = n + 1;
+   if (split) {
+      if (phases & PH_A) {
+         // planes the neighbours need first
+         if (lo && (rc = st.part(Part{1, 2, 0, nb_lo, 0, e->nbl_lo, 0, e->nba_lo, 0, e->ns_lo, 0, e->np_lo, false}))) return rc;
+         if (hi && (rc = st.part(Part{Nx - 2, Nx - 1, NB - nb_hi, nb_hi, e->Nbl - e->nbl_hi, e->nbl_hi, e->Nba - e->nba_hi,
+                                      e->nba_hi, e->Ns - e->ns_hi, e->ns_hi, e->np - e->np_hi, e->np_hi, false})))
+            return rc;
+         CU(cudaGetLastError());
+      }
+      if (phases & PH_X) {
+         // then the exchange on the comm stream while the interior runs
+         CU(cudaEventRecord(e->ev_edge, s));
+         CU(cudaStreamWaitEvent(e->s_comm, e->ev_edge, 0));
+         if ((rc = exchange(e, u0, e->s_comm))) return rc;
+         CU(cudaEventRecord(e->ev_comm, e->s_comm));
+         if (e->peer_lo || e->peer_hi) CU(cudaEventRecord(e->ev_push, e->s_comm));
+         e->comm_pending = 1;
+      }
+      if (phases & PH_B) {
+         const i64 b0 = lo ? nb_lo : 0, b1 = hi ? nb_hi : 0, l0 = lo ? e->nbl_lo : 0, l1 = hi ? e->nbl_hi : 0;
+         const i64 a0 = lo ? e->nba_lo : 0, a1 = hi ? e->nba_hi : 0, s0 = lo ? e->ns_lo : 0, s1 = hi ? e->ns_hi : 0;
+         const i64 p0 = lo ? e->np_lo : 0, p1 = hi ? e->np_hi : 0;
+         if ((rc = st.part(Part{lo ? 2 : 1, hi ? Nx - 2 : Nx - 1, b0, NB - b0 - b1, l0, e->Nbl - l0 - l1, a0, e->Nba - a0 - a1, s0,
+                                e->Ns - s0 - s1, p0, e->np - p0 - p1, true})))
+            return rc;
+         CU(cudaGetLastError());
+      }
+   } else {
+      if (phases & PH_B) {
+         if ((rc = st.part(Part{1, Nx - 1, 0, NB, 0, e->Nbl, 0, e->Nba, 0, e->Ns, 0, e->np, true}))) return rc;
+         CU(cudaGetLastError());
+      }
+      if (phases & PH_X) {
+         if ((rc = exchange(e, u0, s))) return rc;
+         if (e->peer_lo || e->peer_hi) CU(cudaEventRecord(e->ev_push, s));
+      }
+   }
+   if (phases & PH_B) {
+      if (e->energy_on && (rc = energy_post<Real>(e, u0, n, s))) return rc;
+      // 10. advance the device step counter, swap (the boundary history rotates with the counter's parity)
+      pf::k_tick<<<1, 1, 0, s>>>(e->d_n);
+      e->launches += 1;
+      e->n_dev = n + 1;
+      e->cur ^= 1;
+      e->steps_done = n + 1;
+   }
    return PFFDTD_OK;
 }
 
-static int step_any(pffdtd_engine *e, i64 n) { return e->precision == 1 ? step_impl<float>(e, n) : step_impl<double>(e, n); }
+static int step_any(pffdtd_engine *e, i64 n, int phases = PH_ALL) {
+   return e->precision == 1 ? step_impl<float>(e, n, phases) : step_impl<double>(e, n, phases);
+}
 
 // can a step starting now be replayed from a captured graph?
 static bool graphable(const pffdtd_engine *e) {
    return e->use_graph && !e->energy_on && !e->profile_air && !e->manual_halo && !e->peer_lo && !e->peer_hi && e->steps_plain >= 2 &&
-          !(e->halo_dirty && e->fuse && e->fuse_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge);
+          !(e->halo_dirty && step_fused(e));
 }
 
 // Host-side bookkeeping a step changes; capturing a step must leave it as it was (nothing ran).
@@ -1184,11 +1238,11 @@ static int join_comm(pffdtd_engine *e) {
    return 0;
 }
 
-// Capture `count` consecutive steps that start at time index n with grid role `c` (u[c] = current state) into an
-// executable graph; `host_io`: the sequence is one host-driven step with the H2D / D2H copies of its samples.
-// With slabs the NCCL send/recv of the halo planes and the second stream are part of the graph (the exchange is joined at
-// the end of the sequence).  Nothing runs and no host-side state changes, whatever the outcome.
-static int capture_steps(pffdtd_engine *e, int c, i64 n, int count, bool host_io, cudaGraphExec_t *out, double *launches) {
+// Capture `count` consecutive steps (or the given phases of one step) that start at time index n with grid role `c` (u[c] =
+// current state) into an executable graph; `host_io`: the sequence is one host-driven step with the H2D / D2H copies of its
+// samples.  Nothing runs and no host-side state changes, whatever the outcome.
+static int capture_steps(pffdtd_engine *e, int c, i64 n, int count, bool host_io, cudaGraphExec_t *out, double *launches,
+                         int phases = PH_ALL) {
    const HostState keep = save_state(e);
    cudaGraph_t g = nullptr;
    e->cur = c, e->n_dev = n, e->comm_pending = 0, e->abc_pending = 0;
@@ -1203,7 +1257,7 @@ static int capture_steps(pffdtd_engine *e, int c, i64 n, int count, bool host_io
       e->host_mode = 3;
       cc = cudaMemcpyAsync(e->in_stage, e->h_in, (size_t)e->Ns * e->rs, cudaMemcpyHostToDevice, e->s_main);
    }
-   for (int k = 0; k < count && rc == PFFDTD_OK; k++) rc = step_any(e, n + k);
+   for (int k = 0; k < count && rc == PFFDTD_OK; k++) rc = step_any(e, n + k, phases);
    if (host_io && cc == cudaSuccess)
       cc = cudaMemcpyAsync(e->h_out, e->out_stage, (size_t)e->Nr * e->rs, cudaMemcpyDeviceToHost, e->s_main);
    if (e->comm_pending && cc == cudaSuccess) cc = cudaStreamWaitEvent(e->s_main, e->ev_comm, 0);  // re-join the comm stream
@@ -1238,7 +1292,37 @@ extern "C" int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps
       // two steps bring `cur` back: a captured pair replays as one CUDA graph (fused or not, one GPU or a slab with its
       // halo exchange), once the halos are clean and the first plain steps have sized the launches and opened the
       // NCCL connections.  Both grid roles are captured at the first use, so no later call pays for a capture.
-      const bool graph_ok = nend - n >= 2 && graphable(e);
+      if (e->comm && graphable(e)) {
+         // a slab with an NCCL communicator: the work before and after the exchange replays from two graphs per grid role, the
+         // exchange (event, ncclSend/ncclRecv on the comm stream, event) is issued eagerly between them
+         const int c = e->cur;
+         const bool split = step_split(e);
+         int rc = join_comm(e);
+         if (rc) return rc;
+         for (int k = 0; k < 2; k++) {
+            const int cc = c ^ k;
+            if (split && !e->graphA[cc] && (rc = capture_steps(e, cc, n, 1, false, &e->graphA[cc], &e->graphA_launches[cc], PH_A))) return rc;
+            if (!e->graphB[cc] && (rc = capture_steps(e, cc, n, 1, false, &e->graphB[cc], &e->graphB_launches[cc], PH_B))) return rc;
+         }
+         if (e->n_dev != n) {
+            pf::k_set_n<<<1, 1, 0, e->s_main>>>(e->d_n, n);
+            e->n_dev = n;
+         }
+         if (split) {
+            CU(cudaGraphLaunch(e->graphA[c], e->s_main));
+            e->launches += e->graphA_launches[c];
+            if ((rc = step_any(e, n, PH_X))) return rc;
+         }
+         CU(cudaGraphLaunch(e->graphB[c], e->s_main));
+         e->launches += e->graphB_launches[c];
+         if (!split && (rc = step_any(e, n, PH_X))) return rc;
+         e->cur ^= 1;
+         n += 1;
+         e->n_dev = n;
+         e->steps_done = n;
+         continue;
+      }
+      const bool graph_ok = nend - n >= 2 && graphable(e) && !e->comm;
       if (graph_ok) {
          const int c = e->cur;
          int rc = join_comm(e);
@@ -1286,7 +1370,7 @@ extern "C" int pffdtd_step_host(pffdtd_engine *e, int64_t n, const double *in_sa
       else memcpy(e->h_in, in_samples, (size_t)e->Ns * 8);
    }
    int rc = PFFDTD_OK;
-   if (has_in && has_out && graphable(e)) {
+   if (has_in && has_out && graphable(e) && !e->comm) {
       // H2D of the source samples, the step, D2H of the receiver samples: one replayed graph per grid role
       const int c = e->cur;
       if ((rc = join_comm(e))) return rc;

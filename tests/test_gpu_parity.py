@@ -19,7 +19,9 @@ def _kernels(sd):
     sparse rigid nodes and the shell's z faces done by the air kernel's service warp (the default where the grid allows it)"""
     if sd.fcc_flag == 0:
         return (0, 0, 0), (1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 1, 1)
-    return (0, 0, 0), (1, 0, 0), (1, 0, 1)  # FCC: generic and tiled 13-point kernels (unfused step), without / with the service warp
+    # FCC: generic and tiled 13-point kernels (unfused step), without / with the service warp; the fused step (mirror-on-write incl. halo
+    # edges and the seam row, shell by k_abc_faces + the service warp) where the grid allows it
+    return (0, 0, 0), (1, 0, 0), (1, 0, 1), (1, 1, 1)
 
 
 def _engine(sd, ak, fuse, cfg=None, svc=1):
@@ -65,6 +67,8 @@ def test_full_state_bit_exact_from_noise(name, precision):
     o.run_steps(0, 25)
     for ak, fuse, svc in _kernels(sd):
         with _engine(sd, ak, fuse, svc=svc) as e:
+            if fuse and name in ("fcc1_lossy", "fcc2_lossy", "fcc1_wide", "fcc2_wide"):
+                assert e.stat("fused") == 1 and e.stat("svc") == 1
             if svc and ak == 1 and name in ("cart_lossy", "cart_ragged", "cart_long", "cart_nz_a", "fcc1_lossy", "fcc2_lossy", "fcc2_wide"):
                 # the service warp really is in use on the ordinary rooms (the fused step's lists always hold the shell's z faces)
                 assert e.stat("svc") == 1 and (e.stat("svc_entries") > 0 or not fuse)
@@ -103,9 +107,9 @@ def test_every_tile_width_gives_the_same_bits(name, precision):
     want = [o.read_grid(1)[1:-1, 1:-1, 1:-1], o.read_grid(0)[1:-1, 1:-1, 1:-1]]
     vo, go = o.read_boundary_state()
     for cfg, lz in TILE_CFGS["cart" if sd.fcc_flag == 0 else "fcc"]:
-        for fuse in ((0, 1) if sd.fcc_flag == 0 else (0,)):
+        for fuse in (0, 1):
             with _engine(sd, 1, fuse, cfg) as e:
-                if fuse:
+                if fuse and (sd.fcc_flag == 0 or cfg >= 12):  # (the 13-point kernel fuses only with the service warp)
                     assert e.stat("fused") == (1 if _fused_expected(sd, lz) else 0)
                     # the lists exist exactly when the kernel has the warp, the step is fused and no boundary / source node is on the shell
                     assert e.stat("svc") == (1 if cfg >= 12 and _fused_expected(sd, lz) and e.stat("abc_disjoint") else 0) or not _fused_expected(sd, lz)
