@@ -90,12 +90,14 @@ int pffdtd_comm_unique_id(void *id128 /* 128 bytes out */);
 int pffdtd_comm_init(pffdtd_engine *e, const void *id128, int rank, int nranks);
 
 /* Options: "air_kernel" (0 generic one-thread-per-node, 1 tiled TMA sweep [default for Cartesian grids]),
- * "fuse" (1 = the tiled kernel also applies the absorbing shell and mirrors the halos on write [default]),
+ * "fuse" (1 = the tiled kernel mirrors the halos on write and the absorbing shell is finished from stashed values, -1 = the layout's
+ * default [7-point: on; 13-point: off]),
  * "overlap" (1 = edge planes first, halo exchange overlapped with the interior [default]),
  * "air_cfg" (tile configuration), "air_xc" (x-chunk length), "profile_air" (CUDA events around every air launch),
  * "manual_halo" (allow stepping a slab without a communicator; the caller moves the halo planes),
  * "use_graph" (1 = replay captured steps as CUDA graphs [default]), "svc" (1 = the air kernel's service warp finishes the sparse
- * rigid-boundary nodes and the z faces of the absorbing shell from shared memory [default where the grid allows it]), "svc_cap"
+ * rigid-boundary nodes and the z faces of the absorbing shell from shared memory, -1 = the layout's default [7-point: on where the
+ * grid allows it; 13-point: off]), "svc_cap"
  * (tile-planes with more boundary nodes than this leave them to the list kernel [64, at most 192 minus two per tile row]), "abc_overlap" (1 = the absorbing-shell kernel runs beside the boundary kernels when no
  * boundary / source node lies on the shell [default]). */
 int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t value);

@@ -340,6 +340,7 @@ struct FacesArgs {
    int do_z;    // 0: the z faces were finished inside the air kernel (service warp)
    int folded;  // folded FCC grid: no shell and no mirror at the high y end, row Ny-2 is copied to the seam row Ny-1
    int edges;   // 13-point stencil: halo edges are read too, a changed node is copied to its doubly mirrored positions as well
+   int checker; // checkerboard FCC grid (fcc_flag 1): 1 + the parity of the slab's first plane; odd-parity nodes are not grid nodes
    Real lQ1, lQ2, lQ3;
 };
 template <typename Real>
@@ -378,6 +379,9 @@ __global__ void k_abc_faces(const FacesArgs<Real> a) {
    } else {
       return;
    }
+   // (the unused parity of a checkerboard grid normally holds zeros, on which the update is the identity -- but only exactly so for
+   // zeros: leave those nodes alone, as the reference's list does)
+   if (a.checker && ((a.checker - 1 + x + y + z) & 1)) return;
    const int Q = (on_xshell(x) ? 1 : 0) + ((y == 1 || (!fold && y == a.Ny - 2)) ? 1 : 0) + ((z == 1 || z == a.Nz - 2) ? 1 : 0);
    const Real lQ = Q == 1 ? a.lQ1 : (Q == 2 ? a.lQ2 : a.lQ3);
    const i64 P = (i64)a.Ny * a.Nzp;
@@ -407,7 +411,7 @@ __global__ void k_abc_faces(const FacesArgs<Real> a) {
 // full[s] flips when all bytes of a plane have landed in stage s, empty[s] when all NW consumer warps
 // are done with it.  Loads are numbered consecutively over all segments of the CTA; load i uses stage
 // i % S.  A segment of cnt planes loads planes xa-1 .. xa+cnt: the first and the last only as u1.
-template <typename Real, int RPT, int NW, int S, int MAXR, bool FCC, int LZ, bool SVC>
+template <typename Real, int RPT, int NW, int S, int MAXR, bool FCC, int LZ, bool SVC, bool FFUSE>
 __global__ void __maxnreg__(MAXR)
     k_air_tma_cart(const __grid_constant__ CUtensorMap map_u1, const __grid_constant__ CUtensorMap map_u0,
                    const __grid_constant__ CUtensorMap map_mk, Real *__restrict__ u0g, const AirJob jb, const Real a1, const Real a2,
@@ -653,83 +657,83 @@ __global__ void __maxnreg__(MAXR)
          }
       }
 
-      // ---- the end of a row-vector's update, shared by the 7-point and the 13-point paths: the fused step's extras, then the
-      // stores.  `o` = the new values (masked elements carry their stage value), `u0v` = the old ones.
-      //  * rows / planes on the absorbing shell keep the plain air value and stash their old values for k_abc_faces;
-      //  * mirror-on-write: whoever holds index 2 / N-3 of an axis also writes the halo at 0 / N-1 -- inside the vector (or by a
-      //    shuffle / one scalar store) for z, as whole-row copies for y and x; the 13-point stencil also reads halo EDGES, so its
-      //    x copies carry the y copies too (the row vector already carries the z mirror); the seam row of a folded grid is one
-      //    more row copy.
-      // Everything lane-dependent is written as selects / single predicated stores: a divergent branch here would make the
-      // one lane at a z end run the rest of the step on its own.
-      auto emit = [&](const int r, const int x, const unsigned xrole, const unsigned am, Real(&o)[VEC], const Real(&u0v)[VEC], Real *dst,
-                      Real *zo) {
-         const unsigned yr = (yrole >> (4 * r)) & 15u;
-         const bool shell = ((yr | xrole) & 1u) != 0;  // uniform within a row group
-         if (shell) {
-            // row / plane on the absorbing shell: one extra vector store (the planes on the x shell take precedence)
-            Real *sp = (xrole & 1u) ? eg.xold + (((i64)(x == 1 ? 0 : 1) * Ny + (ybase + r)) * Nzp + zv)
-                                    : eg.yold + ((((i64)x * 2 + ((ybase + r) == 1 ? 0 : 1)) * Nzp) + zv);
-            st_vec<Real, VEC>(sp, u0v);
-         }
-         // Mirror targets that live in ANOTHER active lane's vector are delivered by a shuffle (that lane stores
-         // its whole vector; a scalar store from here would race with it); only a target in a vector nobody
-         // stores (the row's far padding) is written directly.
-         __syncwarp(am);  // the row groups may have diverged on `shell`
-         if (zlo_tile) {  // warp-uniform: the tile starts at z = 0
-            // lane 0 holds z=1 (shell): stash its pre-update value; z=2 -> z=0 mirror
-            if (eg.zstash && lz == 0 && !shell) zo[0] = u0v[1];
-            if constexpr (VEC >= 4) {
-               o[0] = (lz == 0) ? o[2] : o[0];
-            } else {
-               const Real t = __shfl_down_sync(am, o[0], 1);  // fp64: z=2 is the first element of the next lane
-               o[0] = (lz == 0) ? t : o[0];
+      if constexpr (FCC) {
+      // ---- the end of a row-vector's update in the FUSED 13-point step (FFUSE kernels): the fused step's extras, then the stores
+         // (the 7-point path below has the same logic inline; kept apart: sharing it cost the 7-point kernel 14 % on B200).  `o` = the new values (masked elements carry their stage value), `u0v` = the old ones.
+         //  * rows / planes on the absorbing shell keep the plain air value and stash their old values for k_abc_faces;
+         //  * mirror-on-write: whoever holds index 2 / N-3 of an axis also writes the halo at 0 / N-1 -- inside the vector (or by a
+         //    shuffle / one scalar store) for z, as whole-row copies for y and x; the 13-point stencil also reads halo EDGES, so its
+         //    x copies carry the y copies too (the row vector already carries the z mirror); the seam row of a folded grid is one
+         //    more row copy.
+         // Everything lane-dependent is written as selects / single predicated stores: a divergent branch here would make the
+         // one lane at a z end run the rest of the step on its own.
+            auto emit = [&](const int r, const int x, const unsigned xrole, const unsigned am, Real(&o)[VEC], const Real(&u0v)[VEC], Real *dst,
+                         Real *zo) {
+            const unsigned yr = (yrole >> (4 * r)) & 15u;
+            const bool shell = ((yr | xrole) & 1u) != 0;  // uniform within a row group
+            if (shell) {
+               // row / plane on the absorbing shell: one extra vector store (the planes on the x shell take precedence)
+               Real *sp = (xrole & 1u) ? eg.xold + (((i64)(x == 1 ? 0 : 1) * Ny + (ybase + r)) * Nzp + zv)
+                                       : eg.yold + ((((i64)x * 2 + ((ybase + r) == 1 ? 0 : 1)) * Nzp) + zv);
+               st_vec<Real, VEC>(sp, u0v);
             }
-         }
-         Real vm = o[0];  // value of z = Nz-3 if this thread holds it
-         if (zhi_tile) {  // warp-uniform: the tile contains z = Nz-3 .. Nz-1
-            Real vs = u0v[0];
-#pragma unroll
-            for (int k = 1; k < VEC; k++) {
-               vs = (k == khs) ? u0v[k] : vs;
-               vm = (k == khm) ? o[k] : vm;
+            // Mirror targets that live in ANOTHER active lane's vector are delivered by a shuffle (that lane stores
+            // its whole vector; a scalar store from here would race with it); only a target in a vector nobody
+            // stores (the row's far padding) is written directly.
+            __syncwarp(am);  // the row groups may have diverged on `shell`
+            if (zlo_tile) {  // warp-uniform: the tile starts at z = 0
+               // lane 0 holds z=1 (shell): stash its pre-update value; z=2 -> z=0 mirror
+               if (eg.zstash && lz == 0 && !shell) zo[0] = u0v[1];
+               if constexpr (VEC >= 4) {
+                  o[0] = (lz == 0) ? o[2] : o[0];
+               } else {
+                  const Real t = __shfl_down_sync(am, o[0], 1);  // fp64: z=2 is the first element of the next lane
+                  o[0] = (lz == 0) ? t : o[0];
+               }
             }
-            if (eg.zstash && khs >= 0 && !shell) zo[1] = vs;  // z = Nz-2 (shell)
+            Real vm = o[0];  // value of z = Nz-3 if this thread holds it
+            if (zhi_tile) {  // warp-uniform: the tile contains z = Nz-3 .. Nz-1
+               Real vs = u0v[0];
 #pragma unroll
-            for (int k = 0; k + 2 < VEC; k++) o[k + 2] = (k == khm) ? o[k] : o[k + 2];  // z=Nz-3 -> z=Nz-1 inside the vector
-            // a vector that starts at z=Nz-2 holds z=Nz-1 as element 1 and finds z=Nz-3 at the end of the previous lane's
-            // (never the first vector of a tile: the engine refuses the fused step for such grids, AirTma::z_edge)
-            __syncwarp(am);
-            const Real t = __shfl_up_sync(am, o[VEC - 1], 1);
-            o[1] = (khs == 0) ? t : o[1];
-         }
-         // Every vector of an active row is stored, fully masked ones too: it may hold the z halo (mirror-on-write: a masked
-         // node at z = 1 / Nz-2 must not keep the halo next to it from being refreshed) or a node the service warp finished
-         // in the stage.  Masked elements carry their stage value.
-         const bool tailz = zhi_tile && khm + 2 == VEC;  // z=Nz-1 opens the next vector, which nobody stores
-         st_vec<Real, VEC>(dst, o);
-         if (tailz) dst[VEC] = vm;
-         if (((yr | xrole) & 14u) != 0u) {
-            // mirror source of a y / x halo (or the seam): the same row goes there as well (warp-uniform, a few rows / planes)
+               for (int k = 1; k < VEC; k++) {
+                  vs = (k == khs) ? u0v[k] : vs;
+                  vm = (k == khm) ? o[k] : vm;
+               }
+               if (eg.zstash && khs >= 0 && !shell) zo[1] = vs;  // z = Nz-2 (shell)
+#pragma unroll
+               for (int k = 0; k + 2 < VEC; k++) o[k + 2] = (k == khm) ? o[k] : o[k + 2];  // z=Nz-3 -> z=Nz-1 inside the vector
+               // a vector that starts at z=Nz-2 holds z=Nz-1 as element 1 and finds z=Nz-3 at the end of the previous lane's
+               // (never the first vector of a tile: the engine refuses the fused step for such grids, AirTma::z_edge)
+               __syncwarp(am);
+               const Real t = __shfl_up_sync(am, o[VEC - 1], 1);
+               o[1] = (khs == 0) ? t : o[1];
+            }
+            // Every vector of an active row is stored, fully masked ones too: it may hold the z halo (mirror-on-write: a masked
+            // node at z = 1 / Nz-2 must not keep the halo next to it from being refreshed) or a node the service warp finished
+            // in the stage.  Masked elements carry their stage value.
+            const bool tailz = zhi_tile && khm + 2 == VEC;  // z=Nz-1 opens the next vector, which nobody stores
+            st_vec<Real, VEC>(dst, o);
+            if (tailz) dst[VEC] = vm;
+            if (((yr | xrole) & 14u) != 0u) {
+               // mirror source of a y / x halo (or the seam): the same row goes there as well (warp-uniform, a few rows / planes)
 #pragma unroll 1
-            for (int tx = 0; tx < 3; tx++) {
-               const bool xon = tx == 0 || (tx == 1 ? (xrole & 2u) != 0 : (xrole & 4u) != 0);
-               const i64 xo = tx == 0 ? 0 : (tx == 1 ? -2 * jb.plane : 2 * jb.plane);
+               for (int tx = 0; tx < 3; tx++) {
+                  const bool xon = tx == 0 || (tx == 1 ? (xrole & 2u) != 0 : (xrole & 4u) != 0);
+                  const i64 xo = tx == 0 ? 0 : (tx == 1 ? -2 * jb.plane : 2 * jb.plane);
 #pragma unroll 1
-               for (int ty = 0; ty < 4; ty++) {
-                  const bool yon = ty == 0 || (ty == 1 ? (yr & 2u) != 0 : ty == 2 ? (yr & 4u) != 0 : (yr & 8u) != 0);
-                  const i64 yo = ty == 0 ? 0 : (ty == 1 ? -2 * (i64)Nzp : ty == 2 ? 2 * (i64)Nzp : (i64)Nzp);
-                  if (xon && yon && (tx | ty) != 0 && (FCC || tx == 0 || ty == 0)) {
-                     Real *d = dst + xo + yo;
-                     st_vec<Real, VEC>(d, o);
-                     if (tailz) d[VEC] = vm;
+                  for (int ty = 0; ty < 4; ty++) {
+                     const bool yon = ty == 0 || (ty == 1 ? (yr & 2u) != 0 : ty == 2 ? (yr & 4u) != 0 : (yr & 8u) != 0);
+                     const i64 yo = ty == 0 ? 0 : (ty == 1 ? -2 * (i64)Nzp : ty == 2 ? 2 * (i64)Nzp : (i64)Nzp);
+                     if (xon && yon && (tx | ty) != 0) {
+                        Real *d = dst + xo + yo;
+                        st_vec<Real, VEC>(d, o);
+                        if (tailz) d[VEC] = vm;
+                     }
                   }
                }
             }
-         }
-      };
+         };
 
-      if constexpr (FCC) {
          // ---- 13-point FCC (cpu_engine.h:205-216; the same stencil on the checkerboard and on the folded grid):
          // the taps of the planes x-1 and x+1 are (y+-1, z) and (y, z+-1), those of plane x are (y+-1, z+-1).
          // Rows y-1, y, y+1 of the three planes live in registers and rotate along the sweep (x+1 -> x -> x-1), so a
@@ -776,9 +780,9 @@ __global__ void __maxnreg__(MAXR)
             Real *u0p = u0g + ((i64)sg.xa * Ny + ybase) * Nzp + zv;
             for (int j = 0; j < sg.cnt; j++) {
                const int x = sg.xa + j;
-               const unsigned xrole = !fuse ? 0u
-                                            : ((((eg.x_lo && x == 1) || (eg.x_hi && x == eg.Nx - 2)) ? 1u : 0u) | ((eg.x_lo && x == 2) ? 2u : 0u) |
-                                               ((eg.x_hi && x == eg.Nx - 3) ? 4u : 0u));
+               const unsigned xrole = !FFUSE ? 0u
+                                             : ((((eg.x_lo && x == 1) || (eg.x_hi && x == eg.Nx - 2)) ? 1u : 0u) | ((eg.x_lo && x == 2) ? 2u : 0u) |
+                                                ((eg.x_hi && x == eg.Nx - 3) ? 4u : 0u));
                Ring gu = gc;  // plane x+1
                gu.next();
                wait_full(gu);
@@ -841,10 +845,13 @@ __global__ void __maxnreg__(MAXR)
                      p = O::add(p, (k < VEC - 1) ? m1[k + 1 < VEC ? k + 1 : k] : m1r);  // -x +z
                      o[k] = ((m >> k) & 1u) ? u0v[k] : p;
                   }
-                  if (r < nrow) {
-                     const unsigned am = __activemask();
-                     if (fuse) emit(r, x, xrole, am, o, u0v, u0p + (i64)r * Nzp, nullptr);
-                     else if (SVC || m != VMASK) st_vec<Real, VEC>(u0p + (i64)r * Nzp, o);
+                  if constexpr (FFUSE) {
+                     if (r < nrow) {
+                        const unsigned am = __activemask();
+                        emit(r, x, xrole, am, o, u0v, u0p + (i64)r * Nzp, nullptr);
+                     }
+                  } else {
+                     if (r < nrow && (SVC || m != VMASK)) st_vec<Real, VEC>(u0p + (i64)r * Nzp, o);
                   }
                   qm0[r] = qc0[r], qm1[r] = qc1[r], qm2[r] = qc2[r];
                   qc0[r] = qp0, qc1[r] = qp1, qc2[r] = qp2, ac1[r] = an1;
@@ -933,10 +940,13 @@ __global__ void __maxnreg__(MAXR)
                      o[k] = ((m >> k) & 1u) ? u0v[k] : p;
                   }
                   // (also a fully masked vector is stored: the service warp may have finished one of its nodes in the stage)
-                  if (r < nrow) {
-                     const unsigned am = __activemask();
-                     if (fuse) emit(r, x, xrole, am, o, u0v, u0p + (i64)r * Nzp, nullptr);
-                     else if (SVC || m != VMASK) st_vec<Real, VEC>(u0p + (i64)r * Nzp, o);
+                  if constexpr (FFUSE) {
+                     if (r < nrow) {
+                        const unsigned am = __activemask();
+                        emit(r, x, xrole, am, o, u0v, u0p + (i64)r * Nzp, nullptr);
+                     }
+                  } else {
+                     if (r < nrow && (SVC || m != VMASK)) st_vec<Real, VEC>(u0p + (i64)r * Nzp, o);
                   }
                }
 #pragma unroll
@@ -1070,7 +1080,67 @@ __global__ void __maxnreg__(MAXR)
                      o[k] = ((m >> k) & 1u) ? u0v[k] : p;
                   }
                }
-               emit(r, x, xrole, am, o, u0v, u0p + (i64)r * Nzp, zop + 2 * r);
+               Real *dst = u0p + (i64)r * Nzp;
+               const unsigned rrole = ((yrole >> (4 * r)) & 7u) | xrole;  // uniform within a row group
+               // Fused extras.  Everything lane-dependent below is written as selects / single predicated stores:
+               // a divergent branch here would make the one lane at a z end run the rest of the step on its own.
+               const bool shell = (rrole & 1u) != 0;
+               if (shell) {
+                  // row / plane on the absorbing shell: keep the plain air value, stash the pre-update values for
+                  // k_abc_faces (one extra vector store; the planes on the x shell take precedence)
+                  Real *sp = (xrole & 1u) ? eg.xold + (((i64)(x == 1 ? 0 : 1) * Ny + (ybase + r)) * Nzp + zv)
+                                          : eg.yold + ((((i64)x * 2 + ((ybase + r) == 1 ? 0 : 1)) * Nzp) + zv);
+                  st_vec<Real, VEC>(sp, u0v);
+               }
+               // Mirror targets that live in ANOTHER active lane's vector are delivered by a shuffle (that lane stores
+               // its whole vector; a scalar store from here would race with it); only a target in a vector nobody
+               // stores (the row's far padding) is written directly.
+               __syncwarp(am);  // the row groups may have diverged on `shell`
+               if (zlo_tile) {  // warp-uniform: the tile starts at z = 0
+                  // lane 0 holds z=1 (shell): stash its pre-update value; z=2 -> z=0 mirror
+                  if (eg.zstash && lz == 0 && !shell) zop[2 * r] = u0v[1];
+                  if constexpr (VEC >= 4) {
+                     o[0] = (lz == 0) ? o[2] : o[0];
+                  } else {
+                     const Real t = __shfl_down_sync(am, o[0], 1);  // fp64: z=2 is the first element of the next lane
+                     o[0] = (lz == 0) ? t : o[0];
+                  }
+               }
+               Real vm = o[0];  // value of z = Nz-3 if this thread holds it
+               if (zhi_tile) {  // warp-uniform: the tile contains z = Nz-3 .. Nz-1
+                  Real vs = u0v[0];
+#pragma unroll
+                  for (int k = 1; k < VEC; k++) {
+                     vs = (k == khs) ? u0v[k] : vs;
+                     vm = (k == khm) ? o[k] : vm;
+                  }
+                  if (eg.zstash && khs >= 0 && !shell) zop[2 * r + 1] = vs;  // z = Nz-2 (shell)
+#pragma unroll
+                  for (int k = 0; k + 2 < VEC; k++) o[k + 2] = (k == khm) ? o[k] : o[k + 2];  // z=Nz-3 -> z=Nz-1 inside the vector
+                  // a vector that starts at z=Nz-2 holds z=Nz-1 as element 1 and finds z=Nz-3 at the end of the previous lane's
+                  // (never the first vector of a tile: the engine refuses the fused step for such grids, AirTma::z_edge)
+                  __syncwarp(am);
+                  const Real t = __shfl_up_sync(am, o[VEC - 1], 1);
+                  o[1] = (khs == 0) ? t : o[1];
+               }
+               // Every vector of an active row is stored, fully masked ones too: it may hold the z halo (mirror-on-write: a masked
+               // node at z = 1 / Nz-2 must not keep the halo next to it from being refreshed) or a node the service warp finished
+               // in the stage.  Masked elements carry their stage value.
+               st_vec<Real, VEC>(dst, o);
+               if (zhi_tile && khm + 2 == VEC) dst[VEC] = vm;  // z=Nz-1 opens the next vector, which nobody stores
+               if (rrole & 6u) {
+                  // mirror source of a y / x halo: the same row goes there as well (warp-uniform, a few rows / planes)
+                  const int y = ybase + r;
+#pragma unroll 1
+                  for (int t = 1; t < 5; t++) {
+                     const bool on = t == 1 ? y == 2 : t == 2 ? y == Ny - 3 : t == 3 ? (xrole & 2u) != 0 : (xrole & 4u) != 0;
+                     if (on) {
+                        Real *d = dst + (t == 1 ? -2 * (i64)Nzp : t == 2 ? 2 * (i64)Nzp : t == 3 ? -2 * jb.plane : 2 * jb.plane);
+                        st_vec<Real, VEC>(d, o);
+                        if (zhi_tile && khm + 2 == VEC) d[VEC] = vm;
+                     }
+                  }
+               }
             }
          }
          release(gc);  // plane x's stage may be refilled; x-1 and x+1 live in registers / the next stage
@@ -1131,10 +1201,13 @@ static int air_tma_attr(int cfg) {
    cudaError_t rc = cudaErrorInvalidValue;
 #define X(id, RPT, NW, S, MAXR, LZ, SVC)                                                                                          \
    if (cfg == id) {                                                                                                                   \
-      rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, false, LZ, SVC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, false, LZ, SVC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 AirCfg<Real, RPT, NW, S, LZ, SVC>::SMEM_BYTES);                                                       \
       if (rc == cudaSuccess)                                                                                                          \
-         rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ, SVC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+         rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ, SVC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   AirCfg<Real, RPT, NW, S, LZ, SVC>::SMEM_BYTES);                                                    \
+      if (rc == cudaSuccess && SVC)                                                                                                   \
+         rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ, SVC, SVC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    AirCfg<Real, RPT, NW, S, LZ, SVC>::SMEM_BYTES);                                                    \
    }
    PF_AIR_CONFIGS(X)
@@ -1250,7 +1323,10 @@ template <typename Real, int RPT, int NW, int S, int MAXR, int LZ, bool SVC>
 static int air_tma_launch_cfg(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real a1, Real a2, const AirEdge<Real> &eg, bool use_lists,
                               cudaStream_t s) {
    typedef AirCfg<Real, RPT, NW, S, LZ, SVC> C;
-   auto kern = t->fcc ? k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ, SVC> : k_air_tma_cart<Real, RPT, NW, S, MAXR, false, LZ, SVC>;
+   // (the fused 13-point step is its own kernel, compiled for the service-warp configurations only: FFUSE = SVC there)
+   auto kern = t->fcc ? ((eg.fuse && SVC) ? k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ, SVC, SVC>
+                                          : k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ, SVC, false>)
+                      : k_air_tma_cart<Real, RPT, NW, S, MAXR, false, LZ, SVC, false>;
    if (t->slots <= 0) {
       int per_sm = 0;
       cudaError_t rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, C::SMEM_BYTES);

@@ -159,7 +159,7 @@ struct pffdtd_engine {
    // with peer copies instead of NCCL send/recv
    pffdtd_engine *peer_lo = nullptr, *peer_hi = nullptr;
    // options
-   int air_kernel = 1, overlap = 1, profile_air = 0, manual_halo = 0, fuse = 1;
+   int air_kernel = 1, overlap = 1, profile_air = 0, manual_halo = 0, fuse = -1;
    int abc_overlap = 1;  // the absorbing-shell kernel runs beside the boundary kernels when their node sets are disjoint
    int abc_disjoint = 0, abc_pending = 0;
    cudaStream_t s_abc = nullptr;
@@ -167,7 +167,7 @@ struct pffdtd_engine {
    // in-kernel boundary work (air_tma.cuh AirSvc): per tile-plane lists of the sparse rigid nodes + the shell's z faces, and the
    // dense remainder of the boundary list that stays with k_rigid
    int mb_max = 0;  // largest branch count among the materials
-   int svc_want = 1, svc_on = 0, svc_cap = 64;
+   int svc_want = -1, svc_on = 0, svc_cap = 64;  // svc_want / fuse: -1 = the layout's default (7-point: on; 13-point: off, measured), 0, 1
    int svc_shell = 0;   // the lists hold the shell's z faces too (fused Cartesian step); otherwise rigid nodes only (any step)
    int bn_off_abc = 0;  // no boundary node is also an absorbing-shell node: the rigid update commutes with the shell update
    float negzero = -0.0f;  // travels as a kernel argument so that the compiler cannot fold it (air_tma.cuh "packed fp32 arithmetic")
@@ -316,12 +316,18 @@ extern "C" int pffdtd_destroy(pffdtd_engine *e) {
 // update, the rigid update and the air update touch disjoint nodes and commute.
 // Rigid nodes may go to the service warp whenever no boundary node is a shell node (bn_off_abc); the shell's z faces go with them
 // when the step is the fused Cartesian one (then the air kernel stashes nothing for them and k_abc_faces skips them).
+// Defaults by layout.  7-point: fused step + service warp (c2: 0.251 -> 0.211 ms per step).  13-point: neither -- its air kernel is
+// bound by its own consumers' issue / LSU slots, not by HBM, so every instruction moved into it costs what it saves elsewhere:
+// measured on B200 (c3s), unfused 0.449 ms per step with or without the service warp, fused 0.560 ms (the fused epilogue spills at the
+// 72 registers that keep 11 consumer warps).  Both stay available (options "fuse" / "svc" = 1) and are covered by the parity tests.
+static bool want_fuse(const pffdtd_engine *e) { return e->fuse < 0 ? e->fcc == 0 : e->fuse != 0; }
+static bool want_svc(const pffdtd_engine *e) { return e->svc_want < 0 ? e->fcc == 0 : e->svc_want != 0; }
 static bool step_fused(const pffdtd_engine *e) {
    // (the 13-point kernel has no stash for the shell's z faces: its fused step needs the service warp to do them)
-   const bool fcc_ok = e->fcc == 0 || (e->svc_want && e->tma.svc && e->bn_off_abc && e->abc_disjoint);
-   return e->fuse && e->fuse_ok && fcc_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge && !e->energy_on;
+   const bool fcc_ok = e->fcc == 0 || (want_svc(e) && e->tma.svc && e->bn_off_abc && e->abc_disjoint);
+   return want_fuse(e) && e->fuse_ok && fcc_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge && !e->energy_on;
 }
-static bool svc_eligible(const pffdtd_engine *e) { return e->svc_want && e->bn_off_abc && e->tma.ok && e->tma.svc && !e->energy_on; }
+static bool svc_eligible(const pffdtd_engine *e) { return want_svc(e) && e->bn_off_abc && e->tma.ok && e->tma.svc && !e->energy_on; }
 static int build_service(pffdtd_engine *e) {
    dfree(e, e->svc_list), dfree(e, e->svc_off), dfree(e, e->bn_left), dfree(e, e->adj_left);
    e->svc_list = e->svc_off = nullptr, e->bn_left = nullptr, e->adj_left = nullptr;
@@ -656,8 +662,8 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    }
    if (dalloc(e, &e->tma.ctr, 2)) return PFFDTD_ECUDA;
    if (dalloc(e, &e->d_n, 1)) return PFFDTD_ECUDA;
-   const int want_svc = e->svc_want && e->bn_off_abc && e->Nb > 0;
-   if ((rc = pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask, -1, want_svc))) {
+   const int svc_cfg = want_svc(e) && e->bn_off_abc && e->Nb > 0;
+   if ((rc = pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask, -1, svc_cfg))) {
       // not fatal: fall back to the generic kernel, remember why
       e->air_kernel = 0;
    }
@@ -735,7 +741,7 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       int rc = build_service(e);  // (whether the lists carry the shell's z faces follows the kind of step)
       if (rc) return rc;
    } else if (k == "fuse") {
-      e->fuse = value != 0;
+      e->fuse = value < 0 ? -1 : (value != 0);
       e->halo_dirty = 1;
       int rc = build_service(e);
       if (rc) return rc;
@@ -751,12 +757,12 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       CU(cudaSetDevice(e->device));
       CU(cudaStreamSynchronize(e->s_main));
       int cfg = e->tma.cfg;
-      if (k == "svc") e->svc_want = value != 0, cfg = -1;
+      if (k == "svc") e->svc_want = value < 0 ? -1 : (value != 0), cfg = -1;
       else if (k == "svc_cap") e->svc_cap = (int)std::max<int64_t>(0, std::min<int64_t>(value, PF_SVC_CAP));
       else cfg = (int)value;
-      const int want_svc = e->svc_want && e->bn_off_abc && e->Nb > 0;
+      const int svc_cfg = want_svc(e) && e->bn_off_abc && e->Nb > 0;
       if (k != "svc_cap" &&
-          pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask, cfg, want_svc))
+          pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask, cfg, svc_cfg))
          return fail(PFFDTD_EINVAL, "air_cfg %lld: %s", (long long)value, e->tma.why.c_str());
       int rc = build_service(e);
       if (rc) return rc;
@@ -900,6 +906,7 @@ struct Step {
          fa.u0 = u0, fa.zold = (const Real *)e->zold, fa.yold = (const Real *)e->yold, fa.xold = (const Real *)e->xold;
          fa.Nx = (int)e->Nx, fa.Ny = (int)e->Ny, fa.Nz = (int)e->Nz, fa.Nzp = (int)e->Nzp, fa.xb = (int)xb, fa.xe = (int)xe;
          fa.x_lo = e->x_lo_edge, fa.x_hi = e->x_hi_edge, fa.do_z = svc ? 0 : 1, fa.folded = e->fcc == 2, fa.edges = e->fcc != 0;
+         fa.checker = e->fcc == 1 ? 1 + (int)(e->ix0 & 1) : 0;
          fa.lQ1 = (Real)((Real)e->l * (Real)1), fa.lQ2 = (Real)((Real)e->l * (Real)2), fa.lQ3 = (Real)((Real)e->l * (Real)3);
          const i64 nt = (svc ? 0 : (xe - xb) * e->Ny * 2) + (xe - xb) * 2 * e->Nz + 2 * e->Ny * e->Nz;
          if (e->abc_overlap && e->abc_disjoint && !e->comm) {  // one GPU only: with slabs the edge parts order their work around the exchange

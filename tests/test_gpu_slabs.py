@@ -137,7 +137,7 @@ def test_multi_gpu_nccl_halo_exchange(tmp_path, name, precision, overlap):
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     logs = []
     try:
-        logs = [p.communicate(timeout=120)[0] for p in procs]
+        logs = [p.communicate(timeout=int(os.environ.get("PFFDTD_TEST_TIMEOUT", "120")))[0] for p in procs]
     finally:
         for p in procs:  # never leave a rank behind (a hung rank would hold the GPU box until the outer timeout)
             if p.poll() is None:
