@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(EN_THREADS) k_energy_abc_corr(const Real *__re
 
 // stored (which = 0): sum_i ssaf_i sum_m [v^2 D + (Ts g)^2 F]  with v = vh1, g = gh1        (sim_fdtd.py:848-849)
 // lost   (which = 1): sum_i ssaf_i sum_m (v + vold)^2 E        with v = new vh1 (the reference's vh0)  (:852-853)
-// state layout [m][pitch]; def = double [Nm][MMB][3] = D, E, F
+// state layout: st_idx (kernels.cuh); `v` = the state buffer, `g_or_vold` = the same buffer + 32 elements (g) or the copy of the
+// pre-step buffer (its v); def = double [Nm][MMB][3] = D, E, F
 template <typename Real, int MMB>
 __global__ void __launch_bounds__(EN_THREADS) k_energy_branches(const Real *__restrict__ ssaf, const uint16_t *__restrict__ matmb,
                                                                 const Real *__restrict__ v, const Real *__restrict__ g_or_vold, i64 Nbl,
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(EN_THREADS) k_energy_branches(const Real *__re
       const double *d = def + (i64)(mm & 0xffu) * MMB * 3;
       double s = 0.0;
       for (int m = 0; m < Mb; m++) {
-         const double a = (double)v[(i64)m * pitch + i], b = (double)g_or_vold[(i64)m * pitch + i];
+         const double a = (double)v[st_idx<MMB>(m, i)], b = (double)g_or_vold[st_idx<MMB>(m, i)];
          if (which == 0) {
             const double tg = Ts * b;
             s += (a * a) * d[3 * m + 0] + (tg * tg) * d[3 * m + 2];

@@ -167,6 +167,7 @@ struct pffdtd_engine {
    // in-kernel boundary work (air_tma.cuh AirSvc): per tile-plane lists of the sparse rigid nodes + the shell's z faces, and the
    // dense remainder of the boundary list that stays with k_rigid
    int mb_max = 0;  // largest branch count among the materials
+   int fd_bulk = 1; // k_fd_bulk (branch state through the TMA unit) instead of k_fd
    int svc_want = -1, svc_on = 0, svc_cap = 64;  // svc_want / fuse: -1 = the layout's default (7-point: on; 13-point: off, measured), 0, 1
    int svc_shell = 0;   // the lists hold the shell's z faces too (fused Cartesian step); otherwise rigid nodes only (any step)
    int bn_off_abc = 0;  // no boundary node is also an absorbing-shell node: the rigid update commutes with the shell update
@@ -517,8 +518,9 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    for (int k = 0; k < 2; k++)
       if (dalloc_bytes(e, &e->hist[k], (size_t)e->Nbl * e->rs)) return PFFDTD_ECUDA;
    if (dalloc_bytes(e, &e->u2ba, (size_t)e->Nba * e->rs)) return PFFDTD_ECUDA;
-   if (dalloc_bytes(e, &e->vh1, (size_t)e->Nblp * PFFDTD_MMB * e->rs)) return PFFDTD_ECUDA;
-   if (dalloc_bytes(e, &e->gh1, (size_t)e->Nblp * PFFDTD_MMB * e->rs)) return PFFDTD_ECUDA;
+   // branch state, v and g interleaved in groups of 32 nodes (kernels.cuh st_idx); gh1 = the same buffer, 32 elements on
+   if (dalloc_bytes(e, &e->vh1, (size_t)e->Nblp * PFFDTD_MMB * 2 * e->rs)) return PFFDTD_ECUDA;
+   e->gh1 = (char *)e->vh1 + 32 * e->rs;
    if (dalloc_bytes(e, &e->lo2Kbg, (size_t)e->Nbl * e->rs)) return PFFDTD_ECUDA;
    if (dalloc_bytes(e, &e->facb, (size_t)e->Nbl * e->rs)) return PFFDTD_ECUDA;
    if (dalloc(e, &e->matmb, (size_t)e->Nbl)) return PFFDTD_ECUDA;
@@ -767,6 +769,8 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       int rc = build_service(e);
       if (rc) return rc;
       e->halo_dirty = 1;
+   } else if (k == "fd_bulk") {
+      e->fd_bulk = value != 0;
    } else if (k == "abc_overlap") {
       e->abc_overlap = value != 0;
    } else if (k == "manual_halo") {
@@ -943,9 +947,19 @@ struct Step {
       if (p.nbl > 0) {
          const int nq = e->Nm * PFFDTD_MMB * 4;
          const size_t sm = (size_t)(nq / 4 * 5) * sizeof(Real);
-         pf::k_fd<Real, PFFDTD_MMB><<<nblk(p.nbl, 128), 128, sm, s>>>(u0, e->bnl, e->matmb, (const Real *)e->lo2Kbg, (const Real *)e->facb,
-                                                                      (Real *)e->hist[0], (Real *)e->hist[1], (Real *)e->vh1, (Real *)e->gh1,
-                                                                      p.l0, p.nbl, e->Nblp, (const Real *)e->quads, nq, e->d_n, e->mb_max);
+         if (e->fd_bulk) {
+            // blocks own 4 whole groups of 32 nodes; the range may start / end inside a group
+            const i64 gfirst = p.l0 >> 5, gend = (p.l0 + p.nbl + 31) >> 5;
+            const unsigned nb = (unsigned)((gend - gfirst + 3) / 4);
+            const size_t smb = (size_t)(4 * 2 * PFFDTD_MMB * 32 + (nq / 4 * 5 + 1) / 2 * 2) * sizeof(Real) + 16;
+            pf::k_fd_bulk<Real, PFFDTD_MMB><<<nb, 128, smb, s>>>(u0, e->bnl, e->matmb, (const Real *)e->lo2Kbg, (const Real *)e->facb,
+                                                              (Real *)e->hist[0], (Real *)e->hist[1], (Real *)e->vh1, p.l0, p.nbl,
+                                                              (const Real *)e->quads, nq, e->d_n, e->mb_max);
+         } else {
+            pf::k_fd<Real, PFFDTD_MMB><<<nblk(p.nbl, 128), 128, sm, s>>>(u0, e->bnl, e->matmb, (const Real *)e->lo2Kbg, (const Real *)e->facb,
+                                                                         (Real *)e->hist[0], (Real *)e->hist[1], (Real *)e->vh1, (Real *)e->gh1,
+                                                                         p.l0, p.nbl, e->Nblp, (const Real *)e->quads, nq, e->d_n, e->mb_max);
+         }
          e->launches += 1;
       }
       if (e->abc_pending) {  // join the absorbing-shell kernel running beside the boundary kernels
@@ -989,7 +1003,7 @@ static int energy_pre(pffdtd_engine *e, Real *u1, Real *u0, i64 n, cudaStream_t 
       pf::k_gather<Real><<<nblk(e->Ns, 128), 128, 0, s>>>(u0, e->in, (Real *)e->u2in, e->Ns);
       e->launches += 1;
    }
-   if (e->Nbl) CU(cudaMemcpyAsync(e->vold, e->vh1, (size_t)e->Nblp * PFFDTD_MMB * e->rs, cudaMemcpyDeviceToDevice, s));
+   if (e->Nbl) CU(cudaMemcpyAsync(e->vold, e->vh1, (size_t)e->Nblp * PFFDTD_MMB * 2 * e->rs, cudaMemcpyDeviceToDevice, s));
    // Lu <- Laplacian of state n, for the next step's H_tot (the reference keeps Lu1 the same way, sim_fdtd.py:603-604)
    const double lfac = e->fcc ? 0.25 : 1.0;
    dim3 blk(64, 4, 1), grd(nblk(e->Nzp, 64), nblk(e->Ny, 4), (unsigned)(e->Nx - 2));
@@ -1032,7 +1046,7 @@ extern "C" int pffdtd_energy_enable(pffdtd_engine *e, const pffdtd_energy_desc *
    CU(cudaStreamSynchronize(e->s_main));
    const size_t npad = (size_t)(e->Nx * e->Ny * e->Nzp);
    if (dalloc_bytes(e, &e->Lu, npad * e->rs)) return PFFDTD_ECUDA;
-   if (dalloc_bytes(e, &e->vold, (size_t)e->Nblp * PFFDTD_MMB * e->rs)) return PFFDTD_ECUDA;
+   if (dalloc_bytes(e, &e->vold, (size_t)e->Nblp * PFFDTD_MMB * 2 * e->rs)) return PFFDTD_ECUDA;
    if (dalloc_bytes(e, &e->u2in, (size_t)e->Ns * e->rs)) return PFFDTD_ECUDA;
    if (dalloc(e, &e->en_def, (size_t)std::max(e->Nm, 1) * PFFDTD_MMB * 3)) return PFFDTD_ECUDA;
    if (e->Nm && d->mat_DEF) CU(cudaMemcpy(e->en_def, d->mat_DEF, (size_t)e->Nm * PFFDTD_MMB * 3 * 8, cudaMemcpyHostToDevice));
@@ -1476,16 +1490,15 @@ extern "C" int pffdtd_read_boundary_state(pffdtd_engine *e, double *vh1, double 
    CU(cudaSetDevice(e->device));
    int rc = pffdtd_sync(e);
    if (rc) return rc;
-   const size_t n = (size_t)e->Nblp * PFFDTD_MMB;
+   const size_t n = (size_t)e->Nblp * PFFDTD_MMB * 2;
    if (e->Nbl == 0) return PFFDTD_OK;
-   std::vector<char> tv(n * e->rs), tg(n * e->rs);
+   std::vector<char> tv(n * e->rs);
    CU(cudaMemcpy(tv.data(), e->vh1, tv.size(), cudaMemcpyDeviceToHost));
-   CU(cudaMemcpy(tg.data(), e->gh1, tg.size(), cudaMemcpyDeviceToHost));
    for (i64 i = 0; i < e->Nbl; i++)
       for (int m = 0; m < PFFDTD_MMB; m++) {
-         const size_t src = (size_t)m * e->Nblp + i, dst = (size_t)i * PFFDTD_MMB + m;
+         const size_t src = (size_t)pf::st_idx<PFFDTD_MMB>(m, i), dst = (size_t)i * PFFDTD_MMB + m;
          vh1[dst] = e->precision == 1 ? (double)((float *)tv.data())[src] : ((double *)tv.data())[src];
-         gh1[dst] = e->precision == 1 ? (double)((float *)tg.data())[src] : ((double *)tg.data())[src];
+         gh1[dst] = e->precision == 1 ? (double)((float *)tv.data())[src + 32] : ((double *)tv.data())[src + 32];
       }
    return PFFDTD_OK;
 }

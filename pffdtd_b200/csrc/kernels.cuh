@@ -197,6 +197,15 @@ __global__ void k_rigid(const Real *__restrict__ u1, Real *__restrict__ u0, cons
 // (material, Mb) into one 16-bit word: the hot kernel then starts its 2*Mb state loads after ONE
 // dependent load instead of three.
 // ------------------------------------------------------------------------------------------------
+// Branch state layout: groups of 32 consecutive lossy nodes; within a group, for each branch m the 32 v values then the 32 g values
+// ([group][m][v|g][32]).  A warp's 2*Mb loads are still one aligned 128-byte line each, but they are NEIGHBOURING lines: the warp
+// streams one contiguous block of up to 3 KB (fp32) instead of touching 24 arrays megabytes apart, which DRAM serves in long bursts.
+// st_idx(m, i) is the v value; the g value sits 32 elements further.
+template <int MMB>
+__host__ __device__ __forceinline__ i64 st_idx(int m, i64 i) {
+   return ((i >> 5) * (2 * MMB) + 2 * m) * 32 + (i & 31);
+}
+
 struct MatTable {
    const void *quads;  // Real [Nm][MMB][4] = b, bd, bDh, bFh
    const void *beta;   // Real [Nm]
@@ -236,33 +245,37 @@ __global__ void __launch_bounds__(128) k_fd(Real *__restrict__ u0, const i64 *__
    extern __shared__ __align__(16) unsigned char fd_smem[];
    Real *qs = reinterpret_cast<Real *>(fd_smem);  // [Nm][MMB][5] = 2*bDh, bFh, b, bd, 2*bFh
    const Real one = (Real)1.0, two = (Real)2.0, half = (Real)0.5;
-   for (int t = threadIdx.x; t < nquads / 4; t += blockDim.x) {
-      const Real b = quads[4 * t + 0], bd = quads[4 * t + 1], bDh = quads[4 * t + 2], bFh = quads[4 * t + 3];
-      qs[5 * t + 0] = O::mul(two, bDh), qs[5 * t + 1] = bFh, qs[5 * t + 2] = b, qs[5 * t + 3] = bd, qs[5 * t + 4] = O::mul(two, bFh);
-   }
-   __syncthreads();
-   const i64 i = i0 + n - 1 - ((i64)blockIdx.x * blockDim.x + threadIdx.x);  // descending, see k_rigid
-   if (i < i0) return;
-   Real *hist = (*d_n & 1) ? hist1 : hist0;  // the value two steps back lives in the buffer of the step's parity
-   // everything this node needs from memory is requested up front and nothing waits for anything else: the state loads are
-   // predicated on the LARGEST branch count of the problem's materials (a kernel argument; the arrays hold MMB branches for every
-   // node, unused ones zero), not on this node's own count, which is itself a load (round 1: the 2*Mb state loads of a thread were
-   // issued only after its material word had arrived); the one dependent load, index -> u0, goes last
+   const i64 iraw = i0 + n - 1 - ((i64)blockIdx.x * blockDim.x + threadIdx.x);  // descending, see k_rigid
+   const bool active = iraw >= i0;
+   const i64 i = active ? iraw : i0;  // (idle threads of the last block shadow node i0: they only help to stage the table)
+   // Everything this node needs from memory is requested up front, before the block stages the coefficient table and meets at
+   // the barrier (round 1 and the first round-2 version loaded the table, synchronised, and only then issued the node's loads:
+   // a memory latency per block with nothing in flight).  The state loads are predicated on the LARGEST branch count of the
+   // problem's materials (a kernel argument; the buffer holds MMB branches for every node, unused ones zero), not on this
+   // node's own count, which is itself a load.  The two dependent loads (step parity -> history buffer, index -> u0) go last.
+   const i64 dn = *d_n;
    const i64 c = bnl[i];
    const unsigned mm = matmb[i];
    constexpr int NB = MB > 0 ? MB : MMB;
    Real v1[NB], g1[NB];
-   Real *pv = vh1 + i, *pg = gh1 + i;
+   Real *pv = vh1 + st_idx<MMB>(0, i);  // (gh1 = vh1 + 32 in the grouped layout; Nbl is unused by it)
 #pragma unroll
    for (int m = 0; m < NB; m++) {
       if (m < mb_max) {
-         v1[m] = pv[(i64)m * Nbl];
-         g1[m] = pg[(i64)m * Nbl];
+         v1[m] = pv[64 * m];
+         g1[m] = pv[64 * m + 32];
       }
    }
    const Real lo2Kbg = lo2Kbg_bnl[i], fac = fac_bnl[i];
+   for (int t = threadIdx.x; t < nquads / 4; t += blockDim.x) {
+      const Real b = quads[4 * t + 0], bd = quads[4 * t + 1], bDh = quads[4 * t + 2], bFh = quads[4 * t + 3];
+      qs[5 * t + 0] = O::mul(two, bDh), qs[5 * t + 1] = bFh, qs[5 * t + 2] = b, qs[5 * t + 3] = bd, qs[5 * t + 4] = O::mul(two, bFh);
+   }
+   Real *hist = (dn & 1) ? hist1 : hist0;  // the value two steps back lives in the buffer of the step's parity
    const Real u2 = hist[i];
    const Real u0c = u0[c];
+   __syncthreads();
+   if (!active) return;
    const int Mb = MB > 0 ? MB : (int)(mm >> 8);
    const Real *q = qs + (mm & 0xffu) * (MMB * 5);
    const Real den = O::add(one, lo2Kbg);
@@ -278,9 +291,125 @@ __global__ void __launch_bounds__(128) k_fd(Real *__restrict__ u0, const i64 *__
    for (int m = 0; m < NB; m++) {
       if (MB > 0 || m < Mb) {
          const Real v0 = O::sub(O::add(O::mul(q[5 * m + 2], du), O::mul(q[5 * m + 3], v1[m])), O::mul(q[5 * m + 4], g1[m]));
-         pg[(i64)m * Nbl] = O::add(g1[m], O::mul(O::add(v0, v1[m]), half));
-         pv[(i64)m * Nbl] = v0;
+         pv[64 * m + 32] = O::add(g1[m], O::mul(O::add(v0, v1[m]), half));
+         pv[64 * m] = v0;
       }
+   }
+}
+
+// The same update with the branch state moved by the TMA unit: a block owns 4 groups of 32 nodes, whose state is one contiguous
+// run of lines per group in the grouped layout; one lane issues a bulk copy global -> shared per group (the first 2*mb_max lines),
+// the threads read and rewrite their 2*Mb values in shared memory, and one lane issues the bulk stores back.  No state value passes
+// through a register on its way in or out and the LSU queue (ncu: lg_throttle, 64 registers, 45 % occupancy in k_fd) is out of the
+// picture: the state streams at copy speed.  Arithmetic and order are k_fd's.
+// Whole groups are copied in and out, also where a group straddles the end of the launch's range [i0, i0+n): the nodes outside
+// it are written back unchanged (launches that share a state buffer run on one stream, in order).
+namespace fdbulk {
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t *bar, int count) {
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect(uint64_t *bar, uint32_t bytes) {
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
+   uint32_t ok;
+   do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(s32(bar)), "r"(parity)
+          : "memory");
+   } while (!ok);
+}
+__device__ __forceinline__ void load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src),
+                "r"(bytes), "r"(s32(bar))
+                : "memory");
+}
+__device__ __forceinline__ void store(void *dst, const void *src, uint32_t bytes) {
+   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(s32(src)), "r"(bytes) : "memory");
+}
+}  // namespace fdbulk
+
+template <typename Real, int MMB>
+__global__ void __launch_bounds__(128) k_fd_bulk(Real *__restrict__ u0, const i64 *__restrict__ bnl, const uint16_t *__restrict__ matmb,
+                                                 const Real *__restrict__ lo2Kbg_bnl, const Real *__restrict__ fac_bnl,
+                                                 Real *__restrict__ hist0, Real *__restrict__ hist1, Real *__restrict__ state, i64 i0, i64 n,
+                                                 const Real *__restrict__ quads, int nquads, const i64 *__restrict__ d_n, int mb_max) {
+   typedef Ops<Real> O;
+   constexpr int GL = 2 * MMB * 32;  // elements of one group's block in the state buffer
+   extern __shared__ __align__(128) unsigned char fdb_smem[];
+   Real *st = reinterpret_cast<Real *>(fdb_smem);                         // [4][2*MMB][32]
+   Real *qs = st + 4 * GL;                                                // [Nm][MMB][5] = 2*bDh, bFh, b, bd, 2*bFh
+   uint64_t *bar = reinterpret_cast<uint64_t *>(qs + (nquads / 4 * 5 + 1) / 2 * 2);
+   const Real one = (Real)1.0, two = (Real)2.0, half = (Real)0.5;
+   // blocks walk the groups downwards from the end of the range (the lines the air kernel touched last are still in L2)
+   const i64 gend = (i0 + n + 31) >> 5;                  // one past the last group of the range
+   const i64 g0 = gend - 4 * ((i64)blockIdx.x + 1);      // first of this block's 4 groups (may be < the range's first group)
+   const i64 gfirst = i0 >> 5;
+   const int tid = threadIdx.x, gl = tid >> 5;
+   const i64 i = (g0 + gl) * 32 + (tid & 31);
+   const bool active = i >= i0 && i < i0 + n;
+   const uint32_t gbytes = (uint32_t)(2 * mb_max * 32 * sizeof(Real));
+   if (tid == 0) {
+      fdbulk::bar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      uint32_t total = 0;
+      for (int g = 0; g < 4; g++)
+         if (g0 + g >= gfirst && g0 + g < gend) total += gbytes;
+      fdbulk::bar_expect(bar, total);
+      for (int g = 0; g < 4; g++)
+         if (g0 + g >= gfirst && g0 + g < gend) fdbulk::load(st + g * GL, state + (g0 + g) * GL, gbytes, bar);
+   }
+   // the node's own small loads go out while the state is on its way
+   const i64 dn = *d_n;
+   const i64 ii = active ? i : i0;
+   const i64 c = bnl[ii];
+   const unsigned mm = matmb[ii];
+   const Real lo2Kbg = lo2Kbg_bnl[ii], fac = fac_bnl[ii];
+   for (int t = tid; t < nquads / 4; t += blockDim.x) {
+      const Real b = quads[4 * t + 0], bd = quads[4 * t + 1], bDh = quads[4 * t + 2], bFh = quads[4 * t + 3];
+      qs[5 * t + 0] = O::mul(two, bDh), qs[5 * t + 1] = bFh, qs[5 * t + 2] = b, qs[5 * t + 3] = bd, qs[5 * t + 4] = O::mul(two, bFh);
+   }
+   Real *hist = (dn & 1) ? hist1 : hist0;  // the value two steps back lives in the buffer of the step's parity
+   const Real u2 = hist[ii];
+   const Real u0c = u0[c];
+   __syncthreads();  // table staged, barrier initialised
+   fdbulk::bar_wait(bar, 0);
+   if (active) {
+      const int Mb = (int)(mm >> 8);
+      const Real *q = qs + (mm & 0xffu) * (MMB * 5);
+      Real *sv = st + gl * GL + (tid & 31);  // v of branch m at sv[64*m], g at sv[64*m + 32]
+      const Real den = O::add(one, lo2Kbg);
+      Real u = O::div(O::add(u0c, O::mul(lo2Kbg, u2)), den);
+#pragma unroll
+      for (int m = 0; m < MMB; m++) {
+         if (m < Mb) u = O::sub(u, O::mul(fac, O::sub(O::mul(q[5 * m + 0], sv[64 * m]), O::mul(q[5 * m + 1], sv[64 * m + 32]))));
+      }
+      const Real du = O::sub(u, u2);
+      hist[i] = u;
+      u0[c] = u;
+#pragma unroll
+      for (int m = 0; m < MMB; m++) {
+         if (m < Mb) {
+            const Real v1 = sv[64 * m], g1 = sv[64 * m + 32];
+            const Real v0 = O::sub(O::add(O::mul(q[5 * m + 2], du), O::mul(q[5 * m + 3], v1)), O::mul(q[5 * m + 4], g1));
+            sv[64 * m + 32] = O::add(g1, O::mul(O::add(v0, v1), half));
+            sv[64 * m] = v0;
+         }
+      }
+   }
+   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy writes above, before the bulk stores read them
+   __syncthreads();
+   if (tid == 0) {
+      for (int g = 0; g < 4; g++)
+         if (g0 + g >= gfirst && g0 + g < gend) fdbulk::store(state + (g0 + g) * GL, st + g * GL, gbytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // shared memory must outlive the stores' reads; writes done before exit
    }
 }
 
