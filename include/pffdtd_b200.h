@@ -97,7 +97,7 @@ int pffdtd_comm_init(pffdtd_engine *e, const void *id128, int rank, int nranks);
  * "manual_halo" (allow stepping a slab without a communicator; the caller moves the halo planes),
  * "use_graph" (1 = replay captured steps as CUDA graphs [default]), "svc" (1 = the air kernel's service warp finishes the sparse
  * rigid-boundary nodes and the z faces of the absorbing shell from shared memory, -1 = the layout's default [7-point: on where the
- * grid allows it; 13-point: off]), "svc_cap"
+ * grid allows it; 13-point: off]), "fd_bulk" (1 = the branch kernel moves its state with TMA bulk copies [0]), "svc_cap"
  * (tile-planes with more boundary nodes than this leave them to the list kernel [64, at most 192 minus two per tile row]), "abc_overlap" (1 = the absorbing-shell kernel runs beside the boundary kernels when no
  * boundary / source node lies on the shell [default]). */
 int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t value);

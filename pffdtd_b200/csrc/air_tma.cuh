@@ -1232,15 +1232,21 @@ static int air_pick_cfg(int fcc, int precision, i64 Nz, int svc = 0) {
    const int vec = precision == 1 ? 4 : 2;
    const int ids[3] = {svc ? (fcc ? 15 : 12) : (fcc ? 5 : 0), svc ? (fcc ? 16 : 13) : (fcc ? 10 : 8), svc ? (fcc ? 17 : 14) : (fcc ? 11 : 9)};
    const int lzs[3] = {32, 16, 8};
-   int best = 0;
+   // A width whose tiles make the shell node z = Nz-2 open a tile (AirTma::z_edge) cannot run the fused step: prefer a wider one
+   // that does not, as long as it still fills half of its columns.  (Nz-2 a multiple of the widest tile defeats all three.)
+   int best = -1;
    double best_eff = 0;
-   for (int k = 0; k < 3; k++) {
-      const i64 tz = (i64)lzs[k] * vec, cols = (Nz - 1 + tz - 1) / tz * tz;
-      const double eff = (double)(Nz - 1) / (double)cols;
-      if (eff >= 0.88) return ids[k];
-      if (eff > best_eff + 1e-9) best_eff = eff, best = k;
+   for (int pass = 0; pass < 2 && best < 0; pass++) {
+      for (int k = 0; k < 3; k++) {
+         const i64 tz = (i64)lzs[k] * vec, cols = (Nz - 1 + tz - 1) / tz * tz;
+         const double eff = (double)(Nz - 1) / (double)cols;
+         const bool edge = (Nz - 2) % tz == 0;
+         if (pass == 0 && (edge || eff < 0.5)) continue;
+         if (eff >= 0.88) return ids[k];
+         if (eff > best_eff + 1e-9) best_eff = eff, best = k;
+      }
    }
-   return ids[best];
+   return ids[best < 0 ? 0 : best];
 }
 
 static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 Nz, i64 Nzp, i64 mwpr, void *u_a, void *u_b, void *mask,

@@ -167,7 +167,7 @@ struct pffdtd_engine {
    // in-kernel boundary work (air_tma.cuh AirSvc): per tile-plane lists of the sparse rigid nodes + the shell's z faces, and the
    // dense remainder of the boundary list that stays with k_rigid
    int mb_max = 0;  // largest branch count among the materials
-   int fd_bulk = 1; // k_fd_bulk (branch state through the TMA unit) instead of k_fd
+   int fd_bulk = 0; // 1: k_fd_bulk (branch state through the TMA unit) instead of k_fd -- measured 53.6 vs 50.9 us on c2: not the default
    int svc_want = -1, svc_on = 0, svc_cap = 64;  // svc_want / fuse: -1 = the layout's default (7-point: on; 13-point: off, measured), 0, 1
    int svc_shell = 0;   // the lists hold the shell's z faces too (fused Cartesian step); otherwise rigid nodes only (any step)
    int bn_off_abc = 0;  // no boundary node is also an absorbing-shell node: the rigid update commutes with the shell update
