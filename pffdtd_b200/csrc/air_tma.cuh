@@ -344,45 +344,54 @@ struct FacesArgs {
    Real lQ1, lQ2, lQ3;
 };
 template <typename Real>
+__device__ __forceinline__ void abc_face_node(const FacesArgs<Real> &a, const int x, const int y, const int z, const Real old, const bool fold,
+                                              const bool xshell);
+template <typename Real>
 __global__ void k_abc_faces(const FacesArgs<Real> a) {
    typedef Ops<Real> O;
+   // 2-D launch, no divisions: blockIdx.y walks "lines" -- nx*2 rows of the y faces (x, side), then 2*Ny rows of the x faces
+   // (side, y), then (do_z) nx*2 lines of the z faces (x, side) that run along y -- and the x dimension of the grid walks the
+   // line (z, or y for the z faces).  (Round 2's first version decoded one linear 64-bit index with three runtime divisions per
+   // thread: 12 us on c2 for 4 MB of traffic.)
    const int nx = a.xe - a.xb;
-   const i64 nZ = a.do_z ? (i64)nx * a.Ny * 2 : 0, nY = (i64)nx * 2 * a.Nz, nX = (i64)2 * a.Ny * a.Nz;
-   // descending x within each class: the planes the air kernel wrote last are still in L2
-   i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-   if (t < nZ) t = nZ - 1 - t;
-   else if (t < nZ + nY) t = nZ + (nY - 1 - (t - nZ));
+   const int rowsY = nx * 2, rowsX = 2 * a.Ny, rowsZ = a.do_z ? nx * 2 : 0;
+   const int w = blockIdx.x * blockDim.x + threadIdx.x;  // position along the line
    int x, y, z;
    Real old;
    auto on_xshell = [&](int xx) { return (a.x_lo && xx == 1) || (a.x_hi && xx == a.Nx - 2); };
    const bool fold = a.folded != 0;
-   if (t < nZ) {
-      const i64 row = t >> 1;
-      x = a.xb + (int)(row / a.Ny), y = (int)(row % a.Ny), z = (t & 1) ? a.Nz - 2 : 1;
-      if (y < 2 || y > (fold ? a.Ny - 2 : a.Ny - 3) || on_xshell(x)) return;
-      old = a.zold[((i64)x * a.Ny + y) * 2 + (t & 1)];
-   } else if (t < nZ + nY) {
-      const i64 q = t - nZ;
-      const int side = (int)((q / a.Nz) & 1);
-      x = a.xb + (int)(q / (2 * (i64)a.Nz)), y = side ? a.Ny - 2 : 1, z = (int)(q % a.Nz);
-      if (z < 1 || z > a.Nz - 2 || on_xshell(x) || (fold && side)) return;
-      old = a.yold[((i64)x * 2 + side) * a.Nzp + z];
-   } else if (t < nZ + nY + nX) {
-      const i64 q = t - nZ - nY;
-      const int side = (int)(q / ((i64)a.Ny * a.Nz));
-      x = side ? a.Nx - 2 : 1;
-      if (!(side ? a.x_hi : a.x_lo) || x < a.xb || x >= a.xe) return;
-      const i64 rq = q - (i64)side * a.Ny * a.Nz;
-      y = (int)(rq / a.Nz), z = (int)(rq % a.Nz);
-      if (y < 1 || y > a.Ny - 2 || z < 1 || z > a.Nz - 2) return;
-      old = a.xold[((i64)side * a.Ny + y) * a.Nzp + z];
-   } else {
-      return;
+   for (int line = blockIdx.y; line < rowsY + rowsX + rowsZ; line += gridDim.y) {
+      if (line < rowsY) {
+         // descending x: the planes the air kernel wrote last are still in L2
+         const int l = rowsY - 1 - line, side = l & 1;
+         x = a.xb + (l >> 1), y = side ? a.Ny - 2 : 1, z = w;
+         if (z < 1 || z > a.Nz - 2 || on_xshell(x) || (fold && side)) continue;
+         old = a.yold[((i64)x * 2 + side) * a.Nzp + z];
+      } else if (line < rowsY + rowsX) {
+         const int l = line - rowsY, side = l >= a.Ny ? 1 : 0;
+         x = side ? a.Nx - 2 : 1, y = l - side * a.Ny, z = w;
+         if (!(side ? a.x_hi : a.x_lo) || x < a.xb || x >= a.xe) continue;
+         if (y < 1 || y > a.Ny - 2 || z < 1 || z > a.Nz - 2) continue;
+         old = a.xold[((i64)side * a.Ny + y) * a.Nzp + z];
+      } else {
+         const int l = rowsZ - 1 - (line - rowsY - rowsX), side = l & 1;
+         x = a.xb + (l >> 1), y = w, z = side ? a.Nz - 2 : 1;
+         if (y < 2 || y > (fold ? a.Ny - 2 : a.Ny - 3) || on_xshell(x)) continue;
+         old = a.zold[((i64)x * a.Ny + y) * 2 + side];
+      }
+      abc_face_node<Real>(a, x, y, z, old, fold, on_xshell(x));
    }
+}
+
+// one shell node of k_abc_faces: the update and the halo copies of the changed value
+template <typename Real>
+__device__ __forceinline__ void abc_face_node(const FacesArgs<Real> &a, const int x, const int y, const int z, const Real old, const bool fold,
+                                              const bool xshell) {
+   typedef Ops<Real> O;
    // (the unused parity of a checkerboard grid normally holds zeros, on which the update is the identity -- but only exactly so for
    // zeros: leave those nodes alone, as the reference's list does)
    if (a.checker && ((a.checker - 1 + x + y + z) & 1)) return;
-   const int Q = (on_xshell(x) ? 1 : 0) + ((y == 1 || (!fold && y == a.Ny - 2)) ? 1 : 0) + ((z == 1 || z == a.Nz - 2) ? 1 : 0);
+   const int Q = (xshell ? 1 : 0) + ((y == 1 || (!fold && y == a.Ny - 2)) ? 1 : 0) + ((z == 1 || z == a.Nz - 2) ? 1 : 0);
    const Real lQ = Q == 1 ? a.lQ1 : (Q == 2 ? a.lQ2 : a.lQ3);
    const i64 P = (i64)a.Ny * a.Nzp;
    Real *p = a.u0 + ((i64)x * a.Ny + y) * a.Nzp + z;

@@ -124,6 +124,7 @@ struct pffdtd_engine {
    void *zold = nullptr, *yold = nullptr, *xold = nullptr;  // pre-update values of the shell nodes (fused step)
    uint16_t *matmb = nullptr;                // per lossy node: material | Mb << 8
    int serial_src = 0;
+   int ticked = 0;       // this step's last k_io advanced the device step counter
    i64 *d_n = nullptr;   // device step counter read by k_io / k_fd
    i64 n_dev = -1;       // value the host knows it holds (-1 unknown)
    cudaGraphExec_t graph[2] = {nullptr, nullptr};  // two consecutive steps starting with cur = 0 / 1
@@ -912,16 +913,19 @@ struct Step {
          fa.x_lo = e->x_lo_edge, fa.x_hi = e->x_hi_edge, fa.do_z = svc ? 0 : 1, fa.folded = e->fcc == 2, fa.edges = e->fcc != 0;
          fa.checker = e->fcc == 1 ? 1 + (int)(e->ix0 & 1) : 0;
          fa.lQ1 = (Real)((Real)e->l * (Real)1), fa.lQ2 = (Real)((Real)e->l * (Real)2), fa.lQ3 = (Real)((Real)e->l * (Real)3);
-         const i64 nt = (svc ? 0 : (xe - xb) * e->Ny * 2) + (xe - xb) * 2 * e->Nz + 2 * e->Ny * e->Nz;
+         // lines: (xe-xb)*2 rows of the y faces, 2*Ny rows of the x faces, (when the service warp does not do them) (xe-xb)*2 lines of
+         // the z faces along y
+         const i64 lines = (xe - xb) * 2 + 2 * e->Ny + (svc ? 0 : (xe - xb) * 2);
+         const dim3 grd(nblk(std::max(e->Nz, svc ? (i64)0 : e->Ny), 128), (unsigned)std::min<i64>(lines, 65535));
          if (e->abc_overlap && e->abc_disjoint && !e->comm) {  // one GPU only: with slabs the edge parts order their work around the exchange
             // no boundary or source node lies on the shell: the shell update commutes with the boundary kernels
             CU(cudaEventRecord(e->ev_abc0, s));
             CU(cudaStreamWaitEvent(e->s_abc, e->ev_abc0, 0));
-            pf::k_abc_faces<Real><<<nblk(nt, 256), 256, 0, e->s_abc>>>(fa);
+            pf::k_abc_faces<Real><<<grd, 128, 0, e->s_abc>>>(fa);
             CU(cudaEventRecord(e->ev_abc1, e->s_abc));
             e->abc_pending = 1;
          } else {
-            pf::k_abc_faces<Real><<<nblk(nt, 256), 256, 0, s>>>(fa);
+            pf::k_abc_faces<Real><<<grd, 128, 0, s>>>(fa);
          }
          e->launches += 1;
       }
@@ -968,11 +972,14 @@ struct Step {
       }
       const i64 nr = p.recv ? e->Nr : 0;
       if (nr > 0 || p.ns > 0) {
-         pf::k_io<Real><<<nblk(std::max(nr, p.ns), 128), 128, 0, s>>>(u1, u0, e->out, (Real *)e->uout, nr, e->Nr, e->in, (Real *)e->insig,
-                                                                     e->Ns, p.s0, p.ns, e->serial_src, e->d_n,
-                                                                     e->host_mode & 1 ? (const Real *)e->in_stage : nullptr,
-                                                                     e->host_mode & 2 ? (Real *)e->out_stage : nullptr);
+         // the step's last part (the one that reads the receivers), one block, no energy bookkeeping after it: k_io also ticks
+         const unsigned nb = nblk(std::max(nr, p.ns), 128);
+         const int tick = (p.recv && nb == 1 && !e->energy_on) ? 1 : 0;
+         pf::k_io<Real><<<nb, 128, 0, s>>>(u1, u0, e->out, (Real *)e->uout, nr, e->Nr, e->in, (Real *)e->insig, e->Ns, p.s0, p.ns,
+                                           e->serial_src, e->d_n, e->host_mode & 1 ? (const Real *)e->in_stage : nullptr,
+                                           e->host_mode & 2 ? (Real *)e->out_stage : nullptr, tick);
          e->launches += 1;
+         if (tick) e->ticked = 1;
       }
       if (fused && p.np > 0) {
          pf::k_pairs<Real><<<nblk(p.np, 128), 128, 0, s>>>(u0, e->pair_src, e->pair_dst, p.p0, p.np);
@@ -1216,9 +1223,13 @@ static int step_impl(pffdtd_engine *e, i64 n, int phases) {
    }
    if (phases & PH_B) {
       if (e->energy_on && (rc = energy_post<Real>(e, u0, n, s))) return rc;
-      // 10. advance the device step counter, swap (the boundary history rotates with the counter's parity)
-      pf::k_tick<<<1, 1, 0, s>>>(e->d_n);
-      e->launches += 1;
+      // 10. advance the device step counter (unless the step's last k_io did), swap (the boundary history rotates with the
+      // counter's parity)
+      if (!e->ticked) {
+         pf::k_tick<<<1, 1, 0, s>>>(e->d_n);
+         e->launches += 1;
+      }
+      e->ticked = 0;
       e->n_dev = n + 1;
       e->cur ^= 1;
       e->steps_done = n + 1;

@@ -441,9 +441,13 @@ __global__ void k_src(Real *__restrict__ u0, const i64 *__restrict__ in_ixyz, co
 template <typename Real>
 __global__ void k_io(const Real *__restrict__ u1, Real *__restrict__ u0, const i64 *__restrict__ out_ixyz, Real *__restrict__ uout,
                      i64 Nr, i64 nr_all, const i64 *__restrict__ in_ixyz, Real *__restrict__ insig, i64 Ns_all, i64 s0, i64 ns,
-                     int serial_src, const i64 *__restrict__ d_n, const Real *__restrict__ in_stage, Real *__restrict__ out_stage) {
+                     int serial_src, i64 *__restrict__ d_n, const Real *__restrict__ in_stage, Real *__restrict__ out_stage, int tick) {
    typedef Ops<Real> O;
    const i64 n = *d_n;
+   if (tick) {  // single-block launch that closes the step: advance the device step counter here (saves the k_tick launch)
+      __syncthreads();
+      if (threadIdx.x == 0) *d_n = n + 1;
+   }
    Real *out_row = uout + n * nr_all;
    Real *in_row = insig + n * Ns_all;
    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
