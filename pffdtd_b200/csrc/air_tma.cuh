@@ -1336,7 +1336,7 @@ static int air_tma_setup(AirTma *t, int precision, int fcc, i64 Nx, i64 Ny, i64 
 
 template <typename Real, int RPT, int NW, int S, int MAXR, int LZ, bool SVC>
 static int air_tma_launch_cfg(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real a1, Real a2, const AirEdge<Real> &eg, bool use_lists,
-                              cudaStream_t s) {
+                              cudaStream_t s, int *ctr) {
    typedef AirCfg<Real, RPT, NW, S, LZ, SVC> C;
    // (the fused 13-point step is its own kernel, compiled for the service-warp configurations only: FFUSE = SVC there)
    auto kern = t->fcc ? ((eg.fuse && SVC) ? k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ, SVC, SVC>
@@ -1356,7 +1356,7 @@ static int air_tma_launch_cfg(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real
    jb.tiles = jb.tz * ty;
    jb.Ny = (int)t->Ny, jb.Nz = (int)t->Nz, jb.Nzp = (int)t->Nzp;
    jb.plane = t->Ny * t->Nzp;
-   jb.ctr = t->ctr;
+   jb.ctr = ctr ? ctr : t->ctr;  // (launches that may run side by side need their own work counters)
    // x-chunk length: 16 planes.  Longer chunks save the two extra u1 planes an item loads (4 % of the traffic at 16) but let the
    // CTAs drift apart along x, and neighbouring tiles stop finding each other's halo rows and columns in L2: measured on B200,
    // c5 (2046 planes): 16 planes 0.975 of the copy peak, 32: 0.963, 60: 0.945; c4 (fp64 1024^3): 16: 0.976, 60: 0.946.
@@ -1377,9 +1377,9 @@ static int air_tma_launch_cfg(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real
 // planes [xb, xe) of the slab; `cur` = index of the grid that currently is u1 (u0 = the other one)
 template <typename Real>
 static int air_tma_launch(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real a1, Real a2, const AirEdge<Real> &eg, bool use_lists,
-                          cudaStream_t s) {
+                          cudaStream_t s, int *ctr = nullptr) {
 #define X(id, RPT, NW, S, MAXR, LZ, SVC) \
-   if (t->cfg == id) return air_tma_launch_cfg<Real, RPT, NW, S, MAXR, LZ, SVC>(t, cur, u0, xb, xe, a1, a2, eg, use_lists, s);
+   if (t->cfg == id) return air_tma_launch_cfg<Real, RPT, NW, S, MAXR, LZ, SVC>(t, cur, u0, xb, xe, a1, a2, eg, use_lists, s, ctr);
    PF_AIR_CONFIGS(X)
 #undef X
    return (int)cudaErrorInvalidValue;

@@ -165,6 +165,9 @@ struct pffdtd_engine {
    int abc_disjoint = 0, abc_pending = 0;
    cudaStream_t s_abc = nullptr;
    cudaEvent_t ev_abc0 = nullptr, ev_abc1 = nullptr;
+   int edge_overlap = 1;  // slabs with two neighbours: the upper edge plane's work runs on s_edge beside the lower one's
+   cudaStream_t s_edge = nullptr;
+   cudaEvent_t ev_e0 = nullptr, ev_e1 = nullptr;
    // in-kernel boundary work (air_tma.cuh AirSvc): per tile-plane lists of the sparse rigid nodes + the shell's z faces, and the
    // dense remainder of the boundary list that stays with k_rigid
    int mb_max = 0;  // largest branch count among the materials
@@ -298,6 +301,9 @@ extern "C" int pffdtd_destroy(pffdtd_engine *e) {
    if (e->ev_abc0) cudaEventDestroy(e->ev_abc0);
    if (e->ev_abc1) cudaEventDestroy(e->ev_abc1);
    if (e->s_abc) cudaStreamDestroy(e->s_abc);
+   if (e->ev_e0) cudaEventDestroy(e->ev_e0);
+   if (e->ev_e1) cudaEventDestroy(e->ev_e1);
+   if (e->s_edge) cudaStreamDestroy(e->s_edge);
    if (e->ev_edge) cudaEventDestroy(e->ev_edge);
    if (e->ev_comm) cudaEventDestroy(e->ev_comm);
    if (e->ev_step) cudaEventDestroy(e->ev_step);
@@ -479,6 +485,9 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
    CU(cudaStreamCreateWithFlags(&e->s_main, cudaStreamNonBlocking));
    CU(cudaStreamCreateWithFlags(&e->s_comm, cudaStreamNonBlocking));
    CU(cudaStreamCreateWithFlags(&e->s_abc, cudaStreamNonBlocking));
+   CU(cudaStreamCreateWithFlags(&e->s_edge, cudaStreamNonBlocking));
+   CU(cudaEventCreateWithFlags(&e->ev_e0, cudaEventDisableTiming));
+   CU(cudaEventCreateWithFlags(&e->ev_e1, cudaEventDisableTiming));
    CU(cudaEventCreateWithFlags(&e->ev_abc0, cudaEventDisableTiming));
    CU(cudaEventCreateWithFlags(&e->ev_abc1, cudaEventDisableTiming));
    CU(cudaEventCreateWithFlags(&e->ev_edge, cudaEventDisableTiming));
@@ -663,7 +672,7 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
       if (e->Nb) pf::k_mask_nodes<<<(unsigned)((e->Nb + 255) / 256), 256, 0, e->s_main>>>(e->mask, e->bn, e->Nb, e->Nzp, e->mwpr);
       CU(cudaGetLastError());
    }
-   if (dalloc(e, &e->tma.ctr, 2)) return PFFDTD_ECUDA;
+   if (dalloc(e, &e->tma.ctr, 4)) return PFFDTD_ECUDA;  // two {next item, CTAs done} pairs: launches on s_main / on s_edge
    if (dalloc(e, &e->d_n, 1)) return PFFDTD_ECUDA;
    const int svc_cfg = want_svc(e) && e->bn_off_abc && e->Nb > 0;
    if ((rc = pf::air_tma_setup(&e->tma, e->precision, e->fcc, e->Nx, e->Ny, e->Nz, e->Nzp, e->mwpr, e->u[0], e->u[1], e->mask, -1, svc_cfg))) {
@@ -770,6 +779,8 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       int rc = build_service(e);
       if (rc) return rc;
       e->halo_dirty = 1;
+   } else if (k == "edge_overlap") {
+      e->edge_overlap = value != 0;
    } else if (k == "fd_bulk") {
       e->fd_bulk = value != 0;
    } else if (k == "abc_overlap") {
@@ -863,6 +874,7 @@ struct Step {
    i64 n;
    bool fused;
    bool svc;  // the air kernel's service warp does the sparse rigid nodes and the shell's z faces; k_rigid gets the dense rest
+   int *ctr = nullptr;  // work counters of the air launches of this chain (null = the engine's first pair)
 
    // 4. air update of planes [xb, xe)
    int air(i64 xb, i64 xe) {
@@ -893,7 +905,7 @@ struct Step {
          eg.lQ1 = (Real)((Real)e->l * (Real)1), eg.lQ2 = (Real)((Real)e->l * (Real)2), eg.lQ3 = (Real)((Real)e->l * (Real)3);
          eg.den1 = 1.0 + (double)eg.lQ1, eg.den2 = 1.0 + (double)eg.lQ2, eg.den3 = 1.0 + (double)eg.lQ3;
          eg.rden1 = 1.0 / eg.den1, eg.rden2 = 1.0 / eg.den2, eg.rden3 = 1.0 / eg.den3;
-         int rc = pf::air_tma_launch<Real>(&e->tma, e->cur, u0, xb, xe, (Real)e->a1, (Real)e->a2, eg, svc, s);
+         int rc = pf::air_tma_launch<Real>(&e->tma, e->cur, u0, xb, xe, (Real)e->a1, (Real)e->a2, eg, svc, s, ctr);
          if (rc) return fail(PFFDTD_ECUDA, "tiled air kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
       } else {
          dim3 blk(64, 4, 1);
@@ -917,7 +929,7 @@ struct Step {
          // the z faces along y
          const i64 lines = (xe - xb) * 2 + 2 * e->Ny + (svc ? 0 : (xe - xb) * 2);
          const dim3 grd(nblk(std::max(e->Nz, svc ? (i64)0 : e->Ny), 128), (unsigned)std::min<i64>(lines, 65535));
-         if (e->abc_overlap && e->abc_disjoint && !e->comm) {  // one GPU only: with slabs the edge parts order their work around the exchange
+         if (e->abc_overlap && e->abc_disjoint && !e->comm && !e->peer_lo && !e->peer_hi) {  // one GPU only: with slabs the edge parts order their work around the exchange
             // no boundary or source node lies on the shell: the shell update commutes with the boundary kernels
             CU(cudaEventRecord(e->ev_abc0, s));
             CU(cudaStreamWaitEvent(e->s_abc, e->ev_abc0, 0));
@@ -1186,11 +1198,23 @@ static int step_impl(pffdtd_engine *e, i64 n, int phases) {
    }
    if (split) {
       if (phases & PH_A) {
-         // planes the neighbours need first
+         // planes the neighbours need first.  A slab with two neighbours runs its two edge planes side by side on two streams:
+         // each is a chain of five short kernels (a one-plane air launch, shell, rigid, branches, io) that leaves the GPU mostly idle
+         const bool both = lo && hi && e->edge_overlap && !e->fd_bulk && !e->profile_air;
+         Step<Real> st2 = st;
+         if (both) {
+            CU(cudaEventRecord(e->ev_e0, s));
+            CU(cudaStreamWaitEvent(e->s_edge, e->ev_e0, 0));
+            st2.s = e->s_edge, st2.ctr = e->tma.ctr + 2;
+         }
          if (lo && (rc = st.part(Part{1, 2, 0, nb_lo, 0, e->nbl_lo, 0, e->nba_lo, 0, e->ns_lo, 0, e->np_lo, false}))) return rc;
-         if (hi && (rc = st.part(Part{Nx - 2, Nx - 1, NB - nb_hi, nb_hi, e->Nbl - e->nbl_hi, e->nbl_hi, e->Nba - e->nba_hi,
-                                      e->nba_hi, e->Ns - e->ns_hi, e->ns_hi, e->np - e->np_hi, e->np_hi, false})))
+         if (hi && (rc = st2.part(Part{Nx - 2, Nx - 1, NB - nb_hi, nb_hi, e->Nbl - e->nbl_hi, e->nbl_hi, e->Nba - e->nba_hi,
+                                       e->nba_hi, e->Ns - e->ns_hi, e->ns_hi, e->np - e->np_hi, e->np_hi, false})))
             return rc;
+         if (both) {
+            CU(cudaEventRecord(e->ev_e1, e->s_edge));
+            CU(cudaStreamWaitEvent(s, e->ev_e1, 0));
+         }
          CU(cudaGetLastError());
       }
       if (phases & PH_X) {
