@@ -327,9 +327,13 @@ def make_engine(ctx, wl, Nt, config):
         ctx.dist.broadcast_object_list(box, src=0)
         eng.comm_init(box[0], ctx.rank, ctx.world)
         eng.set_option("overlap", args.overlap)
-        config["halo_exchange"] = "ncclSend/ncclRecv of one plane per neighbour per step, " + (
-            "overlapped with the interior update on a second stream" if args.overlap else "after the step (not overlapped)") + \
-            "; step pairs replay as CUDA graphs that include the exchange"
+        from pffdtd_b200 import parallel
+        p2p = (not args.no_p2p) and parallel.connect_peers(eng, ctx.rank, ctx.world)
+        how = "overlapped with the interior update on a second stream" if args.overlap else "after the step (not overlapped)"
+        config["halo_exchange"] = (
+            "peer memory: one device-to-device copy of a plane per neighbour per step into a CUDA-IPC mapping of its grid + a copied flag "
+            "word, " + how + "; step pairs replay as CUDA graphs that include the exchange" if p2p else
+            "ncclSend/ncclRecv of one plane per neighbour per step, " + how + "; the work before / after the exchange replays from CUDA graphs")
     eng.set_option("air_kernel", args.air_kernel)
     if args.xc:
         eng.set_option("air_xc", args.xc)
@@ -477,11 +481,15 @@ def reduced_grid_parity(ctx):
         box = [comm_unique_id() if ctx.rank == 0 else None]
         ctx.dist.broadcast_object_list(box, src=0)
         eng.comm_init(box[0], ctx.rank, ctx.world)
+        from pffdtd_b200 import parallel
+        res_p2p = (not ctx.args.no_p2p) and parallel.connect_peers(eng, ctx.rank, ctx.world)
     eng.run_steps(0, Nt)
     graphed = Nt - 2
     u = np.concatenate(ctx.gather(eng.read_outputs(0, Nt)), axis=0)
     eng.close()
     res = {"grid": [Nx, Ny, Nz], "steps": Nt, "slab_planes": list(planes[1]) if planes else [Nx], "steps_replayed_from_graphs": graphed}
+    if ctx.world > 1:
+        res["halo_exchange"] = "peer memory" if res_p2p else "nccl"
     if ctx.rank == 0:
         try:
             from oracle import Oracle, Reference  # checker only
@@ -526,6 +534,7 @@ def main():
     ap.add_argument("--no-also", action="store_true", help="N=1: skip the extra single-GPU workloads")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--also", default=None, help="comma-separated workloads for the `also` key (default: all that are available)")
+    ap.add_argument("--no-p2p", action="store_true", help="N>1: keep the NCCL halo exchange instead of the peer-memory one")
     ap.add_argument("--equal-slabs", action="store_true", help="N>1: the reference's equal-plane split instead of the cost-weighted one")
     ap.add_argument("--xc", type=int, default=0)
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="engine option (pffdtd_set_option), repeatable (tuning / A-B runs)")

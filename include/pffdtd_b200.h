@@ -88,6 +88,14 @@ int pffdtd_destroy(pffdtd_engine *e);
  * with the interior update. */
 int pffdtd_comm_unique_id(void *id128 /* 128 bytes out */);
 int pffdtd_comm_init(pffdtd_engine *e, const void *id128, int rank, int nranks);
+/* The same exchange over PEER MEMORY instead of NCCL (GPUs of one node): every rank exports a blob (CUDA IPC handles of its two
+ * grids and of two flag words), the host hands each rank the blobs of its lower / upper neighbour (NULL at the ends of the grid),
+ * and from then on a step copies its edge planes straight into the neighbours' halo planes, raises their flag from the device,
+ * and starts by waiting for its own flags on the device.  No library call in the step, and the whole step replays from CUDA
+ * graphs again.  Falls back to the communicator of pffdtd_comm_init when not connected. */
+#define PFFDTD_PEER_BLOB 256
+int pffdtd_peer_export(pffdtd_engine *e, void *blob /* PFFDTD_PEER_BLOB bytes out */);
+int pffdtd_peer_connect(pffdtd_engine *e, const void *blob_lo, const void *blob_hi);
 
 /* Options: "air_kernel" (0 generic one-thread-per-node, 1 tiled TMA sweep [default for Cartesian grids]),
  * "fuse" (1 = the tiled kernel mirrors the halos on write and the absorbing shell is finished from stashed values, -1 = the layout's

@@ -156,6 +156,13 @@ struct pffdtd_engine {
    // comm
    void *comm = nullptr;
    int rank = 0, nranks = 1, comm_pending = 0;
+   // multi-process slabs over peer memory (pffdtd_peer_export / _connect): IPC mappings of the neighbours' grids and flag words;
+   // the halo planes are copied straight into them and a flag tells the neighbour (no NCCL in the step)
+   int p2p = 0;
+   long long *flags = nullptr;                 // [0] / [1]: steps whose plane the lower / upper neighbour has delivered, [2] this slab's step count, [3] error
+   void *ipc_u_lo[2] = {nullptr, nullptr}, *ipc_u_hi[2] = {nullptr, nullptr};  // the neighbours' grids
+   long long *ipc_flags_lo = nullptr, *ipc_flags_hi = nullptr;
+   i64 nx_lo = 0;                              // planes of the lower neighbour's slab (its upper halo plane is nx_lo - 1)
    // single-process multi-GPU (pffdtd_multi_*): the engines of the neighbouring slabs; halo planes are pushed into their grids
    // with peer copies instead of NCCL send/recv
    pffdtd_engine *peer_lo = nullptr, *peer_hi = nullptr;
@@ -165,7 +172,7 @@ struct pffdtd_engine {
    int abc_disjoint = 0, abc_pending = 0;
    cudaStream_t s_abc = nullptr;
    cudaEvent_t ev_abc0 = nullptr, ev_abc1 = nullptr;
-   int edge_overlap = 1;  // slabs with two neighbours: the upper edge plane's work runs on s_edge beside the lower one's
+   int edge_overlap = 0;  // 1: slabs with two neighbours run the upper edge plane on s_edge beside the lower one (measured at 4 GPUs: no gain, two persistent air kernels do not share the SMs)
    cudaStream_t s_edge = nullptr;
    cudaEvent_t ev_e0 = nullptr, ev_e1 = nullptr;
    // in-kernel boundary work (air_tma.cuh AirSvc): per tile-plane lists of the sparse rigid nodes + the shell's z faces, and the
@@ -285,6 +292,12 @@ extern "C" int pffdtd_destroy(pffdtd_engine *e) {
    if (e->s_main) cudaStreamSynchronize(e->s_main);
    if (e->s_comm) cudaStreamSynchronize(e->s_comm);
    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+   for (int k = 0; k < 2; k++) {
+      if (e->ipc_u_lo[k]) cudaIpcCloseMemHandle(e->ipc_u_lo[k]);
+      if (e->ipc_u_hi[k]) cudaIpcCloseMemHandle(e->ipc_u_hi[k]);
+   }
+   if (e->ipc_flags_lo) cudaIpcCloseMemHandle(e->ipc_flags_lo);
+   if (e->ipc_flags_hi) cudaIpcCloseMemHandle(e->ipc_flags_hi);
    for (void *p : e->allocs) cudaFree(p);
    if (e->h_in) cudaFreeHost(e->h_in);
    if (e->h_out) cudaFreeHost(e->h_out);
@@ -724,6 +737,58 @@ extern "C" int pffdtd_comm_init(pffdtd_engine *e, const void *id128, int rank, i
    return PFFDTD_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// halo exchange between processes over peer memory (CUDA IPC), without NCCL in the step
+// ------------------------------------------------------------------------------------------------
+static void drop_graphs(pffdtd_engine *e);
+struct PeerBlob {
+   cudaIpcMemHandle_t u[2], flags;
+   int64_t Nx, Ny, Nzp;
+   int32_t rs, device;
+   char pad[PFFDTD_PEER_BLOB - 3 * sizeof(cudaIpcMemHandle_t) - 3 * 8 - 2 * 4];
+};
+static_assert(sizeof(PeerBlob) == PFFDTD_PEER_BLOB, "PeerBlob size");
+
+extern "C" int pffdtd_peer_export(pffdtd_engine *e, void *blob) {
+   if (!e || !blob) return fail(PFFDTD_EINVAL, "NULL argument");
+   CU(cudaSetDevice(e->device));
+   if (!e->flags) {
+      if (dalloc(e, &e->flags, 4)) return PFFDTD_ECUDA;
+   }
+   PeerBlob b;
+   memset(&b, 0, sizeof b);
+   CU(cudaIpcGetMemHandle(&b.u[0], e->u[0]));
+   CU(cudaIpcGetMemHandle(&b.u[1], e->u[1]));
+   CU(cudaIpcGetMemHandle(&b.flags, e->flags));
+   b.Nx = e->Nx, b.Ny = e->Ny, b.Nzp = e->Nzp, b.rs = (int32_t)e->rs, b.device = e->device;
+   memcpy(blob, &b, sizeof b);
+   return PFFDTD_OK;
+}
+
+extern "C" int pffdtd_peer_connect(pffdtd_engine *e, const void *blob_lo, const void *blob_hi) {
+   if (!e) return fail(PFFDTD_EINVAL, "NULL engine");
+   if ((blob_lo != nullptr) == (e->x_lo_edge != 0) || (blob_hi != nullptr) == (e->x_hi_edge != 0))
+      return fail(PFFDTD_EINVAL, "neighbour blobs disagree with the slab's edges (%d,%d)", e->x_lo_edge, e->x_hi_edge);
+   if (!e->flags) return fail(PFFDTD_ESTATE, "call pffdtd_peer_export first");
+   CU(cudaSetDevice(e->device));
+   auto open = [&](const void *blob, void **u, long long **fl, i64 *nx) -> int {
+      PeerBlob b;
+      memcpy(&b, blob, sizeof b);
+      if (b.Ny != e->Ny || b.Nzp != e->Nzp || b.rs != (int32_t)e->rs) return fail(PFFDTD_EINVAL, "neighbour slab has another plane shape");
+      for (int k = 0; k < 2; k++) CU(cudaIpcOpenMemHandle(&u[k], b.u[k], cudaIpcMemLazyEnablePeerAccess));
+      CU(cudaIpcOpenMemHandle((void **)fl, b.flags, cudaIpcMemLazyEnablePeerAccess));
+      if (nx) *nx = b.Nx;
+      return 0;
+   };
+   int rc;
+   if (blob_lo && (rc = open(blob_lo, e->ipc_u_lo, &e->ipc_flags_lo, &e->nx_lo))) return rc;
+   if (blob_hi && (rc = open(blob_hi, e->ipc_u_hi, &e->ipc_flags_hi, nullptr))) return rc;
+   drop_graphs(e);
+   e->p2p = 1;
+   return PFFDTD_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // options / stats
 // ------------------------------------------------------------------------------------------------
@@ -779,6 +844,9 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       int rc = build_service(e);
       if (rc) return rc;
       e->halo_dirty = 1;
+   } else if (k == "p2p") {
+      if (value && !(e->ipc_flags_lo || e->ipc_flags_hi)) return fail(PFFDTD_ESTATE, "p2p needs pffdtd_peer_connect first");
+      e->p2p = value != 0;
    } else if (k == "edge_overlap") {
       e->edge_overlap = value != 0;
    } else if (k == "fd_bulk") {
@@ -838,6 +906,7 @@ extern "C" int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out) {
    else if (k == "energy") *out = e->energy_on;
    else if (k == "mirror_pairs") *out = (double)e->np;
    else if (k == "abc_disjoint") *out = e->abc_disjoint;
+   else if (k == "p2p") *out = e->p2p;
    else if (k == "svc") *out = e->svc_on;
    else if (k == "svc_entries") *out = (double)e->svc_entries;
    else if (k == "nb_left") *out = (double)e->Nb_left;
@@ -929,7 +998,7 @@ struct Step {
          // the z faces along y
          const i64 lines = (xe - xb) * 2 + 2 * e->Ny + (svc ? 0 : (xe - xb) * 2);
          const dim3 grd(nblk(std::max(e->Nz, svc ? (i64)0 : e->Ny), 128), (unsigned)std::min<i64>(lines, 65535));
-         if (e->abc_overlap && e->abc_disjoint && !e->comm && !e->peer_lo && !e->peer_hi) {  // one GPU only: with slabs the edge parts order their work around the exchange
+         if (e->abc_overlap && e->abc_disjoint && !e->comm && !e->p2p && !e->peer_lo && !e->peer_hi) {  // one GPU only: with slabs the edge parts order their work around the exchange
             // no boundary or source node lies on the shell: the shell update commutes with the boundary kernels
             CU(cudaEventRecord(e->ev_abc0, s));
             CU(cudaStreamWaitEvent(e->s_abc, e->ev_abc0, 0));
@@ -1128,6 +1197,19 @@ static int exchange(pffdtd_engine *e, void *unew, cudaStream_t s) {
       if (e->peer_hi) CU(push(e->peer_hi, 0, (size_t)(e->Nx - 2)));
       return 0;
    }
+   if (e->p2p) {
+      const int role = e->cur ^ 1;
+      if (e->ipc_u_lo[role]) {
+         CU(cudaMemcpyAsync((char *)e->ipc_u_lo[role] + (size_t)(e->nx_lo - 1) * pb, g + pb, pb, cudaMemcpyDeviceToDevice, s));
+         CU(cudaMemcpyAsync(e->ipc_flags_lo + 1, e->flags + 2, 8, cudaMemcpyDeviceToDevice, s));  // I am its upper neighbour
+      }
+      if (e->ipc_u_hi[role]) {
+         CU(cudaMemcpyAsync((char *)e->ipc_u_hi[role], g + (size_t)(e->Nx - 2) * pb, pb, cudaMemcpyDeviceToDevice, s));
+         CU(cudaMemcpyAsync(e->ipc_flags_hi + 0, e->flags + 2, 8, cudaMemcpyDeviceToDevice, s));  // I am its lower neighbour
+      }
+      CU(cudaGetLastError());
+      return 0;
+   }
    if (!e->comm) return 0;
    NC(g_nccl.GroupStart());
    if (!e->x_lo_edge) {
@@ -1149,7 +1231,7 @@ static int exchange(pffdtd_engine *e, void *unew, cudaStream_t s) {
 enum { PH_A = 1, PH_X = 2, PH_B = 4, PH_ALL = 7 };
 
 static bool step_split(const pffdtd_engine *e) {
-   const bool linked = e->comm || e->peer_lo || e->peer_hi;
+   const bool linked = e->comm || e->p2p || e->peer_lo || e->peer_hi;
    return linked && (!e->x_lo_edge || !e->x_hi_edge) && e->overlap && e->sorted && e->Nx >= 5;
 }
 
@@ -1164,7 +1246,7 @@ static int step_impl(pffdtd_engine *e, i64 n, int phases) {
    cudaStream_t s = e->s_main;
    const i64 Nx = e->Nx;
    int rc;
-   const bool linked = e->comm || e->peer_lo || e->peer_hi;
+   const bool linked = e->comm || e->p2p || e->peer_lo || e->peer_hi;
    const bool lo = linked && !e->x_lo_edge, hi = linked && !e->x_hi_edge;
    const bool split = step_split(e);
    // the step's opening belongs to PH_A when the step is split around the exchange, else to PH_B (PH_A is then empty)
@@ -1178,6 +1260,10 @@ static int step_impl(pffdtd_engine *e, i64 n, int phases) {
       if (e->comm_pending) {
          CU(cudaStreamWaitEvent(s, e->ev_comm, 0));
          e->comm_pending = 0;
+      }
+      if (e->p2p) {
+         pf::k_p2p_wait<<<1, 1, 0, s>>>(e->flags, e->ipc_flags_lo != nullptr, e->ipc_flags_hi != nullptr, e->flags + 2);
+         e->launches += 1;
       }
       // (single process: the neighbours pushed them; their events were recorded when the host queued their previous step)
       if (e->peer_lo && n > e->first_step) CU(cudaStreamWaitEvent(s, e->peer_lo->ev_push, 0));
@@ -1338,7 +1424,7 @@ extern "C" int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps
    if (!e) return fail(PFFDTD_EINVAL, "NULL engine");
    if (nsteps < 0 || nstart < 0 || nstart + nsteps > e->Nt)
       return fail(PFFDTD_EINVAL, "steps [%lld,%lld) outside [0,%lld)", (long long)nstart, (long long)(nstart + nsteps), (long long)e->Nt);
-   if ((!e->x_lo_edge || !e->x_hi_edge) && !e->comm && !e->manual_halo)
+   if ((!e->x_lo_edge || !e->x_hi_edge) && !e->comm && !e->p2p && !e->manual_halo)
       return fail(PFFDTD_ESTATE, e->peer_lo || e->peer_hi ? "slab of a pffdtd_multi: step it with pffdtd_multi_run_steps"
                                                          : "slab engine without communicator: call pffdtd_comm_init");
    CU(cudaSetDevice(e->device));
@@ -1348,7 +1434,7 @@ extern "C" int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps
       // two steps bring `cur` back: a captured pair replays as one CUDA graph (fused or not, one GPU or a slab with its
       // halo exchange), once the halos are clean and the first plain steps have sized the launches and opened the
       // NCCL connections.  Both grid roles are captured at the first use, so no later call pays for a capture.
-      if (e->comm && graphable(e)) {
+      if (e->comm && !e->p2p && graphable(e)) {
          // a slab with an NCCL communicator: the work before and after the exchange replays from two graphs per grid role, the
          // exchange (event, ncclSend/ncclRecv on the comm stream, event) is issued eagerly between them
          const int c = e->cur;
@@ -1378,7 +1464,7 @@ extern "C" int pffdtd_run_steps(pffdtd_engine *e, int64_t nstart, int64_t nsteps
          e->steps_done = n;
          continue;
       }
-      const bool graph_ok = nend - n >= 2 && graphable(e) && !e->comm;
+      const bool graph_ok = nend - n >= 2 && graphable(e) && (!e->comm || e->p2p);
       if (graph_ok) {
          const int c = e->cur;
          int rc = join_comm(e);
@@ -1411,13 +1497,18 @@ extern "C" int pffdtd_sync(pffdtd_engine *e) {
    CU(cudaSetDevice(e->device));
    CU(cudaStreamSynchronize(e->s_main));
    CU(cudaStreamSynchronize(e->s_comm));
+   if (e->p2p && e->flags) {
+      long long err = 0;
+      CU(cudaMemcpy(&err, e->flags + 3, 8, cudaMemcpyDeviceToHost));
+      if (err) return fail(PFFDTD_ESTATE, "halo exchange over peer memory: a neighbour's plane never arrived (the wait gave up)");
+   }
    return PFFDTD_OK;
 }
 
 extern "C" int pffdtd_step_host(pffdtd_engine *e, int64_t n, const double *in_samples, double *out_samples) {
    if (!e) return fail(PFFDTD_EINVAL, "NULL engine");
    if (n < 0 || n >= e->Nt) return fail(PFFDTD_EINVAL, "step %lld outside [0,%lld)", (long long)n, (long long)e->Nt);
-   if ((!e->x_lo_edge || !e->x_hi_edge) && !e->comm && !e->manual_halo)
+   if ((!e->x_lo_edge || !e->x_hi_edge) && !e->comm && !e->p2p && !e->manual_halo)
       return fail(PFFDTD_ESTATE, "slab engine without communicator: call pffdtd_comm_init");
    CU(cudaSetDevice(e->device));
    const bool has_in = in_samples && e->Ns, has_out = out_samples && e->Nr;
@@ -1426,7 +1517,7 @@ extern "C" int pffdtd_step_host(pffdtd_engine *e, int64_t n, const double *in_sa
       else memcpy(e->h_in, in_samples, (size_t)e->Ns * 8);
    }
    int rc = PFFDTD_OK;
-   if (has_in && has_out && graphable(e) && !e->comm) {
+   if (has_in && has_out && graphable(e) && (!e->comm || e->p2p)) {
       // H2D of the source samples, the step, D2H of the receiver samples: one replayed graph per grid role
       const int c = e->cur;
       if ((rc = join_comm(e))) return rc;

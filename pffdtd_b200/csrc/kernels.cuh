@@ -468,6 +468,31 @@ __global__ void k_io(const Real *__restrict__ u1, Real *__restrict__ u0, const i
    }
 }
 
+// Halo exchange between PROCESSES over peer memory (engine.cu "p2p").  Every slab counts its steps in a device word `seq`.
+// A step starts with k_p2p_wait: it spins until each neighbour's flag has reached the number of steps done so far (the
+// neighbour has delivered the plane of every earlier step), then counts the step.  After the step's edge planes are final they
+// are copied into the neighbour's halo planes through a CUDA IPC mapping of its grid, and the same stream then copies `seq`
+// into the neighbour's flag word -- two copy-engine transfers, no kernel: the persistent air kernel holds every SM, so a
+// signalling kernel (or NCCL's) would only run once it drains, which is why round 1's "overlapped" NCCL exchange never overlapped.
+// The counters live on the device, so the step replays from graphs.  A wait that lasts longer than ~20 s (a dead neighbour)
+// gives up and raises the error word instead of hanging the GPU.
+__global__ void k_p2p_wait(volatile long long *flags, int need_lo, int need_hi, long long *seq) {
+   const long long done = *seq;
+   const long long t0 = clock64();
+   for (int k = 0; k < 2; k++) {
+      if (!(k == 0 ? need_lo : need_hi)) continue;
+      while (flags[k] < done) {
+         __nanosleep(200);
+         if (clock64() - t0 > 40000000000ll) {
+            flags[3] = 1;  // error word, read by pffdtd_sync
+            break;
+         }
+      }
+   }
+   __threadfence_system();
+   *seq = done + 1;
+}
+
 // device step counter: set at the start of a batch of steps, advanced at the end of every step
 __global__ void k_set_n(i64 *d_n, i64 v) { *d_n = v; }
 __global__ void k_tick(i64 *d_n) { *d_n += 1; }

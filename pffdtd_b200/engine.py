@@ -20,6 +20,7 @@ LIB_PATH = HERE / "libpffdtd_b200.so"
 HEADER = HERE.parent / "include" / "pffdtd_b200.h"
 
 OK, EINVAL, ECUDA, ENCCL, ESTATE = 0, -1, -2, -3, -4
+PEER_BLOB = 256  # PFFDTD_PEER_BLOB
 
 
 class pffdtd_energy_desc(C.Structure):
@@ -63,6 +64,8 @@ def lib():
     L.pffdtd_destroy.argtypes = [vp]
     L.pffdtd_comm_unique_id.argtypes = [vp]
     L.pffdtd_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.pffdtd_peer_export.argtypes = [vp, vp]
+    L.pffdtd_peer_connect.argtypes = [vp, vp, vp]
     L.pffdtd_set_option.argtypes = [vp, C.c_char_p, i64]
     L.pffdtd_get_stat.argtypes = [vp, C.c_char_p, dp]
     L.pffdtd_reset_stats.argtypes = [vp]
@@ -157,6 +160,19 @@ class Engine:
         _prefer_torch_nccl()
         buf = C.create_string_buffer(uid, 128)
         _check(self.L.pffdtd_comm_init(self.h, buf, rank, nranks))
+
+    def peer_export(self) -> bytes:
+        """this slab's blob for the halo exchange over peer memory (CUDA IPC handles of its grids and flag words)"""
+        buf = C.create_string_buffer(PEER_BLOB)
+        _check(self.L.pffdtd_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_connect(self, blob_lo, blob_hi):
+        """map the neighbours' grids (None at an end of the grid); from now on the step exchanges its halo planes by
+        device-to-device copies and device-side flags instead of NCCL"""
+        lo = C.create_string_buffer(blob_lo, PEER_BLOB) if blob_lo else None
+        hi = C.create_string_buffer(blob_hi, PEER_BLOB) if blob_hi else None
+        _check(self.L.pffdtd_peer_connect(self.h, lo, hi))
 
     def set_option(self, key: str, value: int):
         _check(self.L.pffdtd_set_option(self.h, key.encode(), int(value)))

@@ -81,3 +81,31 @@ def exchange_planes(send_lo, send_hi, rank, world):
     for q in reqs:
         q.wait()
     return (None if from_lo is None else from_lo.numpy()), (None if from_hi is None else from_hi.numpy())
+
+
+def connect_peers(eng, rank, world):
+    """halo exchange over peer memory (pffdtd_peer_export / _connect) between the ranks of one node: every rank publishes its
+    blob, takes its neighbours'.  Returns True when connected; on any failure (GPUs without peer access, another node) every rank
+    keeps the NCCL exchange -- the decision is collective, so that neighbours never disagree."""
+    dist = init()
+    if dist is None or world == 1 or os.environ.get("PFFDTD_P2P", "1") == "0":
+        return False
+    try:
+        blob = eng.peer_export()
+    except Exception:  # noqa: BLE001
+        blob = None
+    blobs = [None] * world
+    dist.all_gather_object(blobs, blob)
+    ok = all(b is not None for b in blobs)
+    if ok:
+        try:
+            eng.peer_connect(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < world - 1 else None)
+        except Exception:  # noqa: BLE001
+            ok = False
+    oks = [None] * world
+    dist.all_gather_object(oks, ok)
+    if not all(oks):
+        if ok:
+            eng.set_option("p2p", 0)
+        return False
+    return True

@@ -111,6 +111,8 @@ class SimEngine:
     def _comm_init(self):
         uid = parallel.broadcast_bytes(comm_unique_id() if self.rank == 0 else None, src=0)
         self.eng.comm_init(uid, self.rank, self.world)
+        # GPUs of one node: the halo planes go straight into the neighbours' grids over peer memory (NCCL stays as the fallback)
+        self.p2p = parallel.connect_peers(self.eng, self.rank, self.world)
 
     # ---- running ----------------------------------------------------------------------------------
     def run_steps(self, nstart, nsteps):

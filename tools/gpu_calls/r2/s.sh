@@ -1,0 +1,18 @@
+#!/bin/bash
+# r2 call S (8 GPUs): is the edge-first split worth its ~10 short launches per step at 8 GPUs?  c5 with the exchange after the whole step
+cd "$GRAFT_REPO_ROOT" || exit 1
+O=gpurun_out
+runN() { n=$1; name=$2; shift; shift; timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n "$@" > $O/r2s_$name.json 2> $O/r2s_$name.err; python - <<PY
+import json
+try:
+    line=[l for l in open("$O/r2s_$name.json") if l.startswith("{")][-1]
+    d=json.loads(line); r=d["roofline"]
+    print("$name", "value %.1f e2e %.1f ms %.4f air_frac %.3f whole %.3f launches %d" % (d["value"], d.get("e2e",{}).get("value",0), d["ms_per_step"], r["frac"], r["whole_step_frac"], d["gpu_launches"]), d["config"].get("slab_planes"))
+    p=d.get("parity") or {}
+    print("   parity equal", p.get("equal_to_one_gpu_run"), "reduced grid bit exact", (p.get("reduced_grid_vs_cpu_engine") or {}).get("bit_exact"))
+except Exception as ex:
+    print("$name failed", ex); print(open("$O/r2s_$name.err").read()[-1500:])
+PY
+}
+runN 8 c5_n8_noov --steps 100 --warmup 10 --overlap 0
+runN 8 c5_n8_noov_equal --steps 100 --warmup 10 --overlap 0 --equal-slabs --no-parity
