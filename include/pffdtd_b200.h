@@ -184,6 +184,8 @@ int pffdtd_run_sim(const pffdtd_desc *desc, int device, double *u_out, double *e
 typedef struct pffdtd_multi pffdtd_multi; /* opaque */
 int pffdtd_multi_create(const pffdtd_desc *desc, int nslabs, const int *devices, int balance, pffdtd_multi **out);
 int pffdtd_multi_destroy(pffdtd_multi *m);
+/* Diagnostic (no device needed): first owned plane and number of owned planes of every slab as pffdtd_multi_create would cut `desc` */
+int pffdtd_slab_plan(const pffdtd_desc *desc, int nslabs, int balance, int64_t *starts, int64_t *sizes);
 /* number of slabs; planes[r] = owned planes of slab r (up to `max` entries) */
 int pffdtd_multi_slabs(pffdtd_multi *m, int64_t *planes, int max);
 /* the engine of one slab, for pffdtd_set_option / pffdtd_get_stat / pffdtd_read_grid (do not step or destroy it directly) */

@@ -1781,6 +1781,18 @@ static void slab_desc(const pffdtd_desc *d, i64 start, i64 size, bool first, boo
    s->d.out_ixyz = s->out.data(), s->d.in_sigs = s->insig.data();
 }
 
+// Diagnostic (no device needed): the slab plan pffdtd_multi_create would use for `desc`
+extern "C" int pffdtd_slab_plan(const pffdtd_desc *desc, int nslabs, int balance, int64_t *starts, int64_t *sizes) {
+   if (!desc || !starts || !sizes || nslabs < 1) return fail(PFFDTD_EINVAL, "bad slab plan arguments");
+   std::vector<double> cost;
+   if (balance) cost = plane_costs(desc);
+   std::vector<i64> st, sz;
+   int rc = slab_planes(desc->Nx, nslabs, balance ? &cost : nullptr, &st, &sz);
+   if (rc) return rc;
+   for (int r = 0; r < nslabs; r++) starts[r] = st[(size_t)r], sizes[r] = sz[(size_t)r];
+   return PFFDTD_OK;
+}
+
 extern "C" int pffdtd_multi_destroy(pffdtd_multi *m) {
    if (!m) return PFFDTD_OK;
    for (pffdtd_engine *e : m->eng)

@@ -82,6 +82,7 @@ def lib():
     ip = C.POINTER(C.c_int)
     L.pffdtd_multi_create.argtypes = [C.POINTER(pffdtd_desc), C.c_int, ip, C.c_int, C.POINTER(vp)]
     L.pffdtd_multi_destroy.argtypes = [vp]
+    L.pffdtd_slab_plan.argtypes = [C.POINTER(pffdtd_desc), C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64)]
     L.pffdtd_multi_slabs.argtypes = [vp, C.POINTER(i64), C.c_int]
     L.pffdtd_multi_engine.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.pffdtd_multi_run_steps.argtypes = [vp, i64, i64]

@@ -197,3 +197,22 @@ def test_duplicate_source_nodes_are_sorted_and_split():
     want = Oracle(dup).run_all()
     assert not np.array_equal(want, Oracle(sd).run_all())
     assert np.array_equal(_run_slabs_in_process(dup, 2), want)
+
+
+@pytest.mark.parametrize("name", ("cart_lossy_mb11", "cart_tight", "fcc2_lossy"))
+def test_library_slab_plan_is_the_python_one(name):
+    """pffdtd_multi_create (one host thread, all GPUs) cuts the grid with the C++ twins of SimData.plane_costs / slab_planes: same
+    planes for the reference's equal split and for the cost-weighted one, and slabs past the grid's capacity are refused"""
+    import ctypes as C
+    from pffdtd_b200 import engine
+    L = engine.lib()
+    sd = make_sim_data(name, 2).sorted()
+    d = sd.desc()
+    for n in (1, 2, 3, 4):
+        for balance in (0, 1):
+            st, sz = (C.c_int64 * n)(), (C.c_int64 * n)()
+            assert L.pffdtd_slab_plan(C.byref(d), n, balance, st, sz) == 0, L.pffdtd_last_error()
+            want = SimData.slab_planes(sd.Nx, n, cost=sd.plane_costs() if balance else None)
+            assert (list(st), list(sz)) == (list(want[0]), list(want[1])), (name, n, balance)
+    st, sz = (C.c_int64 * 64)(), (C.c_int64 * 64)()
+    assert L.pffdtd_slab_plan(C.byref(d), sd.Nx, 1, st, sz) != 0
