@@ -60,7 +60,7 @@ struct AirTma {
    void *base[2] = {nullptr, nullptr};
    void *mask = nullptr;
    int cfg = 0;         // tile configuration, see PF_AIR_CONFIGS
-   int z_edge = 0;      // the shell node z = Nz-2 opens a z tile of this configuration: no fused step
+   int z_edge = 0;      // the shell node z = Nz-2 opens a z tile of this configuration (7-point: handled in the kernel; 13-point: no fused step)
    int xc = 0;          // planes per (long) x-chunk of the work order, 0 = default
    int sm_count = 148;
    int slots = 0;       // resident CTAs of the chosen configuration on this device
@@ -420,7 +420,7 @@ __device__ __forceinline__ void abc_face_node(const FacesArgs<Real> &a, const in
 // full[s] flips when all bytes of a plane have landed in stage s, empty[s] when all NW consumer warps
 // are done with it.  Loads are numbered consecutively over all segments of the CTA; load i uses stage
 // i % S.  A segment of cnt planes loads planes xa-1 .. xa+cnt: the first and the last only as u1.
-template <typename Real, int RPT, int NW, int S, int MAXR, bool FCC, int LZ, bool SVC, bool FFUSE>
+template <typename Real, int RPT, int NW, int S, int MAXR, bool FCC, int LZ, bool SVC, bool FFUSE, bool ZE = false>
 __global__ void __maxnreg__(MAXR)
     k_air_tma_cart(const __grid_constant__ CUtensorMap map_u1, const __grid_constant__ CUtensorMap map_u0,
                    const __grid_constant__ CUtensorMap map_mk, Real *__restrict__ u0g, const AirJob jb, const Real a1, const Real a2,
@@ -1135,8 +1135,18 @@ __global__ void __maxnreg__(MAXR)
                // Every vector of an active row is stored, fully masked ones too: it may hold the z halo (mirror-on-write: a masked
                // node at z = 1 / Nz-2 must not keep the halo next to it from being refreshed) or a node the service warp finished
                // in the stage.  Masked elements carry their stage value.
-               st_vec<Real, VEC>(dst, o);
-               if (zhi_tile && khm + 2 == VEC) dst[VEC] = vm;  // z=Nz-1 opens the next vector, which nobody stores
+               // Where the z halo lands when its source z = Nz-3 is near the end of the vector:
+               //   tail1: z = Nz-1 opens the next vector, which nobody stores;
+               //   tail2: z = Nz-3 closes the vector, so z = Nz-1 is the SECOND element of the next one.  On grids with
+               //          Nz = 2 (mod tile width) that vector opens the next TILE (`lone`), whose only node is the shell node z = Nz-2:
+               //          its thread stores that one element alone, so that the halo written from here survives whichever tile runs first.
+               // (ZE: a kernel variant of its own for those grids -- the extra live values cost the ordinary kernel 1-2 %)
+               const bool tail1 = zhi_tile && khm + 2 == VEC, tail2 = ZE && zhi_tile && khm + 1 == VEC;
+               const bool lone = ZE && fuse && sg.z0 == Nz - 2;  // warp-uniform
+               if (lone) dst[0] = o[0];
+               else st_vec<Real, VEC>(dst, o);
+               if (tail1) dst[VEC] = vm;
+               if (tail2) dst[VEC + 1] = vm;
                if (rrole & 6u) {
                   // mirror source of a y / x halo: the same row goes there as well (warp-uniform, a few rows / planes)
                   const int y = ybase + r;
@@ -1145,8 +1155,10 @@ __global__ void __maxnreg__(MAXR)
                      const bool on = t == 1 ? y == 2 : t == 2 ? y == Ny - 3 : t == 3 ? (xrole & 2u) != 0 : (xrole & 4u) != 0;
                      if (on) {
                         Real *d = dst + (t == 1 ? -2 * (i64)Nzp : t == 2 ? 2 * (i64)Nzp : t == 3 ? -2 * jb.plane : 2 * jb.plane);
-                        st_vec<Real, VEC>(d, o);
-                        if (zhi_tile && khm + 2 == VEC) d[VEC] = vm;
+                        if (lone) d[0] = o[0];
+                        else st_vec<Real, VEC>(d, o);
+                        if (tail1) d[VEC] = vm;
+                        if (tail2) d[VEC + 1] = vm;
                      }
                   }
                }
@@ -1218,6 +1230,9 @@ static int air_tma_attr(int cfg) {
       if (rc == cudaSuccess && SVC)                                                                                                   \
          rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ, SVC, SVC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    AirCfg<Real, RPT, NW, S, LZ, SVC>::SMEM_BYTES);                                                    \
+      if (rc == cudaSuccess)                                                                                                          \
+         rc = cudaFuncSetAttribute(k_air_tma_cart<Real, RPT, NW, S, MAXR, false, LZ, SVC, false, true>,                               \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, AirCfg<Real, RPT, NW, S, LZ, SVC>::SMEM_BYTES);       \
    }
    PF_AIR_CONFIGS(X)
 #undef X
@@ -1341,7 +1356,8 @@ static int air_tma_launch_cfg(AirTma *t, int cur, Real *u0, i64 xb, i64 xe, Real
    // (the fused 13-point step is its own kernel, compiled for the service-warp configurations only: FFUSE = SVC there)
    auto kern = t->fcc ? ((eg.fuse && SVC) ? k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ, SVC, SVC>
                                           : k_air_tma_cart<Real, RPT, NW, S, MAXR, true, LZ, SVC, false>)
-                      : k_air_tma_cart<Real, RPT, NW, S, MAXR, false, LZ, SVC, false>;
+                      : (t->z_edge ? k_air_tma_cart<Real, RPT, NW, S, MAXR, false, LZ, SVC, false, true>
+                                   : k_air_tma_cart<Real, RPT, NW, S, MAXR, false, LZ, SVC, false, false>);
    if (t->slots <= 0) {
       int per_sm = 0;
       cudaError_t rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, C::SMEM_BYTES);

@@ -346,7 +346,9 @@ static bool want_svc(const pffdtd_engine *e) { return e->svc_want < 0 ? e->fcc =
 static bool step_fused(const pffdtd_engine *e) {
    // (the 13-point kernel has no stash for the shell's z faces: its fused step needs the service warp to do them)
    const bool fcc_ok = e->fcc == 0 || (want_svc(e) && e->tma.svc && e->bn_off_abc && e->abc_disjoint);
-   return want_fuse(e) && e->fuse_ok && fcc_ok && e->air_kernel == 1 && e->tma.ok && !e->tma.z_edge && !e->energy_on;
+   // (a grid whose shell node z = Nz-2 opens a z tile: the 7-point kernel handles it -- see `lone` / `tail2` in air_tma.cuh --, the
+   // fused 13-point epilogue does not)
+   return want_fuse(e) && e->fuse_ok && fcc_ok && e->air_kernel == 1 && e->tma.ok && !(e->tma.z_edge && e->fcc != 0) && !e->energy_on;
 }
 static bool svc_eligible(const pffdtd_engine *e) { return want_svc(e) && e->bn_off_abc && e->tma.ok && e->tma.svc && !e->energy_on; }
 static int build_service(pffdtd_engine *e) {
