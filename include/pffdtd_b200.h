@@ -197,6 +197,41 @@ int pffdtd_multi_read_outputs(pffdtd_multi *m, int64_t n0, int64_t n1, double *u
 /* run_sim() over every visible device (nslabs <= 0) or `nslabs` slabs: create, run Nt steps, write u_out[Nr*Nt], destroy */
 int pffdtd_run_sim_multi(const pffdtd_desc *desc, int nslabs, const int *devices, double *u_out, double *elapsed_s);
 
+/* ---- the voxeliser's hot stage on the GPU.  VoxScene.calc_adj (python/voxelizer/vox_scene.py:95-440) casts, for
+ * every grid point near a triangle, a ray towards each of its 6 (12) neighbours and cuts the link where the ray meets the surface within
+ * one grid step; the reference does it voxel by voxel in numpy over a process pool.  Here one thread block takes one voxel of the
+ * reference's voxel grid (same voxels, same per-voxel triangle lists, same order of triangles and directions, the same arithmetic in
+ * double -- pffdtd_b200/csrc/vox_core.h), so bn_ixyz / adj_bn and the nearest triangle of every boundary node come out identical.
+ * Everything calc_adj reads travels in the descriptor (host arrays, borrowed for the call). */
+typedef struct pffdtd_vox_desc {
+   int32_t struct_size; /* = sizeof(pffdtd_vox_desc) */
+   int32_t NN;          /* 6 Cartesian, 12 FCC */
+   int32_t fcc;         /* FCC: only points of even parity take part (vox_scene.py:176-179) */
+   int32_t reserved;
+   int64_t Nx, Ny, Nz;
+   const double *xv, *yv, *zv;     /* grid coordinates (cart_grid) */
+   double hf, c_bb, c_near, c_far; /* hf; hf*(1+R_EPS); R_EPS*hf; (1+R_EPS)*hf   (vox_scene.py:60, 188-228) */
+   double d_eps, cp_eps;           /* 1e-3*h; 1e-6                              (vox_scene.py:213, tri_ray_intersection.py:67) */
+   const double *vvh;              /* [NN][3] h * direction                     (vox_scene.py:85) */
+   const double *ray_un;           /* [NN][3] normalise(uvv[k])                 (tri_ray_intersection.py:77) */
+   int64_t Nvox;                   /* non-empty voxels, in the reference's order (vox_grid.nonempty_idx) */
+   const int64_t *vox_start;       /* [Nvox][3] ixyz_start */
+   const int64_t *vox_shape;       /* [Nvox][3] Nhxyz (points, halo layer included) */
+   const int64_t *vox_tri_off;     /* [Nvox+1] into vox_tri */
+   const int32_t *vox_tri;         /* triangle indices of every voxel, in the voxel's own order */
+   int64_t Ntris;
+   const double *unor, *cent, *bmin, *bmax; /* [Ntris][3]    (tris_precompute.py) */
+   const double *v;                         /* [Ntris][3][3] */
+   const double *eab, *ebc, *eca;           /* [Ntris][3] outward unit edge normals */
+} pffdtd_vox_desc;
+typedef struct pffdtd_vox pffdtd_vox; /* opaque: the result of one run */
+int pffdtd_vox_run(const pffdtd_vox_desc *d, int device, pffdtd_vox **out);
+int64_t pffdtd_vox_count(const pffdtd_vox *r); /* boundary nodes found */
+/* bn_ixyz[Nb] (voxel by voxel in the reference's order, ascending inside a voxel), adj[Nb][NN] (1 = link open), tidx[Nb] (nearest
+ * triangle), ndist[Nb] (its hit distance) */
+int pffdtd_vox_read(const pffdtd_vox *r, int64_t *bn_ixyz, uint8_t *adj, int32_t *tidx, double *ndist);
+int pffdtd_vox_free(pffdtd_vox *r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 #include "air_tma.cuh"
 #include "energy.cuh"
+#include "vox.cuh"
 
 using pf::i64;
 
@@ -1925,4 +1926,138 @@ extern "C" int pffdtd_run_sim_multi(const pffdtd_desc *desc, int nslabs, const i
    pffdtd_multi_destroy(m);
    g_err = keep;
    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the voxeliser's ray casting (VoxScene.calc_adj) -- see vox.cuh
+// ------------------------------------------------------------------------------------------------
+struct pffdtd_vox {
+   int NN = 0;
+   std::vector<int64_t> bn;
+   std::vector<uint8_t> adj;
+   std::vector<int32_t> tidx;
+   std::vector<double> ndist;
+};
+
+extern "C" int pffdtd_vox_run(const pffdtd_vox_desc *d, int device, pffdtd_vox **out) {
+   if (!d || !out) return fail(PFFDTD_EINVAL, "NULL argument");
+   if (d->struct_size != (int32_t)sizeof(pffdtd_vox_desc)) return fail(PFFDTD_EINVAL, "pffdtd_vox_desc size mismatch");
+   if ((d->NN != 6 && d->NN != 12) || d->Nvox < 0 || d->Ntris < 0) return fail(PFFDTD_EINVAL, "bad voxeliser description");
+   int ndev = 0;
+   CU(cudaGetDeviceCount(&ndev));
+   if (device < 0 || device >= ndev) return fail(PFFDTD_ECUDA, "no CUDA device %d (%d visible)", device, ndev);
+   CU(cudaSetDevice(device));
+   std::vector<void *> dev;
+   auto freeall = [&]() {
+      for (void *p : dev) cudaFree(p);
+   };
+   auto up = [&](const void *src, size_t bytes, const void **dst) -> int {
+      void *p = nullptr;
+      if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return 1;
+      dev.push_back(p);
+      if (bytes && cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+      *dst = p;
+      return 0;
+   };
+   // points of every voxel (halo layer included)
+   std::vector<long long> pt_off((size_t)d->Nvox + 1, 0);
+   for (i64 v = 0; v < d->Nvox; v++) {
+      const int64_t *sh = d->vox_shape + 3 * v, *st = d->vox_start + 3 * v;
+      if (sh[0] < 3 || sh[1] < 3 || sh[2] < 3 || st[0] < 0 || st[1] < 0 || st[2] < 0 || st[0] + sh[0] > d->Nx || st[1] + sh[1] > d->Ny ||
+          st[2] + sh[2] > d->Nz || sh[0] * sh[1] * sh[2] > 0x7fffffff)
+         return fail(PFFDTD_EINVAL, "voxel %lld outside the grid", (long long)v);
+      pt_off[(size_t)v + 1] = pt_off[(size_t)v] + sh[0] * sh[1] * sh[2];
+   }
+   const size_t npt = (size_t)pt_off[(size_t)d->Nvox];
+   const i64 ntl = d->Nvox ? d->vox_tri_off[d->Nvox] : 0;
+   pf::VoxArgs a;
+   memset(&a, 0, sizeof a);
+   a.c = VoxConst{d->hf, d->c_bb, d->c_near, d->c_far, d->d_eps, d->cp_eps, -2.220446049250313e-16};
+   a.NN = d->NN, a.fcc = d->fcc, a.Ny = d->Ny, a.Nz = d->Nz;
+   int bad = 0;
+   bad |= up(d->xv, (size_t)d->Nx * 8, (const void **)&a.xv) | up(d->yv, (size_t)d->Ny * 8, (const void **)&a.yv) | up(d->zv, (size_t)d->Nz * 8, (const void **)&a.zv);
+   bad |= up(d->vvh, (size_t)d->NN * 24, (const void **)&a.vvh) | up(d->ray_un, (size_t)d->NN * 24, (const void **)&a.ray_un);
+   bad |= up(d->vox_start, (size_t)d->Nvox * 24, (const void **)&a.vox_start) | up(d->vox_shape, (size_t)d->Nvox * 24, (const void **)&a.vox_shape);
+   bad |= up(d->vox_tri_off, ((size_t)d->Nvox + 1) * 8, (const void **)&a.vox_tri_off) | up(pt_off.data(), pt_off.size() * 8, (const void **)&a.pt_off);
+   bad |= up(d->vox_tri, (size_t)ntl * 4, (const void **)&a.vox_tri);
+   const size_t t3 = (size_t)d->Ntris * 24;
+   bad |= up(d->unor, t3, (const void **)&a.unor) | up(d->cent, t3, (const void **)&a.cent) | up(d->bmin, t3, (const void **)&a.bmin) | up(d->bmax, t3, (const void **)&a.bmax);
+   bad |= up(d->v, t3 * 3, (const void **)&a.v) | up(d->eab, t3, (const void **)&a.eab) | up(d->ebc, t3, (const void **)&a.ebc) | up(d->eca, t3, (const void **)&a.eca);
+   const void *p_nd = nullptr, *p_ti = nullptr, *p_cu = nullptr, *p_fl = nullptr;
+   bad |= up(nullptr, 0, &p_nd) | up(nullptr, 0, &p_ti) | up(nullptr, 0, &p_cu) | up(nullptr, 0, &p_fl);
+   if (!bad && npt) {
+      // (the four scratch arrays are sized now that the tables are up)
+      for (int k = 0; k < 4; k++) cudaFree(dev[dev.size() - 4 + (size_t)k]);
+      dev.resize(dev.size() - 4);
+      void *q = nullptr;
+      const size_t sizes[4] = {npt * 8, npt * 4, npt * 2, npt};
+      const void **dst[4] = {&p_nd, &p_ti, &p_cu, &p_fl};
+      for (int k = 0; k < 4 && !bad; k++) {
+         if (cudaMalloc(&q, sizes[k]) != cudaSuccess) bad = 1;
+         else dev.push_back(q), *dst[k] = q;
+      }
+   }
+   if (bad) {
+      freeall();
+      return fail(PFFDTD_ECUDA, "voxeliser: device allocation / upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+   }
+   a.ndist = (double *)p_nd, a.tidx = (int *)p_ti, a.cut = (unsigned short *)p_cu, a.fl = (unsigned char *)p_fl;
+   pffdtd_vox *R = new pffdtd_vox();
+   R->NN = d->NN;
+   cudaError_t ce = cudaSuccess;
+   std::vector<double> h_nd(npt);
+   std::vector<int> h_ti(npt);
+   std::vector<unsigned short> h_cu(npt);
+   std::vector<unsigned char> h_fl(npt);
+   if (d->Nvox && npt) {
+      pf::k_vox_calc_adj<<<(unsigned)d->Nvox, 256>>>(a);
+      ce = cudaGetLastError();
+      if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+      if (ce == cudaSuccess) ce = cudaMemcpy(h_nd.data(), a.ndist, npt * 8, cudaMemcpyDeviceToHost);
+      if (ce == cudaSuccess) ce = cudaMemcpy(h_ti.data(), a.tidx, npt * 4, cudaMemcpyDeviceToHost);
+      if (ce == cudaSuccess) ce = cudaMemcpy(h_cu.data(), a.cut, npt * 2, cudaMemcpyDeviceToHost);
+      if (ce == cudaSuccess) ce = cudaMemcpy(h_fl.data(), a.fl, npt, cudaMemcpyDeviceToHost);
+   }
+   freeall();
+   if (ce != cudaSuccess) {
+      delete R;
+      return fail(PFFDTD_ECUDA, "voxeliser kernel: %s", cudaGetErrorString(ce));
+   }
+   // boundary points of every voxel's interior, voxel by voxel, ascending inside a voxel (vox_scene.py:246-279, 343-366); a point
+   // lying on the surface has every link cut (:244)
+   for (i64 v = 0; v < d->Nvox; v++) {
+      const int64_t *sh = d->vox_shape + 3 * v, *st = d->vox_start + 3 * v;
+      const size_t base = (size_t)pt_off[(size_t)v];
+      for (i64 ix = 1; ix <= sh[0] - 2; ix++)
+         for (i64 iy = 1; iy <= sh[1] - 2; iy++)
+            for (i64 iz = 1; iz <= sh[2] - 2; iz++) {
+               const size_t p = base + (size_t)((ix * sh[1] + iy) * sh[2] + iz);
+               unsigned cu = h_cu[p];
+               if (h_fl[p] & 2u) cu = (1u << d->NN) - 1u;
+               if (!cu) continue;
+               R->bn.push_back(((st[0] + ix) * d->Ny + (st[1] + iy)) * d->Nz + (st[2] + iz));
+               for (int k = 0; k < d->NN; k++) R->adj.push_back((cu >> k) & 1u ? 0 : 1);
+               R->tidx.push_back(h_ti[p]);
+               R->ndist.push_back(h_nd[p]);
+            }
+   }
+   *out = R;
+   return PFFDTD_OK;
+}
+
+extern "C" int64_t pffdtd_vox_count(const pffdtd_vox *r) { return r ? (int64_t)r->bn.size() : -1; }
+
+extern "C" int pffdtd_vox_read(const pffdtd_vox *r, int64_t *bn_ixyz, uint8_t *adj, int32_t *tidx, double *ndist) {
+   if (!r || !bn_ixyz || !adj || !tidx || !ndist) return fail(PFFDTD_EINVAL, "NULL argument");
+   if (r->bn.empty()) return PFFDTD_OK;
+   memcpy(bn_ixyz, r->bn.data(), r->bn.size() * 8);
+   memcpy(adj, r->adj.data(), r->adj.size());
+   memcpy(tidx, r->tidx.data(), r->tidx.size() * 4);
+   memcpy(ndist, r->ndist.data(), r->ndist.size() * 8);
+   return PFFDTD_OK;
+}
+
+extern "C" int pffdtd_vox_free(pffdtd_vox *r) {
+   delete r;
+   return PFFDTD_OK;
 }
