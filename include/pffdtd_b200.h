@@ -232,6 +232,24 @@ int64_t pffdtd_vox_count(const pffdtd_vox *r); /* boundary nodes found */
 int pffdtd_vox_read(const pffdtd_vox *r, int64_t *bn_ixyz, uint8_t *adj, int32_t *tidx, double *ndist);
 int pffdtd_vox_free(pffdtd_vox *r);
 
+/* The stage before it: VoxGridBase.fill (python/voxelizer/vox_grid_base.py:67-176) decides which triangles meet which voxel with the
+ * Schwarz-Seidel triangle / box test of common/tri_box_intersection.py:84-120, voxel by voxel in numpy (minutes at production size).
+ * Here one warp takes one voxel and scans the triangle table; the lists come out in ascending triangle order, as the reference's. */
+typedef struct pffdtd_voxfill_desc {
+   int32_t struct_size; /* = sizeof(pffdtd_voxfill_desc) */
+   int32_t reserved;
+   int64_t Nvox;                /* every voxel of the grid (vox_grid.voxels) */
+   const double *vbmin, *vbmax; /* [Nvox][3] the voxels' boxes (vox_grid.py:128-129) */
+   int64_t Ntris;
+   const double *v;                        /* [Ntris][3][3]  (tris_precompute.py) */
+   const double *nor, *cent, *bmin, *bmax; /* [Ntris][3] area-scaled normal, centroid, bounding box */
+} pffdtd_voxfill_desc;
+typedef struct pffdtd_voxfill pffdtd_voxfill;
+int pffdtd_voxfill_run(const pffdtd_voxfill_desc *d, int device, pffdtd_voxfill **out);
+int64_t pffdtd_voxfill_count(const pffdtd_voxfill *r); /* total length of the lists */
+int pffdtd_voxfill_read(const pffdtd_voxfill *r, int64_t *off /* [Nvox+1] */, int32_t *tri /* [count] */);
+int pffdtd_voxfill_free(pffdtd_voxfill *r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,3 +103,30 @@ extern "C" int voxhost_read(const void *h, int64_t *bn, uint8_t *adj, int32_t *t
    return 0;
 }
 extern "C" void voxhost_free(void *h) { delete (HostResult *)h; }
+
+// VoxGridBase.fill (python/voxelizer/vox_grid_base.py:67-176) sequentially: every voxel against every triangle, ascending
+struct HostFill {
+   std::vector<int64_t> off;
+   std::vector<int32_t> tri;
+};
+extern "C" void *voxhost_fill(const pffdtd_voxfill_desc *d) {
+   if (!d || d->struct_size != (int32_t)sizeof(pffdtd_voxfill_desc)) return nullptr;
+   HostFill *R = new HostFill();
+   R->off.assign((size_t)d->Nvox + 1, 0);
+   for (int64_t vi = 0; vi < d->Nvox; vi++) {
+      for (int64_t ti = 0; ti < d->Ntris; ti++)
+         if (pfv_tri_box(d->vbmin + 3 * vi, d->vbmax + 3 * vi, d->v + 9 * ti, d->nor + 3 * ti, d->cent + 3 * ti, d->bmin + 3 * ti, d->bmax + 3 * ti))
+            R->tri.push_back((int32_t)ti);
+      R->off[(size_t)vi + 1] = (int64_t)R->tri.size();
+   }
+   return R;
+}
+extern "C" int64_t voxhost_fill_count(const void *h) { return h ? (int64_t)((const HostFill *)h)->tri.size() : -1; }
+extern "C" int voxhost_fill_read(const void *h, int64_t *off, int32_t *tri) {
+   const HostFill *R = (const HostFill *)h;
+   if (!R) return -1;
+   memcpy(off, R->off.data(), R->off.size() * 8);
+   if (!R->tri.empty()) memcpy(tri, R->tri.data(), R->tri.size() * 4);
+   return 0;
+}
+extern "C" void voxhost_fill_free(void *h) { delete (HostFill *)h; }

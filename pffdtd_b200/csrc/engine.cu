@@ -2061,3 +2061,96 @@ extern "C" int pffdtd_vox_free(pffdtd_vox *r) {
    delete r;
    return PFFDTD_OK;
 }
+
+// VoxGridBase.fill: triangle lists of every voxel -- see vox.cuh (k_vox_fill)
+struct pffdtd_voxfill {
+   std::vector<int64_t> off;
+   std::vector<int32_t> tri;
+};
+
+extern "C" int pffdtd_voxfill_run(const pffdtd_voxfill_desc *d, int device, pffdtd_voxfill **out) {
+   if (!d || !out) return fail(PFFDTD_EINVAL, "NULL argument");
+   if (d->struct_size != (int32_t)sizeof(pffdtd_voxfill_desc)) return fail(PFFDTD_EINVAL, "pffdtd_voxfill_desc size mismatch");
+   if (d->Nvox < 0 || d->Ntris < 0 || d->Nvox > 0x7fffffffLL / 8 * 8 || d->Ntris > 0x7fffffffLL - 32)
+      return fail(PFFDTD_EINVAL, "bad voxel grid description");
+   int ndev = 0;
+   CU(cudaGetDeviceCount(&ndev));
+   if (device < 0 || device >= ndev) return fail(PFFDTD_ECUDA, "no CUDA device %d (%d visible)", device, ndev);
+   CU(cudaSetDevice(device));
+   std::vector<void *> dev;
+   auto freeall = [&]() {
+      for (void *p : dev) cudaFree(p);
+   };
+   auto up = [&](const void *src, size_t bytes, const void **dst) -> int {
+      void *p = nullptr;
+      if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return 1;
+      dev.push_back(p);
+      if (bytes && src && cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+      *dst = p;
+      return 0;
+   };
+   pf::VoxFillArgs a;
+   memset(&a, 0, sizeof a);
+   a.Nvox = d->Nvox, a.Ntris = d->Ntris;
+   const size_t t3 = (size_t)d->Ntris * 24, v3 = (size_t)d->Nvox * 24;
+   int bad = up(d->vbmin, v3, (const void **)&a.vbmin) | up(d->vbmax, v3, (const void **)&a.vbmax) | up(d->v, t3 * 3, (const void **)&a.v);
+   bad |= up(d->nor, t3, (const void **)&a.nor) | up(d->cent, t3, (const void **)&a.cent) | up(d->bmin, t3, (const void **)&a.bmin) | up(d->bmax, t3, (const void **)&a.bmax);
+   const void *p_cnt = nullptr, *p_off = nullptr;
+   bad |= up(nullptr, (size_t)d->Nvox * 8, &p_cnt) | up(nullptr, ((size_t)d->Nvox + 1) * 8, &p_off);
+   if (bad) {
+      freeall();
+      return fail(PFFDTD_ECUDA, "voxel grid fill: device allocation / upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+   }
+   a.count = (long long *)p_cnt, a.off = (const long long *)p_off;
+   pffdtd_voxfill *R = new pffdtd_voxfill();
+   R->off.assign((size_t)d->Nvox + 1, 0);
+   cudaError_t ce = cudaSuccess;
+   if (d->Nvox && d->Ntris) {
+      const unsigned blocks = (unsigned)((d->Nvox + 7) / 8);
+      std::vector<long long> cnt((size_t)d->Nvox);
+      pf::k_vox_fill<false><<<blocks, 256>>>(a);
+      ce = cudaGetLastError();
+      if (ce == cudaSuccess) ce = cudaMemcpy(cnt.data(), a.count, cnt.size() * 8, cudaMemcpyDeviceToHost);
+      if (ce == cudaSuccess) {
+         for (i64 v = 0; v < d->Nvox; v++) R->off[(size_t)v + 1] = R->off[(size_t)v] + cnt[(size_t)v];
+         ce = cudaMemcpy((void *)a.off, R->off.data(), R->off.size() * 8, cudaMemcpyHostToDevice);
+      }
+      const size_t total = (size_t)R->off[(size_t)d->Nvox];
+      if (ce == cudaSuccess && total) {
+         void *q = nullptr;
+         ce = cudaMalloc(&q, total * 4);
+         if (ce == cudaSuccess) {
+            dev.push_back(q);
+            a.tri = (int *)q;
+            pf::k_vox_fill<true><<<blocks, 256>>>(a);
+            ce = cudaGetLastError();
+            R->tri.resize(total);
+            if (ce == cudaSuccess) ce = cudaMemcpy(R->tri.data(), a.tri, total * 4, cudaMemcpyDeviceToHost);
+         }
+      }
+   }
+   freeall();
+   if (ce != cudaSuccess) {
+      delete R;
+      return fail(PFFDTD_ECUDA, "voxel grid fill: %s", cudaGetErrorString(ce));
+   }
+   *out = R;
+   return PFFDTD_OK;
+}
+
+extern "C" int64_t pffdtd_voxfill_count(const pffdtd_voxfill *r) { return r ? (int64_t)r->tri.size() : -1; }
+
+extern "C" int pffdtd_voxfill_read(const pffdtd_voxfill *r, int64_t *off, int32_t *tri) {
+   if (!r || !off) return fail(PFFDTD_EINVAL, "NULL argument");
+   memcpy(off, r->off.data(), r->off.size() * 8);
+   if (!r->tri.empty()) {
+      if (!tri) return fail(PFFDTD_EINVAL, "NULL argument");
+      memcpy(tri, r->tri.data(), r->tri.size() * 4);
+   }
+   return PFFDTD_OK;
+}
+
+extern "C" int pffdtd_voxfill_free(pffdtd_voxfill *r) {
+   delete r;
+   return PFFDTD_OK;
+}

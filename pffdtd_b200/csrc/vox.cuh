@@ -94,4 +94,33 @@ __global__ void __launch_bounds__(256) k_vox_calc_adj(const VoxArgs a) {
    }
 }
 
+// VoxGridBase.fill (vox_grid_base.py:67-176): which triangles meet which voxel.  One warp per voxel; its lanes take 32 consecutive
+// triangles at a time, so that the hits of a voxel come out in ascending triangle order (the order calc_adj later depends on) from a
+// ballot and a population count.  Run twice: WRITE = false counts, WRITE = true fills the lists at the offsets the counts gave.
+struct VoxFillArgs {
+   long long Nvox, Ntris;
+   const double *vbmin, *vbmax, *v, *nor, *cent, *bmin, *bmax;
+   long long *count;      // [Nvox]
+   const long long *off;  // [Nvox + 1]
+   int *tri;
+};
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k_vox_fill(const VoxFillArgs a) {
+   const long long vi = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   if (vi >= a.Nvox) return;
+   const int lane = threadIdx.x & 31;
+   double lo[3], hi[3];
+   for (int j = 0; j < 3; j++) lo[j] = a.vbmin[3 * vi + j], hi[j] = a.vbmax[3 * vi + j];
+   long long run = WRITE ? a.off[vi] : 0;
+   for (long long t0 = 0; t0 < a.Ntris; t0 += 32) {
+      const long long ti = t0 + lane;
+      const bool hit = ti < a.Ntris && pfv_tri_box(lo, hi, a.v + 9 * ti, a.nor + 3 * ti, a.cent + 3 * ti, a.bmin + 3 * ti, a.bmax + 3 * ti);
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (WRITE && hit) a.tri[run + __popc(m & ((1u << lane) - 1u))] = (int)ti;
+      run += __popc(m);
+   }
+   if (!WRITE && lane == 0) a.count[vi] = run;
+}
+
 }  // namespace pf

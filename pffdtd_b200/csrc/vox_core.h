@@ -9,6 +9,9 @@
 //     outward edge functions up to d_eps = 1e-3 h), the hit distance is t - hf, "behind the point" beyond R_EPS*hf is no hit,
 //     |t - hf| <= R_EPS*hf marks the point as lying ON the surface ("near boundary": all its links are cut);
 //   * sums of three products are ((p0 + p1) + p2), as numpy's sum over the last axis of a 3-vector.
+// and, for the stage before it (VoxGridBase.fill, python/voxelizer/vox_grid_base.py:67-176: which triangles meet which voxel),
+// the Schwarz-Seidel triangle / box overlap test of common/tri_box_intersection.py:84-120 for ONE box and ONE triangle
+// (pfv_tri_box).
 #pragma once
 #include <math.h>
 
@@ -75,4 +78,39 @@ PFV_HD double pfv_hit_dist(const VoxConst &c, const double t, bool *near) {
    if (hd < -c.c_near) hd = (double)INFINITY;  // hits behind the point
    *near = fabs(hd) <= c.c_near;
    return *near ? fabs(hd) : hd;
+}
+
+// common/tri_box_intersection.py:84-120 (tri_box_intersection_vec) for one box [bbmin, bbmax] and one triangle given by its rows
+// of tris_precompute (v: 3 corners, nor: the area-scaled normal, cent, and its bounding box).  The bounding-box rejection is also
+// the candidate mask of vox_grid_base.py:110.
+PFV_HD bool pfv_tri_box(const double *bbmin, const double *bbmax, const double *v /* [3][3] */, const double *nor, const double *cent,
+                        const double *tbmin, const double *tbmax) {
+   for (int j = 0; j < 3; j++)
+      if (tbmin[j] > bbmax[j] || bbmin[j] > tbmax[j]) return false;
+   double dp[3], c1[3], c2[3];
+   for (int j = 0; j < 3; j++) {
+      dp[j] = PFV_SUB(bbmax[j], bbmin[j]);
+      const double c = nor[j] > 0.0 ? dp[j] : 0.0;
+      c1[j] = PFV_SUB(c, cent[j]);
+      c2[j] = PFV_SUB(PFV_SUB(dp[j], c), cent[j]);
+   }
+   // the triangle's plane passes through the box
+   const double d1 = pfv_dot3(nor[0], nor[1], nor[2], c1[0], c1[1], c1[2]), d2 = pfv_dot3(nor[0], nor[1], nor[2], c2[0], c2[1], c2[2]);
+   const double np = pfv_dot3(nor[0], nor[1], nor[2], bbmin[0], bbmin[1], bbmin[2]);
+   if (PFV_MUL(PFV_ADD(np, d1), PFV_ADD(np, d2)) > 0.0) return false;
+   // the three axis-aligned projections overlap
+   for (int q = 0; q < 3; q++) {
+      const int xq = q, yq = (q + 1) % 3, zq = (q + 2) % 3;
+      for (int i = 0; i < 3; i++) {
+         const double *va = v + 3 * i, *vb = v + 3 * ((i + 1) % 3);
+         const double ex = PFV_SUB(vb[xq], va[xq]), ey = PFV_SUB(vb[yq], va[yq]);
+         const double mx = PFV_MUL(0.5, PFV_ADD(vb[xq], va[xq])), my = PFV_MUL(0.5, PFV_ADD(vb[yq], va[yq]));
+         double n0 = -ey, n1 = ex;
+         if (nor[zq] < 0.0) n0 = -n0, n1 = -n1;
+         const double dpx = PFV_MUL(dp[xq], n0), dpy = PFV_MUL(dp[yq], n1);
+         const double de = PFV_ADD(PFV_ADD(-PFV_ADD(PFV_MUL(n0, mx), PFV_MUL(n1, my)), dpx > 0.0 ? dpx : 0.0), dpy > 0.0 ? dpy : 0.0);
+         if (PFV_ADD(PFV_ADD(PFV_MUL(n0, bbmin[xq]), PFV_MUL(n1, bbmin[yq])), de) < 0.0) return false;
+      }
+   }
+   return true;
 }

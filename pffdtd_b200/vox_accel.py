@@ -10,6 +10,11 @@ attributes (`bn_ixyz, adj_bn, mat_bn, saf_bn`), so `vs.check_adj_full()` / `vs.s
     vox_scene = VoxScene(room_geo, cart_grid, vox_grid, fcc=fcc_flag)
     pffdtd_b200.vox_accel.calc_adj(vox_scene)          # instead of vox_scene.calc_adj(Nprocs=...)      (sim_setup.py:111)
 
+The stage before it, `VoxGridBase.fill` (python/voxelizer/vox_grid_base.py:67-176: which triangles meet which voxel, a triangle /
+box overlap test per pair, minutes at production size), has the same treatment: `fill(vox_grid)` instead of
+`vox_grid.fill(Nprocs=...)` (sim_setup.py:105) leaves the same `tri_idxs / tris_pre / tris_mat` on every voxel and the same
+`nonempty_idx`, from `pffdtd_voxfill_run` (one warp per voxel).
+
 No CPU fallback: without the library or a CUDA device it raises.
 """
 from __future__ import annotations
@@ -32,6 +37,72 @@ class pffdtd_vox_desc(C.Structure):
                 ("Nvox", C.c_int64), ("vox_start", C.c_void_p), ("vox_shape", C.c_void_p), ("vox_tri_off", C.c_void_p), ("vox_tri", C.c_void_p),
                 ("Ntris", C.c_int64), ("unor", C.c_void_p), ("cent", C.c_void_p), ("bmin", C.c_void_p), ("bmax", C.c_void_p),
                 ("v", C.c_void_p), ("eab", C.c_void_p), ("ebc", C.c_void_p), ("eca", C.c_void_p)]
+
+
+class pffdtd_voxfill_desc(C.Structure):
+    """include/pffdtd_b200.h: pffdtd_voxfill_desc"""
+    _fields_ = [("struct_size", C.c_int32), ("reserved", C.c_int32), ("Nvox", C.c_int64), ("vbmin", C.c_void_p), ("vbmax", C.c_void_p),
+                ("Ntris", C.c_int64), ("v", C.c_void_p), ("nor", C.c_void_p), ("cent", C.c_void_p), ("bmin", C.c_void_p), ("bmax", C.c_void_p)]
+
+
+def fill_inputs_from_grid(vg) -> dict:
+    """everything VoxGridBase.fill reads from a reference VoxGrid (also the layout of tests/golden/voxfill_*.npz)"""
+    tp = vg.tris_pre
+    return dict(vbmin=np.array([v.bmin for v in vg.voxels], np.float64).reshape(-1, 3),
+                vbmax=np.array([v.bmax for v in vg.voxels], np.float64).reshape(-1, 3),
+                v=np.ascontiguousarray(tp["v"]), nor=np.ascontiguousarray(tp["nor"]), cent=np.ascontiguousarray(tp["cent"]),
+                bmin=np.ascontiguousarray(tp["bmin"]), bmax=np.ascontiguousarray(tp["bmax"]))
+
+
+def fill_lists(inp: dict, device=0, host_lib=None):
+    """-> (off [Nvox+1] int64, tri int32): the triangles meeting every voxel, ascending per voxel.  `host_lib`: the host checker
+    (oracle/libvoxhost.so; tests only) instead of the GPU"""
+    keep = [np.ascontiguousarray(inp[k], np.float64) for k in ("vbmin", "vbmax", "v", "nor", "cent", "bmin", "bmax")]
+    d = pffdtd_voxfill_desc()
+    d.struct_size = C.sizeof(pffdtd_voxfill_desc)
+    d.Nvox, d.Ntris = int(keep[0].shape[0]), int(keep[3].shape[0])
+    for k, a in zip(("vbmin", "vbmax", "v", "nor", "cent", "bmin", "bmax"), keep):
+        setattr(d, k, a.ctypes.data if a.size else None)
+    h = C.c_void_p()
+    if host_lib is not None:
+        host_lib.voxhost_fill.restype = C.c_void_p
+        h = C.c_void_p(host_lib.voxhost_fill(C.byref(d)))
+        if not h:
+            raise RuntimeError("voxhost_fill failed")
+        count, read, free = host_lib.voxhost_fill_count, host_lib.voxhost_fill_read, host_lib.voxhost_fill_free
+    else:
+        from .engine import _check, lib
+        L = lib()
+        L.pffdtd_voxfill_run.argtypes = [C.POINTER(pffdtd_voxfill_desc), C.c_int, C.POINTER(C.c_void_p)]
+        _check(L.pffdtd_voxfill_run(C.byref(d), int(device), C.byref(h)))
+        count, read, free = L.pffdtd_voxfill_count, L.pffdtd_voxfill_read, L.pffdtd_voxfill_free
+    count.restype = C.c_int64
+    count.argtypes = free.argtypes = [C.c_void_p]
+    read.argtypes = [C.c_void_p] * 3
+    off, tri = np.zeros(d.Nvox + 1, np.int64), np.zeros(max(int(count(h)), 0), np.int32)
+    rc = read(h, off.ctypes.data, tri.ctypes.data if tri.size else None)
+    free(h)
+    if rc:
+        raise RuntimeError("reading the voxel lists failed")
+    return off, tri
+
+
+def fill(vg, device: int = 0):
+    """drop-in for VoxGridBase.fill (vox_grid_base.py:67-176): sets tri_idxs / tris_pre / tris_mat of every non-empty voxel and
+    vg.nonempty_idx"""
+    if vg.Nvox == 1:  # vox_grid_base.py:85-90
+        vox = vg.voxels[0]
+        vox.tri_idxs, vox.tris_pre, vox.tris_mat = np.arange(vg.Ntris), vg.tris_pre, vg.mats
+        vg.nonempty_idx = [0]
+        return vg
+    off, tri = fill_lists(fill_inputs_from_grid(vg), device)
+    vg.nonempty_idx = []
+    for i in np.flatnonzero(np.diff(off) > 0):
+        vox = vg.voxels[int(i)]
+        vox.tri_idxs = tri[off[i]:off[i + 1]].astype(np.int64)
+        vox.tris_pre, vox.tris_mat = vg.tris_pre[vox.tri_idxs], vg.mats[vox.tri_idxs]
+        vg.nonempty_idx.append(int(i))
+    return vg
 
 
 def inputs_from_scene(vs) -> dict:

@@ -29,6 +29,34 @@ def _host(inp):
     return va._run(L, "voxhost", d, int(inp["NN"]), device=None)
 
 
+def _load_fill(name):
+    """inputs of VoxGridBase.fill (all voxels' boxes + triangle tables) and the lists the reference made"""
+    z, f = np.load(ROOT / "tests" / "golden" / f"vox_{name}.npz"), np.load(ROOT / "tests" / "golden" / f"voxfill_{name}.npz")
+    inp = dict(vbmin=f["vbmin"], vbmax=f["vbmax"], nor=f["nor"], v=z["in_v"], cent=z["in_cent"], bmin=z["in_bmin"], bmax=z["in_bmax"])
+    return inp, f["nonempty_idx"], z["in_vox_tri_off"], z["in_vox_tri"]
+
+
+def _check_fill(inp, nonempty, ref_off, ref_tri, off, tri):
+    assert off.size == inp["vbmin"].shape[0] + 1 and off[0] == 0 and off[-1] == tri.size
+    assert np.array_equal(np.flatnonzero(np.diff(off) > 0), nonempty)  # vox_grid.nonempty_idx
+    assert np.array_equal(np.diff(off)[nonempty], np.diff(ref_off)) and np.array_equal(tri, ref_tri)  # every voxel's list, in order
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_host_fill_equals_the_reference_voxel_grid(name):
+    inp, nonempty, ref_off, ref_tri = _load_fill(name)
+    assert 0 < nonempty.size < inp["vbmin"].shape[0] and ref_tri.size > 5000
+    import oracle
+    oracle.build()
+    off, tri = va.fill_lists(inp, host_lib=C.CDLL(str(ROOT / "oracle" / "libvoxhost.so")))
+    _check_fill(inp, nonempty, ref_off, ref_tri, off, tri)
+    # the overlap test is more than the bounding boxes: they alone admit more pairs (vox_grid_base.py:110 'candidates')
+    k = int(nonempty[nonempty.size // 2])
+    cand = np.all((inp["vbmax"][k] >= inp["bmin"]) & (inp["vbmin"][k] <= inp["bmax"]), axis=-1)
+    cands = sum(int(np.all((inp["vbmax"][j] >= inp["bmin"]) & (inp["vbmin"][j] <= inp["bmax"]), axis=-1).sum()) for j in nonempty[:200])
+    assert cand.sum() >= off[k + 1] - off[k] and cands > int(np.diff(off)[nonempty[:200]].sum())
+
+
 def _check(inp, out, bn, adj, tidx):
     assert np.array_equal(bn, out["bn_ixyz"]) and adj.dtype == bool and np.array_equal(adj, out["adj_bn"])
     mat, saf = va.finish(inp, bn, adj, tidx)
@@ -63,6 +91,18 @@ def test_the_voxel_wide_rules_matter():
     assert bn.size < out["bn_ixyz"].size
 
 
+def test_fill_desc_layout_matches_the_header():
+    import subprocess
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "pffdtd_b200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(pffdtd_voxfill_desc), ' \
+          'offsetof(pffdtd_voxfill_desc, Ntris), offsetof(pffdtd_voxfill_desc, bmax));return 0;}\n'
+    tmp = Path(subprocess.run(["mktemp", "-d"], capture_output=True, text=True).stdout.strip())
+    (tmp / "t.c").write_text(src)
+    subprocess.run(["/usr/bin/gcc", "-I", str(ROOT / "include"), str(tmp / "t.c"), "-o", str(tmp / "t")], check=True)
+    size, o_nt, o_bmax = map(int, subprocess.run([str(tmp / "t")], capture_output=True, text=True).stdout.split())
+    d = va.pffdtd_voxfill_desc
+    assert C.sizeof(d) == size and d.Ntris.offset == o_nt and d.bmax.offset == o_bmax
+
+
 def test_desc_layout_matches_the_header():
     import subprocess
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "pffdtd_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(pffdtd_vox_desc), ' \
@@ -94,3 +134,67 @@ def test_cuda_voxeliser_rejects_bad_descriptions():
     bad["vox_start"][0, 0] = int(inp["Nxyz"][0])  # a voxel outside the grid
     with pytest.raises(PffdtdError):
         va.ray_stage(bad, device=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_fill_equals_the_reference_voxel_grid(name):
+    inp, nonempty, ref_off, ref_tri = _load_fill(name)
+    off, tri = va.fill_lists(inp, device=0)
+    _check_fill(inp, nonempty, ref_off, ref_tri, off, tri)
+
+
+@pytest.mark.gpu
+def test_cuda_fill_drop_in_sets_what_the_reference_fill_sets():
+    """`fill(vox_grid)` on an object with the reference VoxGrid's attributes (vox_grid_base.py:43-66, vox_grid.py:31-39)"""
+    inp, nonempty, ref_off, ref_tri = _load_fill("ctk_h045_fcc")
+    z = np.load(ROOT / "tests" / "golden" / "vox_ctk_h045_fcc.npz")
+
+    class Vox:
+        def __init__(self, lo, hi):
+            self.bmin, self.bmax, self.tri_idxs, self.tris_pre, self.tris_mat = lo, hi, [], None, None
+
+    class Grid:
+        pass
+    vg = Grid()
+    nt = inp["nor"].shape[0]
+    vg.tris_pre = np.zeros(nt, dtype=[(k, np.float64, (3, 3) if k == "v" else (3,)) for k in ("v", "nor", "cent", "bmin", "bmax")])
+    for k in ("v", "nor", "cent", "bmin", "bmax"):
+        vg.tris_pre[k] = inp[k]
+    vg.mats, vg.Ntris, vg.Nvox = z["in_mat_ind"], nt, inp["vbmin"].shape[0]
+    vg.voxels = [Vox(lo, hi) for lo, hi in zip(inp["vbmin"], inp["vbmax"])]
+    va.fill(vg, device=0)
+    assert vg.nonempty_idx == [int(i) for i in nonempty]
+    for j, i in enumerate(nonempty):
+        want = ref_tri[ref_off[j]:ref_off[j + 1]]
+        vox = vg.voxels[int(i)]
+        assert np.array_equal(vox.tri_idxs, want) and np.array_equal(vox.tris_mat, vg.mats[want]) and np.array_equal(vox.tris_pre["cent"], inp["cent"][want])
+    assert all(len(vg.voxels[i].tri_idxs) == 0 for i in set(range(vg.Nvox)) - set(vg.nonempty_idx))
+
+
+LARGE = ROOT / "data_large" / "vox_mv_h003.npz"
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not LARGE.exists(), reason="data_large/vox_mv_h003.npz not built (tools/make_large_vox.py, build container only)")
+def test_cuda_voxeliser_at_production_size(capsys):
+    """Musikverein, FCC grid, h = 0.03 m (1700 x 660 x 508 points, 109 098 voxels of which 21 331 meet the surface, 6.6 M boundary
+    nodes): both stages against what the unmodified reference produced (tools/make_large_vox.py), with their times"""
+    import time
+    z, f = np.load(LARGE), np.load(ROOT / "data_large" / "voxfill_mv_h003.npz")
+    inp = {k[3:]: z[k] for k in z.files if k.startswith("in_")}
+    out = {k[4:]: z[k] for k in z.files if k.startswith("out_")}
+    va.fill_lists(dict(vbmin=f["vbmin"][:64], vbmax=f["vbmax"][:64], nor=f["nor"], v=inp["v"], cent=inp["cent"], bmin=inp["bmin"], bmax=inp["bmax"]), device=0)
+    t0 = time.perf_counter()
+    off, tri = va.fill_lists(dict(vbmin=f["vbmin"], vbmax=f["vbmax"], nor=f["nor"], v=inp["v"], cent=inp["cent"], bmin=inp["bmin"], bmax=inp["bmax"]), device=0)
+    t1 = time.perf_counter()
+    ne = f["nonempty_idx"]
+    assert np.array_equal(np.flatnonzero(np.diff(off) > 0), ne) and np.array_equal(tri, inp["vox_tri"])
+    assert np.array_equal(np.diff(off)[ne], np.diff(inp["vox_tri_off"]))
+    t2 = time.perf_counter()
+    bn, adj, tidx, ndist = va.ray_stage(inp, device=0)
+    t3 = time.perf_counter()
+    _check(inp, out, bn, adj, tidx)
+    with capsys.disabled():
+        print(f"\n[vox production size] fill {t1 - t0:.3f} s (reference: 330 s single process); calc_adj ray stage {t3 - t2:.3f} s for "
+              f"{bn.size} boundary nodes (reference: {float(z['ref_seconds']):.0f} s on {int(z['ref_procs'])} processes)")

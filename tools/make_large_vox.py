@@ -41,5 +41,33 @@ def main():
           f"(7 processes) {t2 - t1:.0f} s -> {dst} ({dst.stat().st_size / 1e6:.1f} MB)", flush=True)
 
 
+def fill_case(h):
+    """the inputs of VoxGridBase.fill for the same grid (all voxels' boxes, the triangles' normals, which voxels the reference found
+    non-empty) -> data_large/voxfill_mv_h<h>.npz; the expected lists are vox_mv_h<h>.npz's in_vox_tri_off / in_vox_tri"""
+    from common.room_geo import RoomGeo
+    from voxelizer.cart_grid import CartGrid
+    from voxelizer.vox_grid import VoxGrid
+    from pffdtd_b200.vox_accel import fill_inputs_from_grid
+    tag = f"h{int(round(h * 100)):03d}"
+    z = np.load(ROOT / "data_large" / f"vox_mv_{tag}.npz")
+    os.chdir("/root/reference/python")
+    rg = RoomGeo("../data/models/Musikverein_ConcertHall/model_export.json", az_el=[0., 0.])
+    cg = CartGrid(h=h, offset=3.5, bmin=rg.bmin, bmax=rg.bmax, fcc=True)
+    vg = VoxGrid(rg, cg)  # (not filled: that is what the reference spent minutes on when vox_mv_<tag>.npz was made)
+    inp = fill_inputs_from_grid(vg)
+    for k in ("v", "cent", "bmin", "bmax"):
+        assert np.array_equal(inp[k], z[f"in_{k}"]), k
+    starts = {tuple(int(x) for x in v.ixyz_start): i for i, v in enumerate(vg.voxels)}
+    nonempty = np.array([starts[tuple(int(x) for x in s)] for s in z["in_vox_start"]], np.int64)
+    assert np.all(np.diff(nonempty) > 0)
+    dst = ROOT / "data_large" / f"voxfill_mv_{tag}.npz"
+    np.savez_compressed(dst, vbmin=inp["vbmin"], vbmax=inp["vbmax"], nor=inp["nor"], nonempty_idx=nonempty)
+    print(f"fill case: Nvox {vg.Nvox} nonempty {nonempty.size} Ntris {vg.Ntris} -> {dst} ({dst.stat().st_size / 1e6:.1f} MB)", flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 2 and sys.argv[2] == "fill":
+        fill_case(float(sys.argv[1]))
+    else:
+        main()
+        fill_case(float(sys.argv[1]) if len(sys.argv) > 1 else 0.03)
