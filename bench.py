@@ -62,6 +62,9 @@ WORKLOADS = {
                     desc="BASELINE configs[2] with the real model: Musikverein, h = 0.06 m, 13-pt FCC folded, fp32, 5 materials x 11 branches"),
     "mv_big": dict(folder="data_large/mv_fcc_gpu_big", precision=1, fcc=True,
                    desc="BASELINE configs[2] with the real model at a finer grid: Musikverein, 13-pt FCC folded, fp32, 5 materials x 11 branches"),
+    "mv_full": dict(folder="data_large/mv_fcc_gpu_full", precision=1, fcc=True,
+                    desc="BASELINE configs[2] at the size of the reference's own script (python/test_script_MV_fcc_gpu.py: fmax 2500 Hz, PPW 7.7, "
+                         "h = 0.0178 m): Musikverein, 13-pt FCC folded, fp32, 5 materials x 11 branches"),
 }
 BYTES_PER_NODE = {1: 12.125, 2: 24.125}  # u1 read + u0 read + u0 write + 1 mask bit
 # CPU-arm sample grids for workloads whose full grid would take the CPU engine minutes per step
@@ -71,7 +74,7 @@ CPU_SAMPLE_GRID = {
     "c4": ((130, 1024, 1024), "one eighth of the c4 grid (130x1024x1024)"),
 }
 # extra single-GPU lines of the N=1 run: workload -> timed steps
-ALSO = (("c2", 200), ("c3s", 100), ("c4", 20), ("ctk_real", 200), ("mv_real", 150), ("mv_big", 40))
+ALSO = (("c2", 200), ("c3s", 100), ("c4", 20), ("ctk_real", 200), ("mv_real", 150), ("mv_big", 40), ("mv_full", 20))
 PARITY_STEPS = 24
 PARITY_FILE = ROOT / "tests" / "golden" / "c5_parity.json"
 
@@ -450,6 +453,13 @@ def measure(ctx, wl, K, W, with_e2e=True, with_parity=False):
                 "note": "air launches timed with CUDA events in a second pass of K steps launched kernel by kernel (%.4f ms/step); "
                         "the `value` pass replays the step as a CUDA graph; whole_step_frac = the whole step's Gvox/s x bytes_per_node "
                         "against the same peak" % (ms_prof / K)}
+    # the step's REQUIRED traffic also holds the lossy boundary nodes' branch state (k_fd: 16 B per branch + 30 B per node in fp32,
+    # DESIGN.md 4), which bytes_per_node leaves out; with it the whole step reads as a fraction of the same peak
+    rs4 = 1 if w["precision"] == 1 else 2
+    fd_bytes = float(np.sum(16 * sd.Mb.astype(np.int64)[sd.mat_bnl.astype(np.int64)] + 30)) * rs4 if sd.Nbl else 0.0
+    fd_bytes_all = sum(ctx.gather(fd_bytes) or [fd_bytes]) if ctx.world > 1 else fd_bytes
+    roofline["boundary_state_bytes_per_step"] = fd_bytes_all
+    roofline["whole_step_frac_with_boundary_state"] = (BYTES_PER_NODE[w["precision"]] * Npts + fd_bytes_all) / ctx.world / (ms / K * 1e-3) / 1e9 / peak
     if ctx.world > 1:
         # non-air time of every rank (the end ranks carry the x walls): what the cost-weighted split balances
         per_rank = ctx.gather({"rank": ctx.rank, "planes": int(sd.Nx), "air_ms": air_ms_per_step, "step_ms_kernel_by_kernel": ms_prof / K,

@@ -141,6 +141,10 @@ struct pffdtd_engine {
    // fused Cartesian step (tiled air kernel applies the ABC shell and mirrors the halos on write)
    int fuse_ok = 0;     // the ABC list is the canonical full shell, so the air kernel may apply it
    int halo_dirty = 0;  // u1's halos were not produced by mirror-on-write: run the mirror kernels first
+   // unfused step: k_abc writes the z halos of the new state (kernels.cuh k_abc `zf`), the next mirror pass skips k_flip_z
+   uint8_t *zf = nullptr;
+   int zflip_want = 1, zflip_ok = 0;  // option; the lists allow it (canonical shell, no boundary / source node at z = 2 | Nz-3)
+   int zhalo_ok = 0;                  // the current state's z halos were written by the previous step's k_abc
    i64 *pair_src = nullptr, *pair_dst = nullptr;  // late halo mirrors (boundary / source nodes at index 2 | N-3)
    i64 np = 0, np_lo = 0, np_hi = 0;
    // prefix/suffix sizes of the sorted node lists that lie in the first/last owned plane (edge work
@@ -342,6 +346,7 @@ extern "C" int pffdtd_destroy(pffdtd_engine *e) {
 // bound by its own consumers' issue / LSU slots, not by HBM, so every instruction moved into it costs what it saves elsewhere:
 // measured on B200 (c3s), unfused 0.449 ms per step with or without the service warp, fused 0.560 ms (the fused epilogue spills at the
 // 72 registers that keep 11 consumer warps).  Both stay available (options "fuse" / "svc" = 1) and are covered by the parity tests.
+static bool zflip_on(const pffdtd_engine *e) { return e->zflip_want && e->zflip_ok && e->zf && !e->energy_on && !e->manual_halo; }
 static bool want_fuse(const pffdtd_engine *e) { return e->fuse < 0 ? e->fcc == 0 : e->fuse != 0; }
 static bool want_svc(const pffdtd_engine *e) { return e->svc_want < 0 ? e->fcc == 0 : e->svc_want != 0; }
 static bool step_fused(const pffdtd_engine *e) {
@@ -628,6 +633,26 @@ static int create_impl(const pffdtd_desc *d, int device, pffdtd_engine *e) {
       for (i64 i = 0; clear && i < e->Nb; i++) clear = !on_shell(d->bn_ixyz[i]);
       for (i64 i = 0; clear && i < e->Ns; i++) clear = !on_shell(d->in_ixyz[i]);
       e->abc_disjoint = clear;
+      // z halos written by k_abc (unfused step): needs the canonical shell (every row's z ends are in the list; not the checkerboard
+      // layout, whose odd-parity nodes are not) and nothing else writing the mirrored nodes z = 2 / Nz-3 afterwards
+      bool zok = ok && !checker && Nz >= 7;
+      auto z_src = [&](i64 v) {
+         const i64 iz = v % Nz;
+         return iz == 2 || iz == Nz - 3;
+      };
+      for (i64 i = 0; zok && i < e->Nb; i++) zok = !z_src(d->bn_ixyz[i]);
+      for (i64 i = 0; zok && i < e->Ns; i++) zok = !z_src(d->in_ixyz[i]);
+      e->zflip_ok = zok;
+      if (zok && e->Nba) {
+         std::vector<uint8_t> zf((size_t)e->Nba, 0);
+         for (i64 i = 0; i < e->Nba; i++) {
+            const i64 v = d->bna_ixyz[i], row = v / Nz, iz = v - row * Nz, ix = row / Ny, iy = row - ix * Ny;
+            const bool shell_row = qx(ix) || qy(iy);
+            zf[(size_t)i] = shell_row ? (uint8_t)((iz == 2 ? 4 : 0) | (iz == Nz - 3 ? 8 : 0)) : (uint8_t)((iz == 1 ? 1 : 0) | (iz == Nz - 2 ? 2 : 0));
+         }
+         if (dalloc(e, &e->zf, zf.size())) return PFFDTD_ECUDA;
+         CU(cudaMemcpy(e->zf, zf.data(), zf.size(), cudaMemcpyHostToDevice));
+      }
    }
    // does any boundary node also sit in the absorbing-shell list?  (a bitmap of the shell list; any layout, any order)
    {
@@ -818,13 +843,18 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       if (value < 0 || value > 1) return fail(PFFDTD_EINVAL, "air_kernel must be 0 or 1");
       e->air_kernel = (int)value;
       e->halo_dirty = 1;
+      e->zhalo_ok = 0;
       int rc = build_service(e);  // (whether the lists carry the shell's z faces follows the kind of step)
       if (rc) return rc;
    } else if (k == "fuse") {
       e->fuse = value < 0 ? -1 : (value != 0);
       e->halo_dirty = 1;
+      e->zhalo_ok = 0;
       int rc = build_service(e);
       if (rc) return rc;
+   } else if (k == "zflip") {
+      e->zflip_want = value != 0;
+      e->zhalo_ok = 0;
    } else if (k == "overlap") {
       e->overlap = value != 0;
    } else if (k == "profile_air") {
@@ -847,6 +877,7 @@ extern "C" int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t valu
       int rc = build_service(e);
       if (rc) return rc;
       e->halo_dirty = 1;
+      e->zhalo_ok = 0;
    } else if (k == "p2p") {
       if (value && !(e->ipc_flags_lo || e->ipc_flags_hi)) return fail(PFFDTD_ESTATE, "p2p needs pffdtd_peer_connect first");
       e->p2p = value != 0;
@@ -905,6 +936,7 @@ extern "C" int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out) {
       pf::air_cfg_shape(e->tma.cfg, &rpt, &nw, &lz);
       *out = e->tma.ok ? lz : 0;
    } else if (k == "Nzp") *out = (double)e->Nzp;
+   else if (k == "zflip") *out = zflip_on(e) && !(step_fused(e) && (e->fcc == 0 || (e->svc_on && e->svc_shell))) ? 1 : 0;
    else if (k == "fused") *out = (step_fused(e) && (e->fcc == 0 || (e->svc_on && e->svc_shell))) ? 1 : 0;
    else if (k == "energy") *out = e->energy_on;
    else if (k == "mirror_pairs") *out = (double)e->np;
@@ -1020,7 +1052,8 @@ struct Step {
       int rc = air(p.xb, p.xe);
       if (rc) return rc;
       if (!fused && p.nba > 0) {
-         pf::k_abc<Real><<<nblk(p.nba, 128), 128, 0, s>>>(u0, e->bna, e->Q, (const Real *)e->u2ba, p.a0, p.nba, (Real)e->l);
+         pf::k_abc<Real><<<nblk(p.nba, 128), 128, 0, s>>>(u0, e->bna, e->Q, (const Real *)e->u2ba, p.a0, p.nba, (Real)e->l,
+                                                          zflip_on(e) ? e->zf : nullptr);
          e->launches += 1;
       }
       if (p.nb > 0) {
@@ -1149,6 +1182,7 @@ extern "C" int pffdtd_energy_enable(pffdtd_engine *e, const pffdtd_energy_desc *
    e->en_Ts = d->Ts;
    drop_graphs(e);
    e->halo_dirty = 1;
+   e->zhalo_ok = 0;
    e->energy_on = 1;
    return build_service(e);  // (energy steps use the list kernels only)
 }
@@ -1166,15 +1200,18 @@ extern "C" int pffdtd_read_energy(pffdtd_engine *e, double *H_tot, double *E_los
 
 // the reference's mirror pass on one grid (cpu_engine.h:135-172): seam row, then z, y, x faces in that order
 template <typename Real>
-static void mirror_pass(pffdtd_engine *e, Real *u, cudaStream_t s) {
+static void mirror_pass(pffdtd_engine *e, Real *u, cudaStream_t s, bool skip_z = false) {
    const i64 Nx = e->Nx, Ny = e->Ny, Nz = e->Nz, Nzp = e->Nzp;
    if (e->fcc == 2) {
       pf::k_fold_seam<Real><<<dim3(nblk(Nz, 128), (unsigned)std::min<i64>(Nx, 65535)), 128, 0, s>>>(u, Nx, Ny, Nz, Nzp);
       e->launches += 1;
    }
-   pf::k_flip_z<Real><<<nblk(Nx * Ny, 128), 128, 0, s>>>(u, Nx * Ny, Nz, Nzp);
+   if (!skip_z) {
+      pf::k_flip_z<Real><<<nblk(Nx * Ny, 128), 128, 0, s>>>(u, Nx * Ny, Nz, Nzp);
+      e->launches += 1;
+   }
    pf::k_flip_y<Real><<<dim3(nblk(Nz, 128), (unsigned)std::min<i64>(Nx, 65535)), 128, 0, s>>>(u, Nx, Ny, Nz, Nzp, e->fcc != 2);
-   e->launches += 2;
+   e->launches += 1;
    if (e->x_lo_edge || e->x_hi_edge) {
       pf::k_flip_x<Real><<<dim3(nblk(Nz, 128), (unsigned)std::min<i64>(Ny, 65535)), 128, 0, s>>>(u, Nx, Ny, Nz, Nzp, e->x_lo_edge, e->x_hi_edge);
       e->launches += 1;
@@ -1277,7 +1314,9 @@ static int step_impl(pffdtd_engine *e, i64 n, int phases) {
             pf::k_gather<Real><<<nblk(e->Nba, 128), 128, 0, s>>>(u0, e->bna, (Real *)e->u2ba, e->Nba);
             e->launches += 1;
          }
-         mirror_pass<Real>(e, u1, s);
+         // (the z halos are in place when the previous step's k_abc wrote them: the seam copy and the z mirror commute, and the y / x
+         // mirrors, which copy whole rows, still come after both)
+         mirror_pass<Real>(e, u1, s, zflip_on(e) && e->zhalo_ok);
          e->halo_dirty = 1;  // the state this step produces has no mirrored halos yet
       } else if (e->halo_dirty) {
          mirror_pass<Real>(e, u1, s);
@@ -1343,6 +1382,7 @@ static int step_impl(pffdtd_engine *e, i64 n, int phases) {
          e->launches += 1;
       }
       e->ticked = 0;
+      e->zhalo_ok = (!fused && zflip_on(e)) ? 1 : 0;
       e->n_dev = n + 1;
       e->cur ^= 1;
       e->steps_done = n + 1;
@@ -1357,21 +1397,21 @@ static int step_any(pffdtd_engine *e, i64 n, int phases = PH_ALL) {
 // can a step starting now be replayed from a captured graph?
 static bool graphable(const pffdtd_engine *e) {
    return e->use_graph && !e->energy_on && !e->profile_air && !e->manual_halo && !e->peer_lo && !e->peer_hi && e->steps_plain >= 2 &&
-          !(e->halo_dirty && step_fused(e));
+          !(e->halo_dirty && step_fused(e)) && !(zflip_on(e) && !step_fused(e) && !e->zhalo_ok);
 }
 
 // Host-side bookkeeping a step changes; capturing a step must leave it as it was (nothing ran).
 struct HostState {
-   int cur, halo_dirty, comm_pending, abc_pending, host_mode;
+   int cur, halo_dirty, comm_pending, abc_pending, host_mode, zhalo_ok;
    i64 n_dev, steps_done;
    double launches;
 };
 static HostState save_state(const pffdtd_engine *e) {
-   return HostState{e->cur, e->halo_dirty, e->comm_pending, e->abc_pending, e->host_mode, e->n_dev, e->steps_done, e->launches};
+   return HostState{e->cur, e->halo_dirty, e->comm_pending, e->abc_pending, e->host_mode, e->zhalo_ok, e->n_dev, e->steps_done, e->launches};
 }
 static void restore_state(pffdtd_engine *e, const HostState &h) {
    e->cur = h.cur, e->halo_dirty = h.halo_dirty, e->comm_pending = h.comm_pending, e->abc_pending = h.abc_pending;
-   e->host_mode = h.host_mode, e->n_dev = h.n_dev, e->steps_done = h.steps_done, e->launches = h.launches;
+   e->host_mode = h.host_mode, e->zhalo_ok = h.zhalo_ok, e->n_dev = h.n_dev, e->steps_done = h.steps_done, e->launches = h.launches;
 }
 
 // a halo exchange still in flight on the comm stream is joined for real (never from inside a capture)
@@ -1611,6 +1651,7 @@ extern "C" int pffdtd_write_grid(pffdtd_engine *e, int which, const double *in) 
    int rc = pffdtd_sync(e);
    if (rc) return rc;
    e->halo_dirty = 1;
+   e->zhalo_ok = 0;
    return e->precision == 1 ? grid_io<float>(e, which, (double *)in, false) : grid_io<double>(e, which, (double *)in, false);
 }
 
@@ -1955,7 +1996,7 @@ extern "C" int pffdtd_vox_run(const pffdtd_vox_desc *d, int device, pffdtd_vox *
       void *p = nullptr;
       if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return 1;
       dev.push_back(p);
-      if (bytes && cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+      if (bytes && src && cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
       *dst = p;
       return 0;
    };
@@ -1983,63 +2024,56 @@ extern "C" int pffdtd_vox_run(const pffdtd_vox_desc *d, int device, pffdtd_vox *
    const size_t t3 = (size_t)d->Ntris * 24;
    bad |= up(d->unor, t3, (const void **)&a.unor) | up(d->cent, t3, (const void **)&a.cent) | up(d->bmin, t3, (const void **)&a.bmin) | up(d->bmax, t3, (const void **)&a.bmax);
    bad |= up(d->v, t3 * 3, (const void **)&a.v) | up(d->eab, t3, (const void **)&a.eab) | up(d->ebc, t3, (const void **)&a.ebc) | up(d->eca, t3, (const void **)&a.eca);
-   const void *p_nd = nullptr, *p_ti = nullptr, *p_cu = nullptr, *p_fl = nullptr;
-   bad |= up(nullptr, 0, &p_nd) | up(nullptr, 0, &p_ti) | up(nullptr, 0, &p_cu) | up(nullptr, 0, &p_fl);
+   const void *p_nd = nullptr, *p_ti = nullptr, *p_cu = nullptr, *p_fl = nullptr, *p_cnt = nullptr, *p_off = nullptr;
+   bad |= up(nullptr, (size_t)d->Nvox * 8, &p_cnt) | up(nullptr, ((size_t)d->Nvox + 1) * 8, &p_off);
    if (!bad && npt) {
-      // (the four scratch arrays are sized now that the tables are up)
-      for (int k = 0; k < 4; k++) cudaFree(dev[dev.size() - 4 + (size_t)k]);
-      dev.resize(dev.size() - 4);
-      void *q = nullptr;
+      // per-point scratch of every voxel: nearest hit, its triangle, cut links, flags
       const size_t sizes[4] = {npt * 8, npt * 4, npt * 2, npt};
       const void **dst[4] = {&p_nd, &p_ti, &p_cu, &p_fl};
-      for (int k = 0; k < 4 && !bad; k++) {
-         if (cudaMalloc(&q, sizes[k]) != cudaSuccess) bad = 1;
-         else dev.push_back(q), *dst[k] = q;
-      }
+      for (int k = 0; k < 4 && !bad; k++) bad |= up(nullptr, sizes[k], dst[k]);
    }
    if (bad) {
       freeall();
       return fail(PFFDTD_ECUDA, "voxeliser: device allocation / upload failed: %s", cudaGetErrorString(cudaGetLastError()));
    }
    a.ndist = (double *)p_nd, a.tidx = (int *)p_ti, a.cut = (unsigned short *)p_cu, a.fl = (unsigned char *)p_fl;
+   a.count = (long long *)p_cnt, a.off = (const long long *)p_off;
    pffdtd_vox *R = new pffdtd_vox();
    R->NN = d->NN;
    cudaError_t ce = cudaSuccess;
-   std::vector<double> h_nd(npt);
-   std::vector<int> h_ti(npt);
-   std::vector<unsigned short> h_cu(npt);
-   std::vector<unsigned char> h_fl(npt);
    if (d->Nvox && npt) {
+      // 1. ray casting, one block per voxel; 2. the voxels' boundary-point counts -> offsets; 3. compaction on the device, in the
+      // reference's order (voxel by voxel, ascending inside a voxel: vox_scene.py:246-279, 343-366)
       pf::k_vox_calc_adj<<<(unsigned)d->Nvox, 256>>>(a);
       ce = cudaGetLastError();
-      if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
-      if (ce == cudaSuccess) ce = cudaMemcpy(h_nd.data(), a.ndist, npt * 8, cudaMemcpyDeviceToHost);
-      if (ce == cudaSuccess) ce = cudaMemcpy(h_ti.data(), a.tidx, npt * 4, cudaMemcpyDeviceToHost);
-      if (ce == cudaSuccess) ce = cudaMemcpy(h_cu.data(), a.cut, npt * 2, cudaMemcpyDeviceToHost);
-      if (ce == cudaSuccess) ce = cudaMemcpy(h_fl.data(), a.fl, npt, cudaMemcpyDeviceToHost);
+      std::vector<long long> cnt((size_t)d->Nvox), off((size_t)d->Nvox + 1, 0);
+      if (ce == cudaSuccess) ce = cudaMemcpy(cnt.data(), a.count, cnt.size() * 8, cudaMemcpyDeviceToHost);
+      if (ce == cudaSuccess) {
+         for (i64 v = 0; v < d->Nvox; v++) off[(size_t)v + 1] = off[(size_t)v] + cnt[(size_t)v];
+         ce = cudaMemcpy((void *)a.off, off.data(), off.size() * 8, cudaMemcpyHostToDevice);
+      }
+      const size_t nb = (size_t)off[(size_t)d->Nvox];
+      if (ce == cudaSuccess && nb) {
+         const void *o1 = nullptr, *o2 = nullptr, *o3 = nullptr, *o4 = nullptr;
+         if (up(nullptr, nb * 8, &o1) | up(nullptr, nb * (size_t)d->NN, &o2) | up(nullptr, nb * 4, &o3) | up(nullptr, nb * 8, &o4)) {
+            ce = cudaGetLastError();
+            if (ce == cudaSuccess) ce = cudaErrorMemoryAllocation;
+         } else {
+            a.o_bn = (long long *)o1, a.o_adj = (unsigned char *)o2, a.o_tidx = (int *)o3, a.o_ndist = (double *)o4;
+            pf::k_vox_emit<<<(unsigned)d->Nvox, 256>>>(a);
+            ce = cudaGetLastError();
+            R->bn.resize(nb), R->adj.resize(nb * (size_t)d->NN), R->tidx.resize(nb), R->ndist.resize(nb);
+            if (ce == cudaSuccess) ce = cudaMemcpy(R->bn.data(), a.o_bn, nb * 8, cudaMemcpyDeviceToHost);
+            if (ce == cudaSuccess) ce = cudaMemcpy(R->adj.data(), a.o_adj, nb * (size_t)d->NN, cudaMemcpyDeviceToHost);
+            if (ce == cudaSuccess) ce = cudaMemcpy(R->tidx.data(), a.o_tidx, nb * 4, cudaMemcpyDeviceToHost);
+            if (ce == cudaSuccess) ce = cudaMemcpy(R->ndist.data(), a.o_ndist, nb * 8, cudaMemcpyDeviceToHost);
+         }
+      }
    }
    freeall();
    if (ce != cudaSuccess) {
       delete R;
       return fail(PFFDTD_ECUDA, "voxeliser kernel: %s", cudaGetErrorString(ce));
-   }
-   // boundary points of every voxel's interior, voxel by voxel, ascending inside a voxel (vox_scene.py:246-279, 343-366); a point
-   // lying on the surface has every link cut (:244)
-   for (i64 v = 0; v < d->Nvox; v++) {
-      const int64_t *sh = d->vox_shape + 3 * v, *st = d->vox_start + 3 * v;
-      const size_t base = (size_t)pt_off[(size_t)v];
-      for (i64 ix = 1; ix <= sh[0] - 2; ix++)
-         for (i64 iy = 1; iy <= sh[1] - 2; iy++)
-            for (i64 iz = 1; iz <= sh[2] - 2; iz++) {
-               const size_t p = base + (size_t)((ix * sh[1] + iy) * sh[2] + iz);
-               unsigned cu = h_cu[p];
-               if (h_fl[p] & 2u) cu = (1u << d->NN) - 1u;
-               if (!cu) continue;
-               R->bn.push_back(((st[0] + ix) * d->Ny + (st[1] + iy)) * d->Nz + (st[2] + iz));
-               for (int k = 0; k < d->NN; k++) R->adj.push_back((cu >> k) & 1u ? 0 : 1);
-               R->tidx.push_back(h_ti[p]);
-               R->ndist.push_back(h_nd[p]);
-            }
    }
    *out = R;
    return PFFDTD_OK;

@@ -150,9 +150,15 @@ __global__ void __launch_bounds__(256) k_air_generic(const Real *__restrict__ u1
 //   lQ = l*Q (Real);  u0 = (u0 + lQ*u2ba)/(1.0 + lQ): the literal 1.0 makes the division a DOUBLE
 //   division of a Real numerator in the reference, also when Real is float.
 // ------------------------------------------------------------------------------------------------
+// `zf` (optional): the shell's z faces also write the z halos of the NEW state, which the next step's mirror pass would otherwise
+// fetch one 32-byte sector at a time (k_flip_z: 4 % of a 13-point step) -- here the sector is in hand.  Per node: bit 0 / 1 = the
+// node is z = 1 / Nz-2 of a row off the x / y shell: copy its neighbour z = 2 / Nz-3 (an air node, final since the air kernel) to the
+// halo z = 0 / Nz-1; bit 2 / 3 = the node is z = 2 / Nz-3 of a row ON the x / y shell (every node of such a row is in this list and
+// gets its shell update from its own thread): it writes its own new value to the halo.  The engine only passes `zf` when no
+// boundary / source node sits at z = 2 / Nz-3 (nothing after this kernel changes the copied values).
 template <typename Real>
 __global__ void k_abc(Real *__restrict__ u0, const i64 *__restrict__ bna, const int8_t *__restrict__ Q,
-                      const Real *__restrict__ u2ba, i64 i0, i64 n, Real l) {
+                      const Real *__restrict__ u2ba, i64 i0, i64 n, Real l, const uint8_t *__restrict__ zf) {
    typedef Ops<Real> O;
    const i64 i = i0 + (i64)blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= i0 + n) return;
@@ -160,7 +166,15 @@ __global__ void k_abc(Real *__restrict__ u0, const i64 *__restrict__ bna, const 
    const i64 ib = bna[i];
    const Real num = O::add(u0[ib], O::mul(lQ, u2ba[i]));
    const double den = __dadd_rn(1.0, (double)lQ);
-   u0[ib] = (Real)__ddiv_rn((double)num, den);
+   const Real v = (Real)__ddiv_rn((double)num, den);
+   u0[ib] = v;
+   if (zf) {
+      const unsigned f = zf[i];
+      if (f & 1u) u0[ib - 1] = u0[ib + 1];
+      if (f & 2u) u0[ib + 1] = u0[ib - 1];
+      if (f & 4u) u0[ib - 2] = v;
+      if (f & 8u) u0[ib + 2] = v;
+   }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -28,7 +28,23 @@ struct VoxArgs {
    int *tidx;
    unsigned short *cut;
    unsigned char *fl;
+   // compaction (vox_scene.py:246-279, 343-366): the boundary points of every voxel's interior, voxel by voxel, ascending in a voxel
+   long long *count;      // [Nvox]
+   const long long *off;  // [Nvox + 1]
+   long long *o_bn;
+   unsigned char *o_adj;  // [Nb][NN], 1 = link open
+   int *o_tidx;
+   double *o_ndist;
 };
+
+// cut links of point p of a voxel if it is a boundary point of the voxel's interior, else 0; a point lying on the surface has every
+// link cut (vox_scene.py:244)
+__device__ __forceinline__ unsigned vox_selected(const int NN, const int p, const long long sx, const long long sy, const long long sz,
+                                                 const unsigned short *cut, const unsigned char *fl) {
+   const long long iz = p % sz, iy = (p / sz) % sy, ix = p / (sz * sy);
+   if (ix < 1 || ix > sx - 2 || iy < 1 || iy > sy - 2 || iz < 1 || iz > sz - 2) return 0u;
+   return (fl[p] & 2u) ? (1u << NN) - 1u : (unsigned)cut[p];
+}
 
 __global__ void __launch_bounds__(256) k_vox_calc_adj(const VoxArgs a) {
    const long long vi = blockIdx.x;
@@ -91,6 +107,50 @@ __global__ void __launch_bounds__(256) k_vox_calc_adj(const VoxArgs a) {
             if (hd < ndist[p]) ndist[p] = hd, tidx[p] = ti;
          }
       }
+   }
+   // how many boundary points this voxel contributes
+   __shared__ int s_cnt;
+   if (threadIdx.x == 0) s_cnt = 0;
+   __syncthreads();
+   int cnt = 0;
+   for (int p = threadIdx.x; p < np; p += blockDim.x) cnt += vox_selected(a.NN, p, sx, sy, sz, cut, fl) != 0u;
+   if (cnt) atomicAdd(&s_cnt, cnt);
+   __syncthreads();
+   if (threadIdx.x == 0) a.count[vi] = s_cnt;
+}
+
+// second pass: the boundary points of voxel vi go to rows off[vi].. of the result, in ascending point order
+__global__ void __launch_bounds__(256) k_vox_emit(const VoxArgs a) {
+   const long long vi = blockIdx.x;
+   const long long sx = a.vox_shape[3 * vi], sy = a.vox_shape[3 * vi + 1], sz = a.vox_shape[3 * vi + 2];
+   const long long gx0 = a.vox_start[3 * vi], gy0 = a.vox_start[3 * vi + 1], gz0 = a.vox_start[3 * vi + 2];
+   const int np = (int)(sx * sy * sz);
+   const long long base = a.pt_off[vi];
+   if (a.off[vi + 1] == a.off[vi]) return;
+   __shared__ int wsum[8];
+   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+   long long run = a.off[vi];
+   for (int p0 = 0; p0 < np; p0 += 256) {
+      const int p = p0 + threadIdx.x;
+      const unsigned cu = p < np ? vox_selected(a.NN, p, sx, sy, sz, a.cut + base, a.fl + base) : 0u;
+      const unsigned m = __ballot_sync(0xffffffffu, cu != 0u);
+      if (lane == 0) wsum[w] = __popc(m);
+      __syncthreads();
+      int before = 0, total = 0;
+      for (int j = 0; j < 8; j++) {
+         before += j < w ? wsum[j] : 0;
+         total += wsum[j];
+      }
+      if (cu) {
+         const long long r = run + before + __popc(m & ((1u << lane) - 1u));
+         const long long iz = p % sz, iy = (p / sz) % sy, ix = p / (sz * sy);
+         a.o_bn[r] = ((gx0 + ix) * a.Ny + (gy0 + iy)) * a.Nz + (gz0 + iz);
+         for (int k = 0; k < a.NN; k++) a.o_adj[r * a.NN + k] = (cu >> k) & 1u ? 0 : 1;
+         a.o_tidx[r] = a.tidx[base + p];
+         a.o_ndist[r] = a.ndist[base + p];
+      }
+      run += total;
+      __syncthreads();
    }
 }
 

@@ -82,6 +82,11 @@ def test_full_state_bit_exact_from_noise(name, precision):
                     # the outer halo layer is scratch: the fused step mirrors it when a value is written,
                     # the reference before it is read, so only the nodes 1..N-2 are comparable
                     a, b = a[1:-1, 1:-1, 1:-1], b[1:-1, 1:-1, 1:-1]
+                elif e.stat("zflip"):
+                    # the unfused step whose shell kernel writes the z halos of the NEW state (k_abc `zf`): those two layers are ahead
+                    # of the reference's, which mirrors them at the start of the next step; everything else, halo rows and planes
+                    # included, is comparable
+                    a, b = a[:, :, 1:-1], b[:, :, 1:-1]
                 assert np.array_equal(a, b), f"{name} p{precision} ak={ak} fuse={fuse} svc={svc} grid{which}: {np.abs(a - b).max():.3e}"
             v, g = e.read_boundary_state()
             vo, go = o.read_boundary_state()
