@@ -107,12 +107,14 @@ int pffdtd_peer_connect(pffdtd_engine *e, const void *blob_lo, const void *blob_
  * rigid-boundary nodes and the z faces of the absorbing shell from shared memory, -1 = the layout's default [7-point: on where the
  * grid allows it; 13-point: off]), "fd_bulk" (1 = the branch kernel moves its state with TMA bulk copies [0]), "svc_cap"
  * (tile-planes with more boundary nodes than this leave them to the list kernel [64, at most 192 minus two per tile row]), "abc_overlap" (1 = the absorbing-shell kernel runs beside the boundary kernels when no
- * boundary / source node lies on the shell [default]). */
+ * boundary / source node lies on the shell [default]), "zflip" (1 = in the unfused step the absorbing-shell kernel also writes the z
+ * halos of the new state, so the next step's mirror pass needs no z kernel; only where no boundary / source node sits at z = 2 or
+ * Nz-3 and the shell list is the canonical one [default]). */
 int pffdtd_set_option(pffdtd_engine *e, const char *key, int64_t value);
 /* Counters/timers: "launches", "steps", "air_ms" / "air_launches_timed" (CUDA-event time of the air launches
  * since reset, with profile_air), "timer_start" / "timer_stop_ms" (device stopwatch on the engine's stream),
  * "fused", "mirror_pairs", "air_kernel", "air_cfg" / "air_lanes_z" (tile configuration in use: 32, 16 or 8 lanes of a warp along z),
- * "abc_disjoint", "Nzp", "energy", "svc" (service-warp lists in use), "svc_entries", "nb_left" (boundary nodes left to k_rigid). */
+ * "abc_disjoint", "Nzp", "energy", "svc" (service-warp lists in use), "svc_entries", "nb_left" (boundary nodes left to k_rigid), "zflip" (the unfused step writes the z halos in k_abc). */
 int pffdtd_get_stat(pffdtd_engine *e, const char *key, double *out);
 int pffdtd_reset_stats(pffdtd_engine *e);
 
