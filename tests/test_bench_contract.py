@@ -94,6 +94,8 @@ def test_bench_line_has_the_contract_keys(monkeypatch, capsys, workload):
     r = line["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and "traffic" in r
     assert r["bytes_per_node"] == 12.125
+    # the step's required traffic with the lossy boundary nodes' branch state counted (16 B per branch + 30 B per node, fp32)
+    assert r["boundary_state_bytes_per_step"] > 0 and r["whole_step_frac_with_boundary_state"] > r["whole_step_frac"] > 0
     e = line["e2e"]
     assert e["unit"] == "Gvox/s" and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     c = line["cpu_baseline"]
