@@ -227,7 +227,7 @@ typedef struct pffdtd_vox_desc {
    const double *eab, *ebc, *eca;           /* [Ntris][3] outward unit edge normals */
 } pffdtd_vox_desc;
 typedef struct pffdtd_vox pffdtd_vox; /* opaque: the result of one run */
-int pffdtd_vox_run(const pffdtd_vox_desc *d, int device, pffdtd_vox **out);
+int pffdtd_vox_run(const pffdtd_vox_desc *d, int device, pffdtd_vox **out); /* env PFFDTD_VOX_TIMING=1: phase times on stderr */
 int64_t pffdtd_vox_count(const pffdtd_vox *r); /* boundary nodes found */
 /* bn_ixyz[Nb] (voxel by voxel in the reference's order, ascending inside a voxel), adj[Nb][NN] (1 = link open), tidx[Nb] (nearest
  * triangle), ndist[Nb] (its hit distance) */

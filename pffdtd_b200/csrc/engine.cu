@@ -1988,6 +1988,16 @@ extern "C" int pffdtd_vox_run(const pffdtd_vox_desc *d, int device, pffdtd_vox *
    CU(cudaGetDeviceCount(&ndev));
    if (device < 0 || device >= ndev) return fail(PFFDTD_ECUDA, "no CUDA device %d (%d visible)", device, ndev);
    CU(cudaSetDevice(device));
+   // PFFDTD_VOX_TIMING=1: wall time of the phases on stderr (diagnostic; adds device synchronisations)
+   const bool timing = getenv("PFFDTD_VOX_TIMING") != nullptr;
+   auto t_last = std::chrono::steady_clock::now();
+   auto lap = [&](const char *what) {
+      if (!timing) return;
+      cudaDeviceSynchronize();
+      const auto now = std::chrono::steady_clock::now();
+      fprintf(stderr, "[pffdtd_vox_run] %-34s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+      t_last = now;
+   };
    std::vector<void *> dev;
    auto freeall = [&]() {
       for (void *p : dev) cudaFree(p);
@@ -2036,6 +2046,7 @@ extern "C" int pffdtd_vox_run(const pffdtd_vox_desc *d, int device, pffdtd_vox *
       freeall();
       return fail(PFFDTD_ECUDA, "voxeliser: device allocation / upload failed: %s", cudaGetErrorString(cudaGetLastError()));
    }
+   lap("allocations + uploads");
    a.ndist = (double *)p_nd, a.tidx = (int *)p_ti, a.cut = (unsigned short *)p_cu, a.fl = (unsigned char *)p_fl;
    a.count = (long long *)p_cnt, a.off = (const long long *)p_off;
    pffdtd_vox *R = new pffdtd_vox();
@@ -2046,6 +2057,7 @@ extern "C" int pffdtd_vox_run(const pffdtd_vox_desc *d, int device, pffdtd_vox *
       // reference's order (voxel by voxel, ascending inside a voxel: vox_scene.py:246-279, 343-366)
       pf::k_vox_calc_adj<<<(unsigned)d->Nvox, 256>>>(a);
       ce = cudaGetLastError();
+      lap("k_vox_calc_adj");
       std::vector<long long> cnt((size_t)d->Nvox), off((size_t)d->Nvox + 1, 0);
       if (ce == cudaSuccess) ce = cudaMemcpy(cnt.data(), a.count, cnt.size() * 8, cudaMemcpyDeviceToHost);
       if (ce == cudaSuccess) {
@@ -2053,6 +2065,7 @@ extern "C" int pffdtd_vox_run(const pffdtd_vox_desc *d, int device, pffdtd_vox *
          ce = cudaMemcpy((void *)a.off, off.data(), off.size() * 8, cudaMemcpyHostToDevice);
       }
       const size_t nb = (size_t)off[(size_t)d->Nvox];
+      lap("counts -> offsets");
       if (ce == cudaSuccess && nb) {
          const void *o1 = nullptr, *o2 = nullptr, *o3 = nullptr, *o4 = nullptr;
          if (up(nullptr, nb * 8, &o1) | up(nullptr, nb * (size_t)d->NN, &o2) | up(nullptr, nb * 4, &o3) | up(nullptr, nb * 8, &o4)) {
@@ -2062,6 +2075,7 @@ extern "C" int pffdtd_vox_run(const pffdtd_vox_desc *d, int device, pffdtd_vox *
             a.o_bn = (long long *)o1, a.o_adj = (unsigned char *)o2, a.o_tidx = (int *)o3, a.o_ndist = (double *)o4;
             pf::k_vox_emit<<<(unsigned)d->Nvox, 256>>>(a);
             ce = cudaGetLastError();
+            lap("result allocation + k_vox_emit");
             R->bn.resize(nb), R->adj.resize(nb * (size_t)d->NN), R->tidx.resize(nb), R->ndist.resize(nb);
             if (ce == cudaSuccess) ce = cudaMemcpy(R->bn.data(), a.o_bn, nb * 8, cudaMemcpyDeviceToHost);
             if (ce == cudaSuccess) ce = cudaMemcpy(R->adj.data(), a.o_adj, nb * (size_t)d->NN, cudaMemcpyDeviceToHost);
@@ -2070,7 +2084,9 @@ extern "C" int pffdtd_vox_run(const pffdtd_vox_desc *d, int device, pffdtd_vox *
          }
       }
    }
+   lap("results to the host");
    freeall();
+   lap("cudaFree");
    if (ce != cudaSuccess) {
       delete R;
       return fail(PFFDTD_ECUDA, "voxeliser kernel: %s", cudaGetErrorString(ce));
