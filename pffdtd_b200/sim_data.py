@@ -73,14 +73,21 @@ def abc_nodes(Nx, Ny, Nz, fcc_flag, ix_range=None):
         iyf = IY
     lin = iyf * Nz + IZ
     par = (IY + IZ) & 1
+    # a plane's selection depends on ix only through "is it an x face" and (FCC) the parity of ix: four patterns, made on demand
+    pattern = {}
+
+    def plane(qx, odd):
+        if (qx, odd) not in pattern:
+            sel = (Qyz + qx) > 0
+            if fcc_flag > 0:
+                sel &= ((par + odd) & 1) == 0
+            pattern[(qx, odd)] = (lin[sel], (Qyz[sel] + qx).astype(np.int8))
+        return pattern[(qx, odd)]
     idx_parts, q_parts = [], []
     for ix in range(lo, hi):
-        qx = 1 if (ix == 1 or ix == Nx - 2) else 0
-        sel = (Qyz + qx) > 0
-        if fcc_flag > 0:
-            sel &= ((par + ix) & 1) == 0
-        idx_parts.append(ix * Nz * Ny + lin[sel])
-        q_parts.append((Qyz[sel] + qx).astype(np.int8))
+        l, q = plane(1 if (ix == 1 or ix == Nx - 2) else 0, ix & 1 if fcc_flag > 0 else 0)
+        idx_parts.append(ix * Nz * Ny + l)
+        q_parts.append(q)
     if idx_parts:
         bna = np.concatenate(idx_parts)
         Q = np.concatenate(q_parts)
